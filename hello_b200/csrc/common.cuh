@@ -1,0 +1,43 @@
+// Shared declarations for the hello_moe CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "hello_moe is written for sm_100a (B200) only"
+#endif
+
+namespace hello {
+
+// One convolution (or linear) layer, weights already weight-norm folded.
+struct ConvDesc {
+    int cin, cout, k, stride, pad, relu;
+    const float* w;     // device: conv [k*cin][cout] (row = tap*cin + ci); linear [cout][cin]
+    const float* b;     // device: [cout]
+    int out_len(int lin) const { return (lin + 2 * pad - k) / stride + 1; }
+};
+
+enum LayerKind { KIND_CONV = 0, KIND_MAXPOOL = 1, KIND_RES = 2, KIND_GAP_LINEAR = 3 };
+
+struct LayerDesc {
+    int kind;
+    int has_shortcut;
+    ConvDesc a, b, s;   // conv: a; maxpool: a.k/a.stride; res: a, b, (s); gap_linear: a
+};
+
+// Where the activations of a layer's input live: element (item n, position p, channel c) is at
+// base[n*sn + p*sl + c*sc]; `is_u8` selects uint8 vs fp32 elements.
+struct ActView {
+    const void* base;
+    long long sn, sl, sc;
+    int len, ch;
+    bool is_u8;
+};
+
+static inline ActView view_cl(const float* p, int len, int ch) {  // channel-last fp32 [n][len][ch]
+    ActView v;
+    v.base = p; v.sn = (long long)len * ch; v.sl = ch; v.sc = 1; v.len = len; v.ch = ch; v.is_u8 = false;
+    return v;
+}
+
+}  // namespace hello

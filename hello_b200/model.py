@@ -1,0 +1,373 @@
+"""Host side of the B200 MoE forward: the reference's two call signatures on top of the C ABI.
+
+  * ``MoEAttentionB200.forward(tensors, numAllelesPerSite, numReadsPerAllele, reference_segments, *args)``
+    -- same arguments and return convention as ``MoEAttention.forward``
+    (reference: python/MixtureOfExpertsAdvanced.py:161-252), the batched call ``WrapperForDataParallel`` makes
+    (python/MixtureOfExpertsDNNFast.py:128-134);
+  * ``MoEMergedWrapperB200(featureDict, segment)`` -- same as ``MoEMergedWrapperAdvanced.forward`` (:520-589),
+    the per-site call of python/caller_calling.py:651-652, with ``.eval()`` and ``.providePredictions``.
+
+PyTorch is used for device memory, streams and host<->device copies only; all arithmetic runs in
+libhello_moe.so (hand-written sm_100a CUDA).  There is no CPU path: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, arch, weights
+from .synth import Pileups, pair_offsets
+
+
+def _csr(counts) -> torch.Tensor:
+    counts = np.asarray(counts, dtype=np.int64)
+    if counts.ndim != 1 or (counts < 1).any():
+        raise ValueError("every CSR slot must hold at least one row (reduceSlots requires it)")
+    off = np.zeros(counts.size + 1, dtype=np.int64)
+    np.cumsum(counts, out=off[1:])
+    if off[-1] >= 2 ** 31:
+        raise ValueError("CSR offsets exceed int32")
+    return torch.from_numpy(off.astype(np.int32))
+
+
+@dataclass
+class DeviceBatch:
+    """A ragged batch resident on the GPU, in the layout hello_moe_forward takes."""
+    reads: Tuple[torch.Tensor, ...]            # uint8, device
+    layout: int
+    allele_read_off_h: Tuple[torch.Tensor, ...]
+    allele_read_off_d: Tuple[torch.Tensor, ...]
+    site_allele_off_h: torch.Tensor
+    site_allele_off_d: torch.Tensor
+    pair_off_h: torch.Tensor
+    pair_off_d: torch.Tensor
+    ref_onehot: Optional[torch.Tensor] = None  # fp32 [S, L, 5], device
+    allele_rank: Optional[torch.Tensor] = None  # int32 [A], device
+
+    @property
+    def n_sites(self) -> int:
+        return self.site_allele_off_h.numel() - 1
+
+    @property
+    def n_alleles(self) -> int:
+        return int(self.site_allele_off_h[-1])
+
+    @property
+    def n_pairs(self) -> int:
+        return int(self.pair_off_h[-1])
+
+    def input_bytes(self) -> int:
+        n = sum(r.numel() for r in self.reads)
+        n += sum(o.numel() * 4 for o in self.allele_read_off_h) + self.site_allele_off_h.numel() * 4
+        n += self.pair_off_h.numel() * 8
+        if self.ref_onehot is not None:
+            n += self.ref_onehot.numel() * 4
+        return n
+
+    @staticmethod
+    def from_host(reads: Sequence[torch.Tensor], layout: int, allele_read_off: Sequence[torch.Tensor],
+                  site_allele_off: torch.Tensor, ref_onehot: Optional[torch.Tensor], device,
+                  allele_rank: Optional[torch.Tensor] = None, non_blocking: bool = True) -> "DeviceBatch":
+        dev = torch.device(device)
+        pair_off = pair_offsets(site_allele_off)
+        up = lambda t: t.to(dev, non_blocking=non_blocking)
+        return DeviceBatch(
+            reads=tuple(up(r.contiguous()) for r in reads), layout=layout,
+            allele_read_off_h=tuple(o.contiguous() for o in allele_read_off),
+            allele_read_off_d=tuple(up(o.contiguous()) for o in allele_read_off),
+            site_allele_off_h=site_allele_off.contiguous(), site_allele_off_d=up(site_allele_off.contiguous()),
+            pair_off_h=pair_off, pair_off_d=up(pair_off),
+            ref_onehot=up(ref_onehot.contiguous().float()) if ref_onehot is not None else None,
+            allele_rank=up(allele_rank.contiguous()) if allele_rank is not None else None)
+
+    @staticmethod
+    def from_pileups(pl: Pileups, device, need_ref: bool = True) -> "DeviceBatch":
+        return DeviceBatch.from_host(pl.reads, _lib.LAYOUT_RLC, pl.allele_read_off, pl.site_allele_off,
+                                     pl.ref_onehot if need_ref else None, device)
+
+
+@dataclass
+class BatchResult:
+    logits: torch.Tensor       # [3, A]
+    meta: torch.Tensor         # [S, 3]
+    pair_prob: torch.Tensor    # [4, P]   mixed, P_e0, P_e1, P_e2
+    pair_mix64: torch.Tensor   # [P]      float64 re-mix (prepareVcf.py:154-162)
+    best_pair: torch.Tensor    # [S, 2]
+    best_prob: torch.Tensor    # [S]
+    pair_off: torch.Tensor     # [S+1] host
+
+    def output_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob))
+
+
+class MoEEngine:
+    """Owns one hello_moe handle (weights on one GPU) plus its workspace."""
+
+    def __init__(self, cfg: arch.ModelConfig, params: Dict[str, torch.Tensor], device="cuda:0",
+                 precision: str = "fp32", workspace_bytes: int = 4 << 30, max_chunk_sites: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.HelloMoEError("hello_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.HelloMoEError("hello_b200 runs on CUDA devices only")
+        self.precision = precision
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        blob = weights.pack_blob(cfg, params)
+        c = _lib.HelloCfg()
+        c.struct_size = C.sizeof(_lib.HelloCfg)
+        c.n_tech = len(cfg.read_cin)
+        for t, ch in enumerate(cfg.read_cin):
+            c.read_channels[t] = ch
+        for e in range(3):
+            c.xattn_present[e] = int(cfg.xattn_present[e])
+        c.has_combiners = int(cfg.combiners)
+        c.meta_kind = {None: _lib.META_NONE, "meta_convolver": _lib.META_SITE,
+                       "meta_convolver_ref": _lib.META_REF}[cfg.meta]
+        c.feature_length = arch.FEATURE_LENGTH
+        c.precision = _lib.PRECISIONS[precision]
+        c.max_chunk_sites = max_chunk_sites
+        handle = C.c_void_p()
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        rc = self.lib.hello_moe_create(buf, len(blob), C.byref(c), index, C.byref(handle))
+        if rc != 0:
+            raise _lib.HelloMoEError("hello_moe_create failed (%d): %s" % (
+                rc, self.lib.hello_moe_last_error(None).decode()))
+        self.handle = handle
+        self.workspace_cap = int(workspace_bytes)
+        self._ws: Optional[torch.Tensor] = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.hello_moe_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing ---------------------------------------------------------------------------------------------
+    def launch_count(self) -> int:
+        return int(self.lib.hello_moe_launch_count(self.handle))
+
+    def workspace_bytes(self, n_reads0: int, n_reads1: int, n_alleles: int, n_sites: int) -> int:
+        return int(self.lib.hello_moe_workspace_bytes(self.handle, n_reads0, n_reads1, n_alleles, n_sites))
+
+    def _workspace(self, need: int) -> torch.Tensor:
+        want = min(max(need, 1 << 20), self.workspace_cap)
+        if self._ws is None or self._ws.numel() < want:
+            self._ws = None
+            self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise _lib.HelloMoEError("%s failed (%d): %s" % (what, rc,
+                                                            self.lib.hello_moe_last_error(self.handle).decode()))
+
+    def alloc_result(self, b: DeviceBatch) -> BatchResult:
+        dev, A, S, P = self.device, b.n_alleles, b.n_sites, b.n_pairs
+        return BatchResult(
+            logits=torch.empty((3, A), dtype=torch.float32, device=dev),
+            meta=torch.empty((S, 3), dtype=torch.float32, device=dev),
+            pair_prob=torch.empty((4, P), dtype=torch.float32, device=dev),
+            pair_mix64=torch.empty((P,), dtype=torch.float64, device=dev),
+            best_pair=torch.empty((S, 2), dtype=torch.int32, device=dev),
+            best_prob=torch.empty((S,), dtype=torch.float32, device=dev),
+            pair_off=b.pair_off_h)
+
+    def run(self, b: DeviceBatch, out: Optional[BatchResult] = None) -> BatchResult:
+        """Enqueue the forward of a device-resident batch on the current stream (asynchronous)."""
+        n_tech = len(self.cfg.read_cin)
+        if len(b.reads) < n_tech:
+            raise ValueError("model needs %d technologies, batch has %d" % (n_tech, len(b.reads)))
+        if self.cfg.meta == "meta_convolver_ref" and b.ref_onehot is None:
+            raise ValueError("this model gates on the reference segment; reference_segments is required")
+        out = out or self.alloc_result(b)
+        hb = _lib.HelloBatch()
+        hb.n_sites, hb.n_alleles = b.n_sites, b.n_alleles
+        hb.input_layout = b.layout
+        nr = [0, 0]
+        for t in range(n_tech):
+            r = b.reads[t]
+            ch = self.cfg.read_cin[t]
+            if r.dtype != torch.uint8 or r.device != self.device or not r.is_contiguous():
+                raise ValueError("reads must be contiguous uint8 tensors on %s" % self.device)
+            want = (arch.FEATURE_LENGTH, ch) if b.layout == _lib.LAYOUT_RLC else (ch, arch.FEATURE_LENGTH)
+            if tuple(r.shape[1:]) != want:
+                raise ValueError("technology %d reads have shape %s, expected [R, %d, %d]" % (
+                    t, tuple(r.shape), want[0], want[1]))
+            nr[t] = r.shape[0]
+            hb.n_reads[t] = r.shape[0]
+            hb.d_reads[t] = r.data_ptr()
+            hb.d_allele_read_off[t] = b.allele_read_off_d[t].data_ptr()
+            hb.h_allele_read_off[t] = b.allele_read_off_h[t].data_ptr()
+            if b.allele_read_off_h[t].numel() != b.n_alleles + 1:
+                raise ValueError("allele_read_off has the wrong length")
+        hb.d_site_allele_off = b.site_allele_off_d.data_ptr()
+        hb.h_site_allele_off = b.site_allele_off_h.data_ptr()
+        hb.d_ref_onehot = b.ref_onehot.data_ptr() if b.ref_onehot is not None else None
+        hb.d_allele_rank = b.allele_rank.data_ptr() if b.allele_rank is not None else None
+        hb.d_pair_off = b.pair_off_d.data_ptr()
+        hr = _lib.HelloResult()
+        hr.d_logits, hr.d_meta = out.logits.data_ptr(), out.meta.data_ptr()
+        hr.d_pair_prob, hr.d_pair_mix64 = out.pair_prob.data_ptr(), out.pair_mix64.data_ptr()
+        hr.d_best_pair, hr.d_best_prob = out.best_pair.data_ptr(), out.best_prob.data_ptr()
+        ws = self._workspace(self.workspace_bytes(nr[0], nr[1], b.n_alleles, b.n_sites))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.hello_moe_forward(self.handle, C.byref(hb), C.byref(hr), ws.data_ptr(), ws.numel(),
+                                            C.c_void_p(stream))
+        self._check(rc, "hello_moe_forward")
+        return out
+
+    def run_net(self, net: str, x: torch.Tensor, layout: int = _lib.LAYOUT_RLC) -> torch.Tensor:
+        """Test hook: one sub-network on `x` (uint8 reads, or fp32 channel-last [n, L, C])."""
+        nid = weights.NET_IDS[net]
+        x = x.contiguous().to(self.device)
+        n = x.shape[0]
+        is_read = nid in (0, 1)
+        lin = arch.FEATURE_LENGTH if is_read else x.shape[1]
+        layers = self.cfg.networks()[net]
+        co, lo = arch.net_out_shape(layers, lin)
+        out = torch.empty((n, lo, co), dtype=torch.float32, device=self.device)
+        ws = self._workspace(1 << 30)
+        oc, ol = C.c_int32(), C.c_int32()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.hello_moe_run_net(self.handle, nid, x.data_ptr(), n, lin, layout, out.data_ptr(),
+                                            C.byref(oc), C.byref(ol), ws.data_ptr(), ws.numel(), C.c_void_p(stream))
+        self._check(rc, "hello_moe_run_net")
+        assert (oc.value, ol.value) == (co, lo), ((oc.value, ol.value), (co, lo))
+        return out
+
+
+def _as_uint8(t: torch.Tensor) -> torch.Tensor:
+    """The reference feeds bytes as floats (``tensors[0].float()``, :162); the kernels take the bytes."""
+    if t.dtype == torch.uint8:
+        return t
+    u = t.to(torch.uint8)
+    if not torch.equal(u.to(t.dtype), t):
+        raise ValueError("read feature tensors must hold integers in [0, 255] (the C++ encoder's byte codes)")
+    return u
+
+
+class MoEAttentionB200:
+    """Drop-in for ``MoEAttention``: same ``forward`` signature and return convention, computed on the GPU."""
+
+    def __init__(self, cfg: arch.ModelConfig, params: Dict[str, torch.Tensor], device="cuda:0",
+                 precision: str = "fp32", **engine_kwargs):
+        self.cfg = cfg
+        self.engine = MoEEngine(cfg, params, device, precision, **engine_kwargs)
+        self.meta = object() if cfg.meta is not None else None   # wrapper tests `moeMerged.meta is not None`
+        self.last_result: Optional[BatchResult] = None
+
+    @classmethod
+    def from_state_dict(cls, state_dict, **kw) -> "MoEAttentionB200":
+        sd = {k: v for k, v in state_dict.items() if not k.endswith(".weight")}
+        return cls(weights.cfg_from_state_dict(sd), sd, **kw)
+
+    @classmethod
+    def from_reference_module(cls, moe_attention, **kw) -> "MoEAttentionB200":
+        """Build from a live reference ``MoEAttention`` (e.g. ``torch.load(...).moeMerged``)."""
+        return cls.from_state_dict(moe_attention.state_dict(), **kw)
+
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = False):
+        if mode:
+            raise NotImplementedError("hello_b200 implements the inference forward only")
+        return self
+
+    def make_batch(self, tensors, numAllelesPerSite, numReadsPerAllele, reference_segments) -> DeviceBatch:
+        n_tech = len(self.cfg.read_cin)
+        reads, offs = [], []
+        for t in range(n_tech):
+            if tensors[t] is None or numReadsPerAllele[t] is None:
+                raise ValueError("hybrid model called without technology %d tensors" % t)
+            reads.append(_as_uint8(tensors[t]))
+            offs.append(_csr(numReadsPerAllele[t]))
+        napS = numAllelesPerSite.tolist() if torch.is_tensor(numAllelesPerSite) else list(numAllelesPerSite)
+        sao = _csr(napS)
+        A = int(sao[-1])
+        for t in range(n_tech):
+            if offs[t].numel() != A + 1 or int(offs[t][-1]) != reads[t].shape[0]:
+                raise ValueError("numReadsPerAllele[%d] does not match tensors / numAllelesPerSite" % t)
+        ref = reference_segments if self.cfg.meta == "meta_convolver_ref" else None
+        if self.cfg.meta == "meta_convolver_ref" and ref is None:
+            raise ValueError("reference_segments is required by this model")
+        return DeviceBatch.from_host(reads, _lib.LAYOUT_RCL, offs, sao, ref, self.engine.device)
+
+    def forward(self, tensors, numAllelesPerSite, numReadsPerAllele, reference_segments=None, *args, **kwargs):
+        in_dev = tensors[0].device
+        batch = self.make_batch(tensors, numAllelesPerSite, numReadsPerAllele, reference_segments)
+        res = self.engine.run(batch)
+        self.last_result = res
+        A = batch.n_alleles
+        logits = res.logits.to(in_dev)
+        if self.cfg.returns_meta:
+            return [logits[e].reshape(A, 1) for e in range(3)], res.meta.to(in_dev)
+        head = 0 if self.cfg.xattn_present[0] else 2
+        return logits[head].reshape(A, 1)
+
+    __call__ = forward
+
+
+class MoEMergedWrapperB200:
+    """Drop-in for ``MoEMergedWrapperAdvanced``: ``network(featureDict, segment)`` for one site."""
+
+    def __init__(self, moeMerged: MoEAttentionB200, providePredictions: bool = False):
+        self.moeMerged = moeMerged
+        self.providePredictions = providePredictions
+
+    def eval(self):
+        return self
+
+    def forward(self, featureDict, segment):
+        cfg = self.moeMerged.cfg
+        eng = self.moeMerged.engine
+        alleles = list(featureDict.keys())
+        n_tech = len(cfg.read_cin)
+        reads, offs = [], []
+        for t in range(n_tech):
+            parts = [featureDict[a][t] for a in alleles]
+            if any(p is None for p in parts):
+                raise ValueError("hybrid model called without technology %d tensors" % t)
+            offs.append(_csr([p.shape[0] for p in parts]))
+            reads.append(_as_uint8(torch.cat(parts, dim=0)))          # stays [r, L, C]: no transpose needed
+        sao = _csr([len(alleles)])
+        # tie-break of the reference's sort is on the allele strings (caller_calling.py:702-705)
+        order = sorted(range(len(alleles)), key=lambda i: alleles[i])
+        rank = torch.empty(len(alleles), dtype=torch.int32)
+        for r, i in enumerate(order):
+            rank[i] = r
+        ref = segment if cfg.meta == "meta_convolver_ref" else None
+        batch = DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, offs, sao, ref, eng.device, allele_rank=rank)
+        res = eng.run(batch)
+        self.moeMerged.last_result = res
+        pp = res.pair_prob.cpu()
+        meta = res.meta[0].cpu()
+        n = len(alleles)
+        keys = [(alleles[i], alleles[j]) for i in range(n) for j in range(i, n)]
+        dicts = [{k: pp[row, q] for q, k in enumerate(keys)} for row in range(4)]
+        self.last_call = (keys[self._pair_index(n, res.best_pair[0].tolist())], float(res.best_prob[0]))
+        if self.providePredictions:
+            return tuple(dicts) + (meta,)
+        return dicts[0]
+
+    @staticmethod
+    def _pair_index(n: int, ij) -> int:
+        i, j = ij
+        return i * n - i * (i - 1) // 2 + (j - i)
+
+    __call__ = forward

@@ -1,0 +1,197 @@
+"""Parameters of a HELLO MoE model: naming, deterministic init, weight-norm folding and the packed blob.
+
+Parameter names are the reference's ``state_dict`` keys for ``MoEAttention``
+(python/MixtureOfExpertsAdvanced.py:104-115; layers built by NNTools.Network, python/NNTools.py:633-657;
+weight-normed layers hold ``weight_g``/``weight_v``/``bias`` under ``.conv1d`` / ``.linear``,
+python/NNTools.py:780-799), so a real ``.wrapper.dnn`` state dict drops straight in.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+from . import arch
+
+NET_IDS = {
+    "read_convolver0": 0, "read_convolver1": 1, "compressor0": 2, "compressor1": 3,
+    "xattn0": 4, "xattn1": 5, "xattn2": 6, "combiner0": 7, "combiner1": 8, "meta": 9,
+}
+N_NET_SLOTS = 10
+
+KIND_CONV, KIND_MAXPOOL, KIND_RES, KIND_GAP_LINEAR = 0, 1, 2, 3
+BLOB_MAGIC = b"HELLOB2\0"
+BLOB_VERSION = 1
+_HEADER_BYTES = 128
+_REC_INTS = 32
+
+
+def conv_keys(net: str, layers) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """[(key prefix, v-shape, kind)] for every parametrised layer, in reference registration order."""
+    out = []
+    for slot, layer in arch.with_slots(layers):
+        base = "%s.network.%d" % (net, slot)
+        if isinstance(layer, arch.Conv):
+            out.append((base + ".conv1d", (layer.cout, layer.cin, layer.k), "conv"))
+        elif isinstance(layer, arch.Res):
+            a, b, s = layer.conv_a, layer.conv_b, layer.conv_s
+            out.append((base + ".ffNetwork.network.0.conv1d", (a.cout, a.cin, a.k), "conv"))
+            out.append((base + ".ffNetwork.network.3.conv1d", (b.cout, b.cin, b.k), "conv"))
+            if s is not None:
+                out.append((base + ".shNetwork.network.0.conv1d", (s.cout, s.cin, s.k), "conv"))
+        elif isinstance(layer, arch.GapLinear):
+            out.append(("%s.network.%d.linear" % (net, slot + 3), (layer.cout, layer.cin), "linear"))
+    return out
+
+
+def param_shapes(cfg: arch.ModelConfig) -> Dict[str, Tuple[int, ...]]:
+    """name -> shape for the whole model, mirroring MoEAttention.state_dict()."""
+    shapes = {}
+    for net, layers in cfg.networks().items():
+        for prefix, vshape, _ in conv_keys(net, layers):
+            shapes[prefix + ".bias"] = (vshape[0],)
+            shapes[prefix + ".weight_g"] = (vshape[0],) + (1,) * (len(vshape) - 1)
+            shapes[prefix + ".weight_v"] = vshape
+    return shapes
+
+
+def init_params(cfg: arch.ModelConfig, seed: int = 13) -> Dict[str, torch.Tensor]:
+    """Random-init weights of the named architecture (BASELINE.json: the shipped blobs are git-lfs pointers).
+
+    Machine-independent (numpy PCG64, float64 -> float32) so the same weights exist in this container, where the
+    golden vectors are made with the reference, and on the GPU box.  Distribution mirrors torch's default
+    Conv1d/Linear init (uniform, bound 1/sqrt(fan_in)); the weight-norm gain g is |v| scaled by U(0.75, 1.25) so
+    that folding g*v/|v| is exercised with g != |v| as in a trained model.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    params = {}
+    for net, layers in cfg.networks().items():
+        for prefix, vshape, _ in conv_keys(net, layers):
+            fan_in = int(np.prod(vshape[1:]))
+            bound = 1.0 / np.sqrt(fan_in)
+            v = ((rng.random(vshape) * 2.0 - 1.0) * bound).astype(np.float32)
+            norm = np.sqrt((v.astype(np.float64) ** 2).reshape(vshape[0], -1).sum(axis=1))
+            g = (norm * (0.75 + 0.5 * rng.random(vshape[0]))).astype(np.float32)
+            b = ((rng.random(vshape[0]) * 2.0 - 1.0) * bound).astype(np.float32)
+            params[prefix + ".weight_v"] = torch.from_numpy(v)
+            params[prefix + ".weight_g"] = torch.from_numpy(g.reshape((vshape[0],) + (1,) * (len(vshape) - 1)))
+            params[prefix + ".bias"] = torch.from_numpy(b)
+    return params
+
+
+def params_digest(params: Dict[str, torch.Tensor]) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for k in sorted(params):
+        h.update(k.encode())
+        h.update(params[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def check_params(cfg: arch.ModelConfig, params: Dict[str, torch.Tensor]) -> None:
+    shapes = param_shapes(cfg)
+    missing = [k for k in shapes if k not in params]
+    if missing:
+        raise KeyError("missing parameters for %s: %s ..." % (cfg.name, missing[:4]))
+    for k, shp in shapes.items():
+        if tuple(params[k].shape) != shp:
+            raise ValueError("parameter %s has shape %s, expected %s" % (k, tuple(params[k].shape), shp))
+
+
+def fold_weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """w = g * v / |v|, norm over all dims but 0 -- torch.nn.utils.weight_norm(dim=0) as used by
+    NNTools.WeightNormedConv1d/Linear (python/NNTools.py:783-785, 794-796).  Done once at load."""
+    return torch._weight_norm(v.float(), g.float(), 0)
+
+
+def folded(params: Dict[str, torch.Tensor], prefix: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    if prefix + ".weight" in params and prefix + ".weight_v" not in params:
+        w = params[prefix + ".weight"].float()          # plain (non weight-normed) layer
+    else:
+        w = fold_weight_norm(params[prefix + ".weight_v"], params[prefix + ".weight_g"])
+    return w, params[prefix + ".bias"].float()
+
+
+def cfg_from_state_dict(params: Dict[str, torch.Tensor]) -> arch.ModelConfig:
+    """Recognise which reference config a MoEAttention state dict belongs to."""
+    for cfg in arch.CONFIGS.values():
+        shapes = param_shapes(cfg)
+        if set(shapes) == {k for k in params if not k.endswith(".weight")} or set(shapes) == set(params):
+            if all(tuple(params[k].shape) == s for k, s in shapes.items()):
+                return cfg
+    raise ValueError("state dict does not match any supported HELLO MoE configuration")
+
+
+class _BlobWriter:
+    def __init__(self):
+        self.floats: List[np.ndarray] = []
+        self.n = 0
+
+    def add(self, t: torch.Tensor) -> int:
+        a = t.detach().cpu().contiguous().numpy().astype(np.float32).ravel()
+        off = self.n
+        pad = (-a.size) % 4           # keep every tensor 16-byte aligned for float4 loads
+        self.floats.append(a)
+        if pad:
+            self.floats.append(np.zeros(pad, np.float32))
+        self.n += a.size + pad
+        return off
+
+
+def _conv_rec(conv: arch.Conv, params, prefix, bw: _BlobWriter) -> List[int]:
+    w, b = folded(params, prefix)                      # [cout, cin, k]
+    wt = w.permute(2, 1, 0).reshape(conv.k * conv.cin, conv.cout)   # row kk = tap*cin + ci, cout contiguous
+    return [conv.cin, conv.cout, conv.k, conv.stride, conv.pad, int(conv.relu), bw.add(wt), bw.add(b)]
+
+
+def pack_blob(cfg: arch.ModelConfig, params: Dict[str, torch.Tensor]) -> bytes:
+    """Serialise folded weights + layer tables for hello_moe_create (include/hello_moe.h).
+
+    Layout (little endian): 128-byte header | records (32 x int32 each) | fp32 data.
+      header: magic[8] u32 version u32 n_net_slots u64 rec_off u64 n_rec u64 data_off u64 n_floats
+              u32 first_rec[10] u32 n_rec[10]
+      record: kind, has_shortcut, conv_a[8], conv_b[8], conv_s[8], pad   with
+              conv = cin, cout, k, stride, pad, relu, w_off, b_off   (offsets in floats into the data section)
+      conv weights are stored transposed [k*cin, cout] (row = tap*cin + ci) for channel-last activations;
+      linear weights as [cout, cin].
+    """
+    check_params(cfg, params)
+    bw = _BlobWriter()
+    recs: List[List[int]] = []
+    first = [0] * N_NET_SLOTS
+    count = [0] * N_NET_SLOTS
+    zero8 = [0] * 8
+    for net, layers in cfg.networks().items():
+        nid = NET_IDS[net]
+        first[nid] = len(recs)
+        for slot, layer in arch.with_slots(layers):
+            base = "%s.network.%d" % (net, slot)
+            if isinstance(layer, arch.Front):
+                continue
+            if isinstance(layer, arch.Conv):
+                recs.append([KIND_CONV, 0] + _conv_rec(layer, params, base + ".conv1d", bw) + zero8 + zero8)
+            elif isinstance(layer, arch.MaxPool):
+                recs.append([KIND_MAXPOOL, 0] + [0, 0, layer.k, layer.stride, 0, 0, 0, 0] + zero8 + zero8)
+            elif isinstance(layer, arch.Res):
+                a = _conv_rec(layer.conv_a, params, base + ".ffNetwork.network.0.conv1d", bw)
+                b = _conv_rec(layer.conv_b, params, base + ".ffNetwork.network.3.conv1d", bw)
+                s = _conv_rec(layer.conv_s, params, base + ".shNetwork.network.0.conv1d", bw) \
+                    if layer.conv_shortcut else zero8
+                recs.append([KIND_RES, int(layer.conv_shortcut)] + a + b + s)
+            elif isinstance(layer, arch.GapLinear):
+                w, b = folded(params, "%s.network.%d.linear" % (net, slot + 3))
+                recs.append([KIND_GAP_LINEAR, 0] + [layer.cin, layer.cout, 1, 1, 0, 0, bw.add(w), bw.add(b)]
+                            + zero8 + zero8)
+        count[nid] = len(recs) - first[nid]
+    rec_arr = np.zeros((len(recs), _REC_INTS), np.int32)
+    for i, r in enumerate(recs):
+        rec_arr[i, :len(r)] = r
+    data = np.concatenate(bw.floats) if bw.floats else np.zeros(0, np.float32)
+    rec_off = _HEADER_BYTES
+    data_off = rec_off + rec_arr.nbytes
+    header = struct.pack("<8sIIQQQQ", BLOB_MAGIC, BLOB_VERSION, N_NET_SLOTS, rec_off, len(recs), data_off, data.size)
+    header += struct.pack("<%dI" % N_NET_SLOTS, *first) + struct.pack("<%dI" % N_NET_SLOTS, *count)
+    assert len(header) == _HEADER_BYTES, len(header)
+    return header + rec_arr.tobytes() + data.tobytes()

@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference/python).
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+For every supported configuration it
+  1. builds the reference model with ``create_moe_attention_model`` from the reference's own config module and
+     asserts that hello_b200/arch.py describes it exactly (same state_dict keys, order and shapes);
+  2. loads the deterministic weights of hello_b200.weights.init_params into it;
+  3. runs the reference's batched ``MoEAttention.forward`` and the per-site
+     ``MoEMergedWrapperAdvanced.forward`` (providePredictions=True) on small synthetic pileups;
+  4. stores inputs, outputs, the genotype call made with caller_calling.py's rule and a digest of the weights.
+One configuration per subprocess: the reference's architecture modules are mutable singletons.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import subprocess
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/python"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (n_sites, coverage, seed, uniform_bytes)
+    "single_tech": (8, 10, 101, False),
+    "single_tech_hp": (6, 8, 102, False),
+    "hybrid_no_ensemble": (6, 8, 103, False),
+    "hybrid_ensemble2": (6, 8, 104, False),
+    "hybrid_full": (6, 8, 105, False),
+    "hybrid_no_ensemble_wide": (3, 6, 106, False),
+    "single_tech_uniform": (4, 8, 107, True),
+}
+
+
+def run_case(case: str) -> None:
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)
+    import torch
+    torch.set_num_threads(1)
+    import MixtureOfExpertsAdvanced as M          # the reference
+    from hello_b200 import arch, weights, synth
+
+    name = case.replace("_uniform", "")
+    n_sites, cov, seed, uniform = CASES[case]
+    cfg = arch.CONFIGS[name]
+    mod = importlib.import_module(arch.REFERENCE_CONFIG_MODULE[name])
+    moe = M.create_moe_attention_model(mod.configDict).eval()
+    shapes = weights.param_shapes(cfg)
+    sd = moe.state_dict()
+    assert list(sd.keys()) == list(shapes.keys()), "arch.py does not describe the reference model"
+    for k in sd:
+        assert tuple(sd[k].shape) == shapes[k], k
+    f_read, f_allele, f_site = arch.flops_model(cfg)
+
+    params = weights.init_params(cfg, seed=13)
+    moe.load_state_dict(params)
+    pl = synth.make_pileups(n_sites, coverage=cov, channels=cfg.read_cin, seed=seed, uniform_bytes=uniform)
+    args = pl.forward_args()
+    with torch.no_grad():
+        res = moe(*args)
+    out = {
+        "digest": np.array(weights.params_digest(params)),
+        "torch_version": np.array(torch.__version__),
+        "site_allele_off": pl.site_allele_off.numpy(),
+        "ref_onehot_idx": pl.ref_onehot.argmax(-1).to(torch.uint8).numpy(),
+        "flops": np.array(list(f_read) + [f_allele, f_site], dtype=np.int64),
+    }
+    for t, r in enumerate(pl.reads):
+        out["reads%d" % t] = r.numpy()
+        out["allele_read_off%d" % t] = pl.allele_read_off[t].numpy()
+    if cfg.returns_meta:
+        experts, meta = res
+        out["logits"] = torch.stack([e.reshape(-1) for e in experts]).numpy()
+        out["meta"] = meta.numpy()
+    else:
+        out["logits"] = res.reshape(1, -1).numpy()
+
+    # per-site strict drop-in call, exactly as python/caller_calling.py:651-652, 702-705
+    net = M.createMoEFullMergedAdvancedModelWrapper(moe).eval()
+    net.providePredictions = True
+    mixed, experts, metas, best = [], [[], [], []], [], []
+    for s in range(pl.n_sites):
+        fd, seg = pl.site_feature_dict(s)
+        with torch.no_grad():
+            r = net(fd, seg)
+        keys = list(r[0].keys())
+        mixed += [float(r[0][k]) for k in keys]
+        for e in range(3):
+            experts[e] += [float(r[1 + e][k]) for k in keys]
+        metas.append(r[4].numpy())
+        top = sorted([(v, k) for k, v in r[0].items()], reverse=True)[0]
+        names = list(fd.keys())
+        best.append([names.index(top[1][0]), names.index(top[1][1])])
+    out["pair_mixed"] = np.array(mixed, np.float32)
+    out["pair_experts"] = np.array(experts, np.float32)
+    out["site_meta"] = np.stack(metas).astype(np.float32)
+    out["best_pair"] = np.array(best, np.int32)
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, case + ".npz"), **out)
+    print("%-28s sites %d alleles %d reads %s logits[%.3f, %.3f] -> %s.npz" % (
+        case, pl.n_sites, pl.n_alleles, [int(r.shape[0]) for r in pl.reads],
+        out["logits"].min(), out["logits"].max(), case))
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        run_case(sys.argv[1])
+    else:
+        env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+        for c in CASES:
+            subprocess.run([sys.executable, os.path.abspath(__file__), c], check=True, env=env)

@@ -1,0 +1,265 @@
+"""CUDA path (through the C ABI) against the CPU oracle and the reference-made golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, flat_result, load_golden, params_for
+from hello_b200 import arch, synth, weights
+
+pytestmark = pytest.mark.gpu
+
+# Floating-point tolerance (north_star: "max abs error <= 1e-3 in fp32 accumulate").  fp32 mode is plain fp32
+# FMA with a different summation order than oneDNN's, so it lands far inside that.
+TOL_LOGIT = {"fp32": 2e-4, "bf16x3": 1e-3}
+TOL_PROB = {"fp32": 5e-5, "bf16x3": 5e-4}
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from hello_b200 import model
+    return model
+
+
+_engines = {}
+
+
+def net_for(model, cfg, precision="fp32", **kw):
+    key = (cfg.name, precision, tuple(sorted(kw.items())))
+    if key not in _engines:
+        _engines[key] = model.MoEAttentionB200(cfg, params_for(cfg), device=DEV, precision=precision, **kw)
+    return _engines[key]
+
+
+def oracle_for(cfg):
+    from oracle import hello_oracle as O
+    return O.OracleModel(cfg, params_for(cfg))
+
+
+# ------------------------------------------------------------------------------------------------ sub-networks
+@pytest.mark.parametrize("name", ["single_tech", "single_tech_hp"])
+def test_read_convolver_per_read(gpu, name):
+    cfg = arch.CONFIGS[name]
+    pl = synth.make_pileups(5, coverage=9, channels=cfg.read_cin, seed=21)
+    net = net_for(gpu, cfg)
+    from hello_b200 import _lib
+    got_rlc = net.engine.run_net("read_convolver0", pl.reads[0], _lib.LAYOUT_RLC).cpu()
+    got_rcl = net.engine.run_net("read_convolver0", pl.reads[0].transpose(1, 2).contiguous(), _lib.LAYOUT_RCL).cpu()
+    ref = oracle_for(cfg).read_features(pl.reads[0].transpose(1, 2))            # [R, 64, 36]
+    assert got_rlc.shape == (pl.reads[0].shape[0], 36, 64)
+    assert torch.equal(got_rlc, got_rcl), "the two input layouts must give identical results"
+    err = (got_rlc.transpose(1, 2) - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item() / 100), err
+
+
+@pytest.mark.parametrize("net_name,shape", [("compressor0", (7, 36, 64)), ("xattn0", (7, 18, 128))])
+def test_head_networks(gpu, net_name, shape):
+    cfg = arch.CONFIGS["single_tech"]
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(shape, generator=g) * 40).float()
+    got = net_for(gpu, cfg).engine.run_net(net_name, x).cpu()
+    ref = oracle_for(cfg).nets[net_name](x.transpose(1, 2))
+    if ref.dim() == 3:
+        ref = ref.transpose(1, 2)
+    else:
+        got = got.reshape(ref.shape)
+    scale = max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() < 2e-5 * scale
+
+
+def test_combiner_and_meta_networks(gpu):
+    cfg = arch.CONFIGS["hybrid_full"]
+    g = torch.Generator().manual_seed(6)
+    net, orc = net_for(gpu, cfg), oracle_for(cfg)
+    x = (torch.randn((5, 18, 256), generator=g) * 20).float()
+    got = net.engine.run_net("combiner0", x).cpu()
+    ref = orc.nets["combiner0"](x.transpose(1, 2)).transpose(1, 2)
+    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    s = (torch.randn((4, 18, 128), generator=g) * 20).float()
+    got = net.engine.run_net("meta", s).cpu().reshape(4, 3)
+    ref = orc.nets["meta"](s.transpose(1, 2))
+    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------ whole forward
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_forward_matches_reference_golden(gpu, case):
+    """Same weights + same inputs as the reference run that produced tests/golden/*.npz."""
+    cfg, pl, g = load_golden(case)
+    assert weights.params_digest(params_for(cfg)) == str(g["digest"])
+    net = net_for(gpu, cfg)
+    tensors, naps, nrpa, ref_seg = pl.forward_args()
+    res = net.forward(tensors, naps, nrpa, ref_seg)
+    logits, meta = flat_result(cfg, res)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=TOL_LOGIT["fp32"])
+    if meta is not None:
+        np.testing.assert_allclose(meta.numpy(), g["meta"], rtol=0, atol=TOL_PROB["fp32"])
+    r = net.last_result
+    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], rtol=0, atol=TOL_PROB["fp32"])
+    np.testing.assert_allclose(r.pair_prob[1:].cpu().numpy(), g["pair_experts"], rtol=0, atol=TOL_PROB["fp32"])
+    np.testing.assert_allclose(r.meta.cpu().numpy(), g["site_meta"], rtol=0, atol=TOL_PROB["fp32"])
+    # float64 re-mix of prepareVcf.py
+    mix64 = (g["pair_experts"].astype(np.float64) *
+             np.repeat(g["site_meta"].astype(np.float64), np.diff(r.pair_off.numpy()), axis=0).T).sum(0)
+    np.testing.assert_allclose(r.pair_mix64.cpu().numpy(), mix64, rtol=0, atol=TOL_PROB["fp32"])
+    # genotype call: bit-exact wherever the reference's own top-2 margin exceeds the posterior tolerance
+    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB["fp32"])
+
+
+def check_calls(result, ref_mixed, ref_best, tol):
+    off = result.pair_off.numpy()
+    got = result.best_pair.cpu().numpy()
+    n_tight = 0
+    for s in range(len(off) - 1):
+        probs = np.sort(ref_mixed[off[s]:off[s + 1]])[::-1]
+        margin = probs[0] - probs[1] if probs.size > 1 else np.inf
+        if margin > 2 * tol:
+            assert tuple(got[s]) == tuple(ref_best[s]), (s, got[s], ref_best[s], probs[:3])
+        else:
+            n_tight += 1
+    return n_tight
+
+
+@pytest.mark.parametrize("name", ["single_tech", "hybrid_ensemble2", "hybrid_full", "hybrid_no_ensemble"])
+def test_forward_matches_oracle_seeded(gpu, name):
+    from oracle import hello_oracle as O
+    cfg = arch.CONFIGS[name]
+    pl = synth.make_pileups(24, coverage=14, channels=cfg.read_cin, seed=77)
+    net = net_for(gpu, cfg)
+    res = net.forward(*pl.forward_args())
+    ref = oracle_for(cfg).forward(*pl.forward_args())
+    lg, mg = flat_result(cfg, res)
+    lr, mr = flat_result(cfg, ref)
+    assert (lg - lr).abs().max().item() < TOL_LOGIT["fp32"]
+    if mr is not None:
+        assert (mg - mr).abs().max().item() < TOL_PROB["fp32"]
+    post = O.batched_posteriors(cfg, ref, pl.num_alleles_per_site())
+    mixed = torch.cat([p[0] for p in post]).numpy()
+    best = np.array([p[3] for p in post], np.int32)
+    r = net.last_result
+    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=TOL_PROB["fp32"])
+    check_calls(r, mixed, best, TOL_PROB["fp32"])
+    np.testing.assert_allclose(r.best_prob.cpu().numpy(), np.array([p[4] for p in post], np.float32), rtol=0,
+                               atol=TOL_PROB["fp32"])
+
+
+def test_strict_drop_in_wrapper_call(gpu):
+    """network(featureDict, segment) with providePredictions, as python/caller_calling.py:651-652 calls it."""
+    from oracle import hello_oracle as O
+    for name in ("single_tech", "hybrid_full"):
+        cfg = arch.CONFIGS[name]
+        pl = synth.make_pileups(4, coverage=8, channels=cfg.read_cin, seed=9)
+        network = gpu.MoEMergedWrapperB200(net_for(gpu, cfg)).eval()
+        network.providePredictions = True
+        orc = oracle_for(cfg)
+        for s in range(pl.n_sites):
+            fd, seg = pl.site_feature_dict(s, allele_names=["T", "AC", "A", "G"][:len(pl.site_feature_dict(s)[0])])
+            with torch.no_grad():
+                got = network(fd, seg)
+            ref = O.wrapper_forward(orc, fd, seg, provide_predictions=True)
+            assert len(got) == 5
+            for dg, dr in zip(got[:4], ref[:4]):
+                assert list(dg.keys()) == list(dr.keys())
+                for k in dg:
+                    assert dg[k].dim() == 0 and abs(float(dg[k]) - float(dr[k])) < TOL_PROB["fp32"]
+            assert (got[4] - ref[4]).abs().max().item() < TOL_PROB["fp32"]
+            key, value, _ = O.call_genotype(ref[0])
+            vals = sorted((float(v) for v in ref[0].values()), reverse=True)
+            if len(vals) == 1 or vals[0] - vals[1] > 2 * TOL_PROB["fp32"]:
+                assert network.last_call[0] == key
+        network.providePredictions = False
+        assert isinstance(network(fd, seg), dict)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_chunking_does_not_change_results(gpu):
+    cfg = arch.CONFIGS["single_tech"]
+    pl = synth.make_pileups(40, coverage=10, channels=cfg.read_cin, seed=31)
+    whole = net_for(gpu, cfg)
+    res_a = whole.forward(*pl.forward_args())
+    ra = whole.last_result
+    tiny = net_for(gpu, cfg, max_chunk_sites=7)
+    res_b = tiny.forward(*pl.forward_args())
+    rb = tiny.last_result
+    assert torch.equal(res_a, res_b)
+    assert torch.equal(ra.pair_prob, rb.pair_prob) and torch.equal(ra.best_pair, rb.best_pair)
+    small_ws = net_for(gpu, cfg, workspace_bytes=48 << 20)
+    res_c = small_ws.forward(*pl.forward_args())
+    assert torch.equal(res_a, res_c)
+
+
+def test_ragged_edges(gpu):
+    """One read / one allele sites, a many-allele site, an all-zero technology row."""
+    from oracle import hello_oracle as O
+    cfg = arch.CONFIGS["hybrid_ensemble2"]
+    g = torch.Generator().manual_seed(3)
+    n_alleles = [1, 6, 1, 2]
+    nr0 = [1, 3, 1, 2, 1, 4, 2, 1, 5, 1]
+    nr1 = [1, 1, 2, 1, 1, 1, 3, 1, 1, 2]
+    r0 = torch.randint(0, 256, (sum(nr0), 150, 6), generator=g, dtype=torch.uint8)
+    r1 = torch.randint(0, 256, (sum(nr1), 150, 6), generator=g, dtype=torch.uint8)
+    r1[0] = 0                                              # technology without support: one all-zero row
+    onehot = torch.nn.functional.one_hot(torch.randint(0, 5, (4, 150), generator=g), 5).float()
+    tensors = (r0.transpose(1, 2), r1.transpose(1, 2))
+    net = net_for(gpu, cfg)
+    res = net.forward(tensors, n_alleles, (nr0, nr1), onehot)
+    ref = oracle_for(cfg).forward(tensors, n_alleles, (nr0, nr1), onehot)
+    lg, mg = flat_result(cfg, res)
+    lr, mr = flat_result(cfg, ref)
+    scale = max(1.0, lr.abs().max().item())
+    assert (lg - lr).abs().max().item() < TOL_LOGIT["fp32"] * scale
+    assert (mg - mr).abs().max().item() < TOL_PROB["fp32"]
+    assert net.last_result.pair_prob.shape[1] == 1 + 21 + 1 + 3
+    post = O.batched_posteriors(cfg, ref, n_alleles)
+    mixed = torch.cat([p[0] for p in post]).numpy()
+    np.testing.assert_allclose(net.last_result.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=TOL_PROB["fp32"])
+
+
+def test_float_inputs_and_errors(gpu):
+    cfg = arch.CONFIGS["single_tech"]
+    pl = synth.make_pileups(3, coverage=6, channels=cfg.read_cin, seed=4)
+    net = net_for(gpu, cfg)
+    tensors, naps, nrpa, ref = pl.forward_args()
+    a = net.forward(tensors, naps, nrpa, ref)
+    b = net.forward((tensors[0].float(), None), naps, nrpa, ref)       # the reference passes floats
+    assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        net.forward((tensors[0].float() + 0.5, None), naps, nrpa, ref)
+    with pytest.raises(ValueError):
+        net.forward(tensors, naps, ([0] + nrpa[0][1:], None), ref)      # empty slot
+    with pytest.raises(ValueError):
+        net.forward(tensors, naps[:-1], nrpa, ref)                      # inconsistent CSR
+
+
+def test_tie_break_uses_allele_rank(gpu):
+    """Two identical alleles give exactly equal pair probabilities; the reference's sort picks the greatest key."""
+    cfg = arch.CONFIGS["single_tech"]
+    g = torch.Generator().manual_seed(8)
+    row = torch.randint(0, 256, (3, 150, 6), generator=g, dtype=torch.uint8).float()
+    network = gpu.MoEMergedWrapperB200(net_for(gpu, cfg))
+    for names in (["A", "C"], ["C", "A"]):
+        fd = {names[0]: (row.clone(), None), names[1]: (row.clone(), None)}
+        out = network(fd, torch.zeros(1, 150, 5))
+        assert float(out[(names[0], names[0])]) == float(out[(names[1], names[1])])
+        from oracle import hello_oracle as O
+        key, _, _ = O.call_genotype(out)
+        assert network.last_call[0] == key
+
+
+# ------------------------------------------------------------------------------------------------ properties
+def test_read_order_and_site_independence(gpu):
+    """Sites are independent: a site's result does not depend on which other sites share the batch."""
+    cfg = arch.CONFIGS["single_tech"]
+    pl = synth.make_pileups(12, coverage=10, channels=cfg.read_cin, seed=55)
+    net = net_for(gpu, cfg)
+    full = net.forward(*pl.forward_args())
+    sao = pl.site_allele_off
+    aro = pl.allele_read_off[0]
+    for s in (0, 5, 11):
+        a0, a1 = int(sao[s]), int(sao[s + 1])
+        r0, r1 = int(aro[a0]), int(aro[a1])
+        sub = net.forward((pl.reads[0][r0:r1].transpose(1, 2), None), [a1 - a0],
+                          (torch.diff(aro[a0:a1 + 1]).tolist(), None), None)
+        assert torch.equal(sub, full[a0:a1])

@@ -1,0 +1,87 @@
+"""The CPU oracle against golden vectors produced by the unmodified reference (oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN_CASES, flat_result, load_golden, params_for
+from hello_b200 import arch, weights
+from oracle import hello_oracle as O
+
+# the oracle is bit-identical to the reference on the machine that made the fixtures; a different host CPU may
+# pick another oneDNN/ATen kernel, so allow fp32 reassociation noise
+TOL = 5e-5
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_weights_are_the_ones_the_reference_was_given(case):
+    cfg, _, g = load_golden(case)
+    assert weights.params_digest(params_for(cfg)) == str(g["digest"])
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_flops_model(case):
+    cfg, _, g = load_golden(case)
+    f_read, f_allele, f_site = arch.flops_model(cfg)
+    assert list(f_read) + [f_allele, f_site] == g["flops"].tolist()
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_batched_forward_matches_reference(case):
+    cfg, pl, g = load_golden(case)
+    torch.set_num_threads(1)
+    res = O.OracleModel(cfg, params_for(cfg)).forward(*pl.forward_args())
+    logits, meta = flat_result(cfg, res)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=TOL)
+    if meta is not None:
+        np.testing.assert_allclose(meta.numpy(), g["meta"], rtol=0, atol=TOL)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_per_site_wrapper_matches_reference(case):
+    cfg, pl, g = load_golden(case)
+    torch.set_num_threads(1)
+    model = O.OracleModel(cfg, params_for(cfg))
+    mixed, experts, metas, best = [], [[], [], []], [], []
+    for s in range(pl.n_sites):
+        fd, seg = pl.site_feature_dict(s)
+        r = O.wrapper_forward(model, fd, seg, provide_predictions=True)
+        keys = list(r[0].keys())
+        names = list(fd.keys())
+        assert keys == [(names[i], names[j]) for i, j in O.pair_list(len(names))]
+        mixed += [float(r[0][k]) for k in keys]
+        for e in range(3):
+            experts[e] += [float(r[1 + e][k]) for k in keys]
+        metas.append(r[4].numpy())
+        key, value, qual = O.call_genotype(r[0])
+        best.append([names.index(key[0]), names.index(key[1])])
+        assert 0 <= qual <= 80.0001
+    np.testing.assert_allclose(np.array(mixed, np.float32), g["pair_mixed"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(np.array(experts, np.float32), g["pair_experts"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(np.stack(metas), g["site_meta"], rtol=0, atol=TOL)
+    assert np.array_equal(np.array(best, np.int32), g["best_pair"])
+
+
+def test_batched_equals_per_site_tail():
+    cfg, pl, g = load_golden("hybrid_full")
+    res = O.OracleModel(cfg, params_for(cfg)).forward(*pl.forward_args())
+    post = O.batched_posteriors(cfg, res, pl.num_alleles_per_site())
+    mixed = torch.cat([p[0] for p in post]).numpy()
+    np.testing.assert_allclose(mixed, g["pair_mixed"], rtol=0, atol=TOL)
+
+
+def test_reduce_slots_is_a_segmented_sum():
+    d = torch.randn(11, 3, 5)
+    slots = [1, 4, 2, 1, 3]
+    out = O.reduce_slots(d, slots)
+    off = np.cumsum([0] + slots)
+    for g_, (a, b) in enumerate(zip(off[:-1], off[1:])):
+        torch.testing.assert_close(out[g_], d[a:b].sum(0), rtol=1e-5, atol=1e-5)
+
+
+def test_call_rule_tie_break_and_quality():
+    # equal values: the lexicographically greatest key wins (sorted(..., reverse=True)[0])
+    key, value, qual = O.call_genotype({("A", "A"): 0.25, ("A", "C"): 0.5, ("C", "C"): 0.5})
+    assert key == ("C", "C") and value == 0.5
+    key, value, qual = O.call_genotype({("A", "A"): 1.0})
+    assert abs(qual - 80.0) < 1e-6
+    assert O.remix_float64([[0.5], [0.25], [0.125]], [0.5, 0.25, 0.25]) == [0.5 * 0.5 + 0.25 * 0.25 + 0.125 * 0.25]
