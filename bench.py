@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Benchmark of the HELLO MoE forward on B200: candidate sites/sec through the batched forward (read convolver ->
+allele/site heads -> genotype posteriors + argmax), BASELINE.json config 2 ("Illumina 30x model on 1M synthetic
+sites, 1 B200") by default.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+One JSON line on stdout (rank 0).  `value` = sites/s with inputs resident in HBM; `e2e` = the same job through
+MoEEngine.forward_host with pinned HOST buffers (H2D of the pileups and D2H of the per-site results inside the
+timed region); `roofline` = the read-convolver stage (dominant kernel) timed with CUDA events by the library;
+`cpu_baseline` = the oracle port of the reference forward on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "candidate_sites_per_sec"
+WORKLOADS = {
+    # name: (model config, coverage, description)
+    "illumina_30x": ("single_tech", 30, "Illumina 30x single-technology model"),
+    "pacbio_hp_30x": ("single_tech_hp", 30, "PacBio 30x model with haplotag channel"),
+    "hybrid_no_ensemble_30x": ("hybrid_no_ensemble", 30, "hybrid Illumina+PacBio no_ensemble model"),
+    "hybrid_ensemble2_30x": ("hybrid_ensemble2", 30, "hybrid 2-expert gated model"),
+    "wgs_ragged_15_60x": ("single_tech", (15, 60), "ragged coverage 15x-60x sweep"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="illumina_30x", choices=sorted(WORKLOADS))
+    ap.add_argument("--sites", type=int, default=1_000_000, help="sites per GPU (weak scaling)")
+    ap.add_argument("--precision", default=os.environ.get("HELLO_PRECISION", "fp32"))
+    ap.add_argument("--workspace-gb", type=float, default=6.0)
+    ap.add_argument("--chunk-sites", type=int, default=0, help="cap on sites per internal chunk (0 = auto)")
+    ap.add_argument("--e2e-chunk-sites", type=int, default=32768)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sites", type=int, default=0, help="sites per CPU step (0 = 128 per worker)")
+    ap.add_argument("--cpu-workers", type=int, default=0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference forward on the host cores
+_W = {}
+
+
+def _cpu_worker_init(cfg_name):
+    import torch
+    torch.set_num_threads(1)                      # the reference runs 1 torch thread per worker process
+    from hello_b200 import arch, weights          # (python/caller_calling.py:39, python/call.py:26,30)
+    from oracle import hello_oracle as O
+    cfg = arch.CONFIGS[cfg_name]
+    _W["model"] = O.OracleModel(cfg, weights.init_params(cfg, seed=13))
+    _W["cfg"] = cfg
+    _W["O"] = O
+
+
+def _cpu_worker_run(task):
+    import torch
+    tensors, naps, nrpa, ref = task
+    model, cfg, O = _W["model"], _W["cfg"], _W["O"]
+    res = model.forward(tensors, naps, nrpa, ref)
+    post = O.batched_posteriors(cfg, res, naps)
+    return len(post)
+
+
+def _cpu_tasks(pl, cfg, batch_sites):
+    import torch
+    tasks = []
+    sao = pl.site_allele_off
+    for s0 in range(0, pl.n_sites, batch_sites):
+        s1 = min(pl.n_sites, s0 + batch_sites)
+        a0, a1 = int(sao[s0]), int(sao[s1])
+        tensors, nrpa = [], []
+        for t in range(len(cfg.read_cin)):
+            aro = pl.allele_read_off[t]
+            r0, r1 = int(aro[a0]), int(aro[a1])
+            tensors.append(pl.reads[t][r0:r1].transpose(1, 2).contiguous())
+            nrpa.append(torch.diff(aro[a0:a1 + 1]).tolist())
+        if len(tensors) == 1:
+            tensors.append(None)
+            nrpa.append(None)
+        tasks.append((tuple(tensors), torch.diff(sao[s0:s1 + 1]).tolist(), tuple(nrpa), pl.ref_onehot[s0:s1]))
+    return tasks
+
+
+def run_reference(args):
+    """Times the reference algorithm (oracle port: same torch-CPU ops, same per-worker threading model as
+    python/call.py's Pool of single-threaded callers) on `cpu_sites` sites per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from hello_b200 import arch, synth
+    cfg_name, cov, desc = WORKLOADS[args.workload]
+    cfg = arch.CONFIGS[cfg_name]
+    workers = args.cpu_workers or len(os.sched_getaffinity(0))
+    n_sites = args.cpu_sites or 128 * workers
+    pl = synth.make_pileups(n_sites, coverage=cov, channels=cfg.read_cin, seed=13)
+    tasks = _cpu_tasks(pl, cfg, 16)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers, initializer=_cpu_worker_init, initargs=(cfg_name,)) as pool:
+        def step():
+            return sum(pool.map(_cpu_worker_run, tasks, chunksize=1))
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(args.steps):
+            done += step()
+        dt = time.perf_counter() - t0
+    value = done / dt
+    sample = "%d synthetic %s sites per step (seed 13, CPU generator), 16-site calls, %d worker processes x 1 torch " \
+             "thread" % (n_sites, args.workload, workers)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model": cfg_name, "sites_per_step": n_sites, "coverage": cov},
+        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return line
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, "/tmp/hello_clocks_%d_%d.csv" % (os.getpid(), index)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       power_w_max=max(power), samples=len(sm))
+        return out
+
+
+def generate_on_device(cfg, cov, n_sites, device, seed, gen_chunk=16384):
+    """Synthetic pileups generated on the GPU in slices, concatenated into one resident batch."""
+    import torch
+    from hello_b200 import synth
+    reads = [[] for _ in cfg.read_cin]
+    rpa = [[] for _ in cfg.read_cin]
+    apS, refs = [], []
+    for i, s0 in enumerate(range(0, n_sites, gen_chunk)):
+        n = min(gen_chunk, n_sites - s0)
+        pl = synth.make_pileups(n, coverage=cov, channels=cfg.read_cin, seed=seed + 7919 * i, device=device)
+        for t in range(len(cfg.read_cin)):
+            reads[t].append(pl.reads[t])
+            rpa[t].append(torch.diff(pl.allele_read_off[t]))
+        apS.append(torch.diff(pl.site_allele_off))
+        if cfg.meta == "meta_convolver_ref":
+            refs.append(pl.ref_onehot)
+    def csr(parts):
+        c = torch.cat(parts).to(torch.int64)
+        off = torch.zeros(c.numel() + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(c, 0)
+        return off.to(torch.int32)
+    reads = tuple(torch.cat(r) for r in reads)
+    return reads, tuple(csr(r) for r in rpa), csr(apS), (torch.cat(refs) if refs else None)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hello_b200 import _lib, arch, model, weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this repo has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg_name, cov, desc = WORKLOADS[args.workload]
+    cfg = arch.CONFIGS[cfg_name]
+    params = weights.init_params(cfg, seed=13)
+    engine = model.MoEEngine(cfg, params, device=dev, precision=args.precision,
+                             workspace_bytes=int(args.workspace_gb * (1 << 30)), max_chunk_sites=args.chunk_sites)
+
+    reads, aro, sao, ref = generate_on_device(cfg, cov, args.sites, dev, seed=13 + 1000 * rank)
+    batch = model.DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, aro, sao, ref, dev)
+    result = engine.alloc_result(batch)
+    S, A = batch.n_sites, batch.n_alleles
+    R = [int(r.shape[0]) for r in reads]
+    input_gb = sum(r.numel() for r in reads) / 1e9
+    f_read, f_allele, f_site = arch.flops_model(cfg)
+    flops_read = sum(R[t] * f_read[t] for t in range(len(R)))
+    flops_step = flops_read + A * f_allele + S * f_site
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        engine.run(batch, result)
+    barrier()
+    engine.profile_enable(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = engine.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        engine.run(batch, result)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = engine.launch_count() - launches0
+    rc_ms, rc_regions = engine.profile_collect()
+    engine.profile_enable(False)
+    value = world * S * args.steps / (ms_total / 1e3)
+
+    # ---- e2e: host buffers, copies inside the timed region -------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hb = model.HostBatch([r.cpu() for r in reads], _lib.LAYOUT_RLC, aro, sao,
+                             ref.cpu() if ref is not None else None, pin=True)
+        del batch, reads
+        torch.cuda.empty_cache()
+        engine.forward_host(hb, args.e2e_chunk_sites)                       # warm-up (allocations, pinned outputs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = engine.forward_host(hb, args.e2e_chunk_sites)
+            torch.cuda.synchronize(dev)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * S * args.steps / dt, "unit": "sites/s", "h2d_bytes_per_step": hb.input_nbytes(),
+               "d2h_bytes_per_step": out.nbytes(), "api": "MoEEngine.forward_host (pinned host buffers, "
+               "%d-site chunks, copy/compute overlap on 2 streams)" % args.e2e_chunk_sites}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md, sustained)"
+    achieved = flops_read * args.steps / (rc_ms / 1e3) / 1e12 if rc_ms > 0 else None
+    roofline = {
+        "kernel": "read convolver stage (%s)" % ("readconv_tc" if args.precision != "fp32" else
+                                                "conv1d_fp32_kernel x19 + maxpool per chunk"),
+        "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+        "frac": (achieved / tensor_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "algorithmic_flops_per_read": list(f_read), "reads_per_step": R,
+        "stage_ms_per_step": rc_ms / max(args.steps, 1), "regions_per_step": rc_regions / max(args.steps, 1),
+        "stage_share_of_step": rc_ms / ms_total if ms_total > 0 else None,
+        "note": ("fp32 mode runs the convolutions on CUDA cores (FFMA); the fraction is quoted against the bf16 "
+                 "tensor-core peak the north star targets" if args.precision == "fp32" else
+                 "bf16x3 issues 3 MMAs per algorithmic MAC: ceiling = 1/3 of the tensor peak"),
+    }
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+               "--workload", args.workload]
+        try:
+            out_ = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, RANK="0"))
+            cpu_baseline = json.loads(out_.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as exc:  # report, never hide
+            cpu_baseline = {"error": repr(exc)[:200]}
+    line = {
+        "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "%s_%dk_sites_per_gpu" % (args.workload, args.sites // 1000), "model": cfg_name,
+                   "weights": "random-init (seed 13), shipped blobs are git-lfs pointers", "sites_per_gpu": S,
+                   "alleles_per_gpu": A, "reads_per_gpu": R, "coverage": cov, "precision": args.precision,
+                   "partition": "sites sharded across ranks, no data-path collective",
+                   "l2": "inputs (%.1f GB per step) are far larger than L2; no flush needed" % input_gb,
+                   "flops_per_step_per_gpu": flops_step},
+        "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,9 @@ struct hello_moe {
     int read_len = 0, read_ch = 0;   // read convolver output (36, 64)
     int comp_len = 0, comp_ch = 0;   // compressor output (18, 128)
     ReadConvTC* tc[2] = {nullptr, nullptr};
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;            // pairs (start, stop), created lazily
+    size_t ev_used = 0;
 };
 
 namespace {
@@ -273,6 +276,18 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
         // read convolver (architectures/read_convolver.py) on uint8 rows
         const uint8_t* reads = dry ? nullptr : in->d_reads[t] + (size_t)ck.r0[t] * L * C;
+        cudaEvent_t ev_stop = nullptr;
+        if (!dry && h->profile && nr > 0) {
+            if (h->ev_used + 2 > h->ev_pool.size()) {
+                cudaEvent_t a = nullptr, b = nullptr;
+                if (!run.check(cudaEventCreate(&a), "cudaEventCreate") || !run.check(cudaEventCreate(&b), "cudaEventCreate"))
+                    return false;
+                h->ev_pool.push_back(a); h->ev_pool.push_back(b);
+            }
+            if (!run.check(cudaEventRecord(h->ev_pool[h->ev_used], run.st), "cudaEventRecord")) return false;
+            ev_stop = h->ev_pool[h->ev_used + 1];
+            h->ev_used += 2;
+        }
         if (h->tc[t]) {
             if (!dry && nr > 0) {
                 cudaError_t e = readconv_tc_launch(h->tc[t], reads, nr, in->input_layout, r_feat, run.st);
@@ -285,6 +300,7 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
             if (!dry && in->input_layout == HELLO_LAYOUT_RCL) { v.sc = L; v.sl = 1; } else { v.sc = 1; v.sl = C; }
             if (!run.run_net(h->nets[NET_RC0 + t], v, nr, r_feat, nullptr)) return false;
         }
+        if (ev_stop && !run.check(cudaEventRecord(ev_stop, run.st), "cudaEventRecord")) return false;
         // reads -> alleles (reduceSlots, :163)
         if (!run.segsum(r_feat, a_feat, dry ? nullptr : in->d_allele_read_off[t] + ck.a0, na, (int)ck.r0[t], read_e))
             return false;
@@ -518,6 +534,7 @@ void hello_moe_destroy(hello_moe* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (int t = 0; t < 2; ++t) readconv_tc_destroy(h->tc[t]);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->d_weights) cudaFree(h->d_weights);
     delete h;
 }
@@ -528,6 +545,29 @@ size_t hello_moe_workspace_bytes(const hello_moe* h, int64_t n_reads0, int64_t n
                                  int64_t n_sites) {
     if (!h) return 0;
     return dry_bytes(const_cast<hello_moe*>(h), n_reads0, n_reads1, n_alleles, n_sites);
+}
+
+int hello_moe_profile_enable(hello_moe* h, int on) {
+    if (!h) return HELLO_ERR_ARG;
+    h->profile = on != 0;
+    if (!on) h->ev_used = 0;
+    return HELLO_OK;
+}
+
+int hello_moe_profile_collect(hello_moe* h, double* ms_read_conv, int64_t* n_regions) {
+    if (!h || !ms_read_conv || !n_regions) return HELLO_ERR_ARG;
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        cudaError_t e = cudaEventSynchronize(h->ev_pool[i + 1]);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]);
+        if (e != cudaSuccess) { h->err = std::string("profile_collect: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }
+        total += ms;
+    }
+    *ms_read_conv = total;
+    *n_regions = (int64_t)(h->ev_used / 2);
+    h->ev_used = 0;
+    return HELLO_OK;
 }
 
 int64_t hello_moe_launch_count(const hello_moe* h) { return h ? h->launches : 0; }

@@ -169,6 +169,16 @@ class MoEEngine:
             self._ws = torch.empty(want, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.hello_moe_profile_enable(self.handle, int(on)), "hello_moe_profile_enable")
+
+    def profile_collect(self):
+        """(milliseconds spent in the read-convolver stage, number of bracketed regions) since the last collect."""
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.lib.hello_moe_profile_collect(self.handle, C.byref(ms), C.byref(n)),
+                    "hello_moe_profile_collect")
+        return ms.value, n.value
+
     def _check(self, rc: int, what: str):
         if rc != 0:
             raise _lib.HelloMoEError("%s failed (%d): %s" % (what, rc,
@@ -185,7 +195,8 @@ class MoEEngine:
             best_prob=torch.empty((S,), dtype=torch.float32, device=dev),
             pair_off=b.pair_off_h)
 
-    def run(self, b: DeviceBatch, out: Optional[BatchResult] = None) -> BatchResult:
+    def run(self, b: DeviceBatch, out: Optional[BatchResult] = None,
+            workspace: Optional[torch.Tensor] = None) -> BatchResult:
         """Enqueue the forward of a device-resident batch on the current stream (asynchronous)."""
         n_tech = len(self.cfg.read_cin)
         if len(b.reads) < n_tech:
@@ -222,12 +233,49 @@ class MoEEngine:
         hr.d_logits, hr.d_meta = out.logits.data_ptr(), out.meta.data_ptr()
         hr.d_pair_prob, hr.d_pair_mix64 = out.pair_prob.data_ptr(), out.pair_mix64.data_ptr()
         hr.d_best_pair, hr.d_best_prob = out.best_pair.data_ptr(), out.best_prob.data_ptr()
-        ws = self._workspace(self.workspace_bytes(nr[0], nr[1], b.n_alleles, b.n_sites))
+        ws = workspace if workspace is not None else \
+            self._workspace(self.workspace_bytes(nr[0], nr[1], b.n_alleles, b.n_sites))
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             rc = self.lib.hello_moe_forward(self.handle, C.byref(hb), C.byref(hr), ws.data_ptr(), ws.numel(),
                                             C.c_void_p(stream))
         self._check(rc, "hello_moe_forward")
+        return out
+
+    def forward_host(self, hb: "HostBatch", chunk_sites: int = 65536) -> "HostResult":
+        """End-to-end call on HOST buffers: stream chunks of sites host->device, run them, bring the per-site
+        results back.  Two streams alternate so the copies of one chunk overlap the kernels of the previous one."""
+        if not hasattr(self, "_streams"):
+            self._streams = [torch.cuda.Stream(self.device) for _ in range(2)]
+            self._ws2 = [None, None]
+        out = hb.result_buffers()
+        S = hb.n_sites
+        main = torch.cuda.current_stream(self.device)
+        for st in self._streams:
+            st.wait_stream(main)
+        for i, s0 in enumerate(range(0, S, chunk_sites)):
+            s1 = min(S, s0 + chunk_sites)
+            st = self._streams[i % 2]
+            with torch.cuda.stream(st):
+                db, (a0, a1), (p0, p1) = hb.device_chunk(s0, s1, self.device)
+                need = self.workspace_bytes(db.reads[0].shape[0], db.reads[1].shape[0] if len(db.reads) > 1 else 0,
+                                            db.n_alleles, db.n_sites)
+                want = min(max(need, 1 << 20), self.workspace_cap)
+                if self._ws2[i % 2] is None or self._ws2[i % 2].numel() < want:
+                    self._ws2[i % 2] = None
+                    self._ws2[i % 2] = torch.empty(want, dtype=torch.uint8, device=self.device)
+                res = self.run(db, workspace=self._ws2[i % 2])
+                out.logits[:, a0:a1].copy_(res.logits, non_blocking=True)
+                out.meta[s0:s1].copy_(res.meta, non_blocking=True)
+                out.pair_prob[:, p0:p1].copy_(res.pair_prob, non_blocking=True)
+                out.pair_mix64[p0:p1].copy_(res.pair_mix64, non_blocking=True)
+                out.best_pair[s0:s1].copy_(res.best_pair, non_blocking=True)
+                out.best_prob[s0:s1].copy_(res.best_prob, non_blocking=True)
+                for t in (res.logits, res.meta, res.pair_prob, res.pair_mix64, res.best_pair, res.best_prob) + \
+                        db.reads + db.allele_read_off_d + (db.site_allele_off_d, db.pair_off_d):
+                    t.record_stream(st)
+        for st in self._streams:
+            main.wait_stream(st)
         return out
 
     def run_net(self, net: str, x: torch.Tensor, layout: int = _lib.LAYOUT_RLC) -> torch.Tensor:
@@ -249,6 +297,70 @@ class MoEEngine:
         self._check(rc, "hello_moe_run_net")
         assert (oc.value, ol.value) == (co, lo), ((oc.value, ol.value), (co, lo))
         return out
+
+
+@dataclass
+class HostResult:
+    """Per-site results in (pinned) host memory."""
+    logits: torch.Tensor
+    meta: torch.Tensor
+    pair_prob: torch.Tensor
+    pair_mix64: torch.Tensor
+    best_pair: torch.Tensor
+    best_prob: torch.Tensor
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob))
+
+
+class HostBatch:
+    """A ragged batch in HOST memory (pinned when possible) -- what a caller of the drop-in holds."""
+
+    def __init__(self, reads: Sequence[torch.Tensor], layout: int, allele_read_off: Sequence[torch.Tensor],
+                 site_allele_off: torch.Tensor, ref_onehot: Optional[torch.Tensor] = None, pin: bool = True):
+        pin_ = (lambda t: t if t.is_pinned() else t.pin_memory()) if pin else (lambda t: t)
+        self.reads = tuple(pin_(r.contiguous()) for r in reads)
+        self.layout = layout
+        self.allele_read_off = tuple(o.contiguous() for o in allele_read_off)
+        self.site_allele_off = site_allele_off.contiguous()
+        self.ref_onehot = pin_(ref_onehot.contiguous()) if ref_onehot is not None else None
+        self.pair_off = pair_offsets(self.site_allele_off)
+        self.pin = pin
+        self._out: Optional[HostResult] = None
+
+    @property
+    def n_sites(self) -> int:
+        return self.site_allele_off.numel() - 1
+
+    def input_nbytes(self) -> int:
+        n = sum(r.numel() for r in self.reads) + sum(o.numel() * 4 for o in self.allele_read_off)
+        n += self.site_allele_off.numel() * 4
+        if self.ref_onehot is not None:
+            n += self.ref_onehot.numel() * 4
+        return n
+
+    def result_buffers(self) -> HostResult:
+        if self._out is None:
+            A, S, P = int(self.site_allele_off[-1]), self.n_sites, int(self.pair_off[-1])
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=self.pin)
+            self._out = HostResult(mk((3, A), torch.float32), mk((S, 3), torch.float32), mk((4, P), torch.float32),
+                                   mk((P,), torch.float64), mk((S, 2), torch.int32), mk((S,), torch.float32))
+        return self._out
+
+    def device_chunk(self, s0: int, s1: int, device):
+        """Upload sites [s0, s1) (asynchronously on the current stream) with chunk-local CSR offsets."""
+        sao = self.site_allele_off
+        a0, a1 = int(sao[s0]), int(sao[s1])
+        reads, offs = [], []
+        for t, r in enumerate(self.reads):
+            aro = self.allele_read_off[t]
+            r0, r1 = int(aro[a0]), int(aro[a1])
+            reads.append(r[r0:r1])
+            offs.append(aro[a0:a1 + 1] - r0)
+        ref = self.ref_onehot[s0:s1] if self.ref_onehot is not None else None
+        db = DeviceBatch.from_host(reads, self.layout, offs, sao[s0:s1 + 1] - a0, ref, device)
+        return db, (a0, a1), (int(self.pair_off[s0]), int(self.pair_off[s1]))
 
 
 def _as_uint8(t: torch.Tensor) -> torch.Tensor:

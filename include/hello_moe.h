@@ -127,6 +127,12 @@ size_t hello_moe_workspace_bytes(const hello_moe* h, int64_t n_reads0, int64_t n
 int hello_moe_forward(hello_moe* h, const hello_batch* in, const hello_result* out, void* d_workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Stage timing (a measurement aid for bench.py): while enabled, forward() brackets the read-convolver stage of
+ * every chunk (the dominant kernel) with CUDA events on the launching stream. collect() waits for those events and
+ * returns the accumulated milliseconds and the number of bracketed regions since the previous collect. */
+int hello_moe_profile_enable(hello_moe* h, int on);
+int hello_moe_profile_collect(hello_moe* h, double* ms_read_conv, int64_t* n_regions);
+
 /* Number of kernel launches enqueued by this handle since creation (bench.py reports the delta). */
 int64_t hello_moe_launch_count(const hello_moe* h);
 
