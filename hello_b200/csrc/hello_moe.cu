@@ -49,6 +49,7 @@ struct hello_moe {
     hello_cfg cfg;
     int device = 0;
     float* d_weights = nullptr;
+    std::vector<float> h_weights;    // host copy of the folded fp32 weights (packed to bf16 by the tensor-core path)
     size_t n_floats = 0;
     std::vector<LayerDesc> nets[N_NETS];
     std::string err;
@@ -420,6 +421,8 @@ bool parse_blob(hello_moe* h, const void* blob, size_t nbytes, std::string& err)
         err = "cudaMemcpy(weights) failed"; return false;
     }
     h->n_floats = n_floats;
+    h->h_weights.resize(n_floats);
+    std::memcpy(h->h_weights.data(), p + data_off, n_floats * 4);
     auto conv_from = [&](const int32_t* r, ConvDesc* c) -> bool {
         c->cin = r[0]; c->cout = r[1]; c->k = r[2]; c->stride = r[3]; c->pad = r[4]; c->relu = r[5];
         if ((uint64_t)r[6] >= n_floats + 1 || (uint64_t)r[7] >= n_floats + 1) return false;
@@ -517,8 +520,8 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
     if (cfg->precision != HELLO_PREC_FP32) {
         for (int t = 0; t < cfg->n_tech; ++t) {
             std::string terr;
-            h->tc[t] = readconv_tc_create(h->nets[NET_RC0 + t], h->d_weights, cfg->read_channels[t],
-                                          cfg->feature_length, cfg->precision, terr);
+            h->tc[t] = readconv_tc_create(h->nets[NET_RC0 + t], h->d_weights, h->h_weights.data(),
+                                          cfg->read_channels[t], cfg->feature_length, cfg->precision, terr);
             if (!h->tc[t]) {
                 g_create_error = "hello_moe_create: tensor-core read convolver: " + terr;
                 hello_moe_destroy(h);
@@ -692,6 +695,21 @@ int hello_moe_run_net(hello_moe* h, int net_id, const void* d_in, int64_t n_item
     Runner::GapOut g{d_out, co, 0};
     run.run_net(net, v, n_items, gap ? nullptr : d_out, gap ? &g : nullptr);
     return run.status;
+}
+
+int hello_moe_readconv_debug(hello_moe* h, int tech, const uint8_t* d_reads, int64_t n_reads, int32_t input_layout,
+                             int32_t phase, float* d_out, float* d_dbg, void* stream) {
+    if (!h) return HELLO_ERR_ARG;
+    h->err.clear();
+    if (tech < 0 || tech > 1 || !h->tc[tech]) { h->err = "no tensor-core read convolver for this technology"; return HELLO_ERR_UNSUPPORTED; }
+    if (!d_reads || !d_out || n_reads < 0) { h->err = "bad buffers"; return HELLO_ERR_ARG; }
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess)
+        e = readconv_tc_launch(h->tc[tech], d_reads, n_reads, input_layout, d_out, static_cast<cudaStream_t>(stream),
+                               d_dbg, d_dbg ? phase : -1);
+    h->launches++;
+    if (e != cudaSuccess) { h->err = std::string("readconv_tc: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }
+    return HELLO_OK;
 }
 
 }  // extern "C"

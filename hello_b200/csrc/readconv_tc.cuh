@@ -1,20 +1,670 @@
-// Fused tcgen05 read convolver (placeholder interface; implementation lands with the tensor-core path).
+// Fused tcgen05 read convolver: the whole 19-convolution per-read stack of HELLO's read_convolver
+// (reference: python/architectures/read_convolver.py:9-144, run per read by MoEAttention.forward,
+// python/MixtureOfExpertsAdvanced.py:162) in ONE persistent kernel.  uint8 pileup rows go in, fp32 [R,36,64]
+// feature maps come out; nothing in between touches HBM.
+//
+// How a Conv1d becomes tensor-core work
+//   Activations live in shared memory channel-chunked: for every group of 8 channels one array of 16-byte rows
+//   (row = position, 8 bf16).  That is exactly the K-major "no swizzle" canonical operand layout of tcgen05.mma
+//   (core matrix = 8 rows x 16 B, contiguous), with SBO = 128 B and LBO = the distance between chunk arrays.
+//   Tap t of a k=3 convolution is then the SAME array read one row further down: the A descriptor of the MMA
+//   for tap t simply starts 16 bytes later.  One convolution = taps x (Cin/16) MMAs of shape 128 x Cout x 16
+//   accumulating into one TMEM tile; no im2col is ever materialised.
+//   Reads are packed back to back along M with a fixed pitch (160 / 80 / 40 rows for the three resolutions);
+//   the unused rows of each pitch are kept at zero and double as the zero padding of the pad=1 convolutions.
+//   Stride-2 layers (MaxPool1d(3,2), the stride-2 residual block) read an even/odd de-interleaved copy that the
+//   previous epilogue writes, which turns stride 2 back into unit row shifts.
+//
+// Pipeline (one CTA per SM, 11 warps)
+//   warps 0-3 / 4-7  epilogue of read group 0 / 1: TMEM -> registers (bias, ReLU, residual, max-pool), split to
+//                    bf16 hi (+lo), write the next layer's operand back to shared memory IN PLACE, keep the fp32
+//                    residual stream in TMEM.
+//   warps 8 / 9      MMA issuer of group 0 / 1: fully unrolled tcgen05.mma sequences (operand offsets are
+//                    immediates), one elected lane issues.  The tensor pipe works on one group while the CUDA
+//                    cores run the other group's epilogue.
+//   warp 10          one thread streams the weights of the next layer from L2 into a 2-slot ring with
+//                    cp.async.bulk (TMA unit) while the current layer computes.
+//   Precision: HELLO_PREC_BF16X3 splits activations and weights into bf16 hi+lo and issues hi*hi + hi*lo + lo*hi
+//   (fp32 accumulate) -> ~2^-17 relative error per product; HELLO_PREC_BF16 issues hi*hi only.
 #pragma once
+#include <algorithm>
+#include <cstring>
 #include <string>
 #include <vector>
+
+#include "../../include/hello_moe.h"
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace hello {
+namespace tc {
 
-struct ReadConvTC;
+constexpr int G = 6;                           // reads per group (two groups in flight per CTA)
+constexpr int P1 = 160, P2 = 80, P3 = 40;      // row pitch of one read at the three resolutions
+constexpr int ROWS1 = G * P1, ROWS2 = G * P2, ROWS3 = G * P3;
+constexpr int T1 = 8, T2 = 4, T3 = 2;          // 128-row MMA tiles per group
+constexpr int LIN = 150, LV1 = 148, LV2 = 146, LV3 = 71, LV4 = 36;   // valid lengths
+constexpr int LOUT = 36, COUT = 64;
+constexpr int N_PHASES = 17;
+constexpr int N_BIAS = 832;
 
-static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>&, const float*, int, int, int, std::string& err) {
-    err = "tensor-core read convolver not built in this revision; use HELLO_PREC_FP32";
-    return nullptr;
+// byte layout of one group's activation buffer (offsets relative to its base)
+constexpr uint32_t X_STRIDE = (ROWS1 + 8) * 16;   // layer-1 operand: X0[m] = x[m], X1[m] = x[m+1]  (8 ch, hi only)
+constexpr uint32_t A1_CH = (ROWS1 + 2) * 16;      // layer-1 output: 2 chunks, natural rows
+constexpr uint32_t A2_ARR = (ROWS2 + 2) * 16;     // layer-2 output: (chunk, parity) arrays, pitch 80
+constexpr uint32_t S2_CH = (ROWS2 + 2) * 16;      // 32-channel stage: 4 chunks, lead zero row
+constexpr uint32_t E3_ARR = (ROWS3 + 2) * 16;     // stage-2 output de-interleaved: (chunk, parity), pitch 40, lead row
+constexpr uint32_t S3_CH = (ROWS3 + 2) * 16;      // 64-channel stage: 8 chunks, lead zero row
+constexpr uint32_t XCHG_OFF = 61952;              // 16 x 32 floats for the max-pool row exchange
+constexpr uint32_t ACT_BYTES = 64000;
+constexpr uint32_t WSLOT_BYTES = 49152;
+
+constexpr uint32_t OFF_ACT = 0;
+constexpr uint32_t OFF_W = 2 * ACT_BYTES;
+constexpr uint32_t OFF_BIAS = OFF_W + 2 * WSLOT_BYTES;
+constexpr uint32_t OFF_BAR = OFF_BIAS + N_BIAS * 4;
+constexpr uint32_t OFF_TMEM = OFF_BAR + 8 * 8;
+constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(2 * A1_CH * 2 <= XCHG_OFF && 8 * A2_ARR <= XCHG_OFF && 8 * S2_CH <= XCHG_OFF &&
+              16 * E3_ARR <= XCHG_OFF && 16 * S3_CH <= XCHG_OFF && 2 * X_STRIDE <= XCHG_OFF, "activation layouts");
+
+// bias table (floats)
+constexpr int B_L1 = 0, B_L2 = 16, B_L3 = 32, B_S2 = 64, B_RCA = 256, B_RCS = 320, B_RCB = 384, B_S3 = 448;
+
+// Per layer phase: where its packed weights live and how many bytes the producer streams into a slot.
+struct TcParams {
+    uint32_t w_src[N_PHASES];
+    uint32_t w_bytes[N_PHASES];
+    const uint8_t* reads;
+    const uint8_t* weights;
+    const float* bias;
+    float* out;
+    float* dbg;
+    long long n_reads;
+    int n_items, channels, layout, dbg_phase;
+};
+
+// bytes of the bf16 "hi" weights of each phase kind (the "lo" copy follows at this offset in the slot)
+constexpr uint32_t WHI_L1 = 2 * 16 * 32, WHI_L2 = 3 * 16 * 32, WHI_L3 = 3 * 32 * 32, WHI_S2 = 6 * 32 * 32,
+                   WHI_RC = 8 * 64 * 32, WHI_S3 = 12 * 64 * 32;
+constexpr uint32_t RC_SHORTCUT_B_OFF = 6 * 64 * 32;
+
+enum { OUT_NAT = 0, OUT_EO = 1, OUT_GLOBAL = 2 };
+
+// ------------------------------------------------------------------------------------------------ device side
+template <int MODE>
+__device__ __forceinline__ void store_chunk8(uint8_t* p, uint32_t lo_delta, const float* v) {
+    uint32_t h[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = ptx::pack_bf16x2(v[2 * q], v[2 * q + 1]);
+    *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (MODE == 3) {
+        uint32_t l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float h0 = __uint_as_float(h[q] << 16), h1 = __uint_as_float(h[q] & 0xffff0000u);
+            l[q] = ptx::pack_bf16x2(v[2 * q] - h0, v[2 * q + 1] - h1);
+        }
+        *reinterpret_cast<uint4*>(p + lo_delta) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
 }
-static cudaError_t readconv_tc_launch(ReadConvTC*, const uint8_t*, long long, int, float*, cudaStream_t) {
-    return cudaErrorNotSupported;
+
+// uint8 pileup rows of one group -> layer-1 operand (two row-shifted copies, bf16, channels padded to 8)
+__device__ __forceinline__ void load_input(uint8_t* act, const uint8_t* __restrict__ reads, long long r0, int n_reads,
+                                           int C, int layout, int tid) {
+    for (int m = tid; m < ROWS1 + 8; m += 128) {
+        const int i = m / P1, p = m - i * P1;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (i < n_reads && p < LIN) {
+            const uint8_t* src = reads + (r0 + i) * (long long)(LIN * C);
+            uint32_t b[8];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+                uint32_t x = 0u;
+                if (ch < C) x = layout == HELLO_LAYOUT_RLC ? __ldg(src + p * C + ch) : __ldg(src + ch * LIN + p);
+                b[ch] = __float_as_uint((float)x) >> 16;          // 0..255 are exact in bf16
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = b[2 * q] | (b[2 * q + 1] << 16);
+        }
+        const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(act + (uint32_t)m * 16) = v;
+        if (m >= 1) *reinterpret_cast<uint4*>(act + X_STRIDE + (uint32_t)(m - 1) * 16) = v;
+    }
+    if (tid == 0) *reinterpret_cast<uint4*>(act + X_STRIDE + (uint32_t)(ROWS1 + 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
 }
-static void readconv_tc_destroy(ReadConvTC*) {}
+
+// Epilogue of one convolution for one group.  Thread = row (TMEM lane); loops over tiles and 32-column blocks.
+//   y = relu(acc + bias) [+ resid (+ bias2)], invalid rows forced to zero, written as the next operand.
+template <int MODE, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID, int OUT,
+          int LEAD>
+__device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, int d_stride, const float* bias,
+                                         const float* bias2, int n_reads, uint32_t out_stride, uint32_t out_lo,
+                                         float* __restrict__ gout, float* __restrict__ dbg, int wrow, int lane) {
+    constexpr int CB = N < 32 ? N : 32;
+    constexpr int ROWS = G * PITCH;
+    for (int tile = 0; tile < TILES; ++tile) {
+        const int m = tile * 128 + wrow + lane;
+        const int i = m / PITCH, p = m - i * PITCH;
+        const bool valid = (i < n_reads) && (p < LVALID);
+        const bool in_buf = m < ROWS;
+#pragma unroll
+        for (int cb = 0; cb < N / CB; ++cb) {
+            float v[CB];
+            float r[RESID ? CB : 1];
+            ptx::tmem_ld<CB>(tl + tile * d_stride + cb * CB, v);
+            if (RESID) ptx::tmem_ld<CB>(tl + 128 + tile * N + cb * CB, r);
+            ptx::tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                float x = fmaxf(v[c] + bias[cb * CB + c], 0.f);
+                if (RESID) x += RES_BIAS ? (r[c] + bias2[cb * CB + c]) : r[c];
+                v[c] = valid ? x : 0.f;
+            }
+            if (WRITE_RESID) ptx::tmem_st32(tl + 128 + tile * N + cb * CB, v);
+            if (dbg) {
+#pragma unroll
+                for (int c = 0; c < CB; ++c) dbg[m * 64 + cb * CB + c] = v[c];
+            }
+            if (OUT == OUT_GLOBAL) {
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(gout + ((long long)i * LOUT + p) * COUT + cb * CB);
+#pragma unroll
+                    for (int q = 0; q < CB / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                }
+            } else if (in_buf) {
+#pragma unroll
+                for (int q = 0; q < CB / 8; ++q) {
+                    const int c8 = cb * (CB / 8) + q;
+                    uint8_t* dst = OUT == OUT_NAT
+                                       ? act + c8 * out_stride + (uint32_t)(m + LEAD) * 16
+                                       : act + (c8 * 2 + (m & 1)) * out_stride + (uint32_t)((m >> 1) + LEAD) * 16;
+                    store_chunk8<MODE>(dst, out_lo, v + 8 * q);
+                }
+            }
+        }
+    }
+    if (LEAD && OUT != OUT_GLOBAL && wrow + lane == 0) {          // zero padding row in front of the first read
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        constexpr int ARRS = (N / 8) * (OUT == OUT_EO ? 2 : 1);
+#pragma unroll
+        for (int a = 0; a < ARRS; ++a) {
+            *reinterpret_cast<uint4*>(act + a * out_stride) = z;
+            if (MODE == 3) *reinterpret_cast<uint4*>(act + a * out_stride + out_lo) = z;
+        }
+    }
+    if (WRITE_RESID) ptx::tmem_wait_st();
+}
+
+// Epilogue of stem conv 3 fused with MaxPool1d(3,2): E[m] = conv(2p), O[m] = conv(2p+1) sit in two accumulators,
+// conv(2p+2) = E[m+1] comes from the neighbouring lane (shared-memory exchange across warp / tile borders).
+template <int MODE>
+__device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float* bias, int n_reads, int g, int wq,
+                                         int lane, float* __restrict__ dbg) {
+    float* xchg = reinterpret_cast<float*>(act + XCHG_OFF);
+    for (int tile = 0; tile < T2; ++tile) {
+        float e[32];
+        ptx::tmem_ld32(tl + tile * 64, e);
+        ptx::tmem_wait_ld();
+        if (lane == 0) {
+            float4* dst = reinterpret_cast<float4*>(xchg + (tile * 4 + wq) * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+        }
+    }
+    ptx::named_bar_sync(1 + g, 128);
+    for (int tile = T2 - 1; tile >= 0; --tile) {     // descending: the residual columns alias later tiles' accumulators
+        float e[32], o[32];
+        ptx::tmem_ld32(tl + tile * 64, e);
+        ptx::tmem_ld32(tl + tile * 64 + 32, o);
+        ptx::tmem_wait_ld();
+        const int m = tile * 128 + wq * 32 + lane;
+        const int i = m / P2, p = m - i * P2;
+        const bool valid = (i < n_reads) && (p < LV3);
+        const int nxt = tile * 4 + wq + 1;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            float e1 = __shfl_down_sync(0xffffffffu, e[c], 1);
+            if (lane == 31) e1 = nxt < 16 ? xchg[nxt * 32 + c] : e[c];
+            const float x = fmaxf(fmaxf(fmaxf(e[c], o[c]), e1) + bias[c], 0.f);
+            o[c] = valid ? x : 0.f;
+        }
+        ptx::tmem_st32(tl + 128 + tile * 32, o);
+        if (dbg) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) dbg[m * 64 + c] = o[c];
+        }
+        if (m < ROWS2) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                store_chunk8<MODE>(act + q * S2_CH + (uint32_t)(m + 1) * 16, 4 * S2_CH, o + 8 * q);
+        }
+    }
+    if (wq == 0 && lane == 0) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            *reinterpret_cast<uint4*>(act + a * S2_CH) = z;
+            if (MODE == 3) *reinterpret_cast<uint4*>(act + a * S2_CH + 4 * S2_CH) = z;
+        }
+    }
+    ptx::tmem_wait_st();
+}
+
+// All tcgen05.mma of one 128-row tile of one convolution, fully unrolled: every operand offset is an immediate,
+// so one MMA costs two integer adds plus the issue.  Runs on a converged warp with warp-uniform values.
+//   AO0..2  byte offset of the A operand of each tap (row shift / even-odd array selection)
+//   A_LBO   distance between 8-channel chunk arrays;  A_LO / W_LO  distance to the "lo" copies
+template <int MODE, int N, int NTAPS, int K16, bool A_HAS_LO, uint32_t AO0, uint32_t AO1, uint32_t AO2, uint32_t A_LBO,
+          uint32_t A_LO, uint32_t B_OFF, uint32_t W_LO>
+__device__ __forceinline__ void issue_tile(uint32_t act_lo, uint32_t w_lo, uint32_t d) {
+    constexpr uint32_t AO[3] = {AO0 >> 4, AO1 >> 4, AO2 >> 4};
+    constexpr int NC = MODE == 3 ? (A_HAS_LO ? 3 : 2) : 1;
+    constexpr uint32_t idesc = ptx::idesc_bf16_m128(N);
+    const uint32_t a0 = act_lo | (((A_LBO >> 4) & 0x3FFFu) << 16);
+    const uint32_t b0 = (w_lo + (B_OFF >> 4)) | ((((uint32_t)N * 16u) >> 4) << 16);
+#pragma unroll
+    for (int combo = NC - 1; combo >= 0; --combo) {          // small terms first: lo*hi, hi*lo, then hi*hi
+#pragma unroll
+        for (int t = 0; t < NTAPS; ++t) {
+#pragma unroll
+            for (int j = 0; j < K16; ++j) {
+                const uint32_t a = a0 + AO[t] + (combo == 2 ? (A_LO >> 4) : 0u) + (uint32_t)j * ((2u * A_LBO) >> 4);
+                const uint32_t b = b0 + (combo == 1 ? (W_LO >> 4) : 0u) + (uint32_t)(t * K16 + j) * (((uint32_t)N * 32u) >> 4);
+                ptx::mma_bf16_ss(d, a, b, idesc, (combo == NC - 1 && t == 0 && j == 0) ? 0u : 1u);
+            }
+        }
+    }
+}
+
+// All MMAs of layer phase `ph` for one group.  act_lo / w_lo: shared-memory addresses >> 4; d0: TMEM base of the group.
+template <int MODE>
+__device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_lo, uint32_t d0) {
+    if (ph == 0) {
+#pragma unroll 1
+        for (uint32_t t = 0; t < T1; ++t)
+            issue_tile<MODE, 16, 2, 1, false, 0, 32, 0, X_STRIDE, 0, 0, WHI_L1>(act_lo + t * 128u, w_lo, d0 + t * 16u);
+    } else if (ph == 1) {
+#pragma unroll 1
+        for (uint32_t t = 0; t < T1; ++t)
+            issue_tile<MODE, 16, 3, 1, true, 0, 16, 32, A1_CH, 2 * A1_CH, 0, WHI_L2>(act_lo + t * 128u, w_lo, d0 + t * 16u);
+    } else if (ph == 2) {
+#pragma unroll 1
+        for (uint32_t t = 0; t < T2; ++t) {
+            // E[m] = conv at position 2p (taps: even[p], odd[p], even[p+1]);  O[m] = conv at 2p+1
+            issue_tile<MODE, 32, 3, 1, true, 0, A2_ARR, 16, 2 * A2_ARR, 4 * A2_ARR, 0, WHI_L3>(act_lo + t * 128u, w_lo, d0 + t * 64u);
+            issue_tile<MODE, 32, 3, 1, true, A2_ARR, 16, A2_ARR + 16, 2 * A2_ARR, 4 * A2_ARR, 0, WHI_L3>(act_lo + t * 128u, w_lo,
+                                                                                                      d0 + t * 64u + 32u);
+        }
+    } else if (ph < 9) {
+#pragma unroll 1
+        for (uint32_t t = 0; t < T2; ++t)
+            issue_tile<MODE, 32, 3, 2, true, 0, 16, 32, S2_CH, 4 * S2_CH, 0, WHI_S2>(act_lo + t * 128u, w_lo, d0 + t * 32u);
+    } else if (ph == 9) {
+#pragma unroll 1
+        for (uint32_t t = 0; t < T3; ++t) {
+            // stride 2: x[2p-1], x[2p], x[2p+1] = odd[p-1], even[p], odd[p]; the 1x1 shortcut reads even[p] and
+            // accumulates straight into the residual columns
+            issue_tile<MODE, 64, 3, 2, true, E3_ARR, 16, E3_ARR + 16, 2 * E3_ARR, 8 * E3_ARR, 0, WHI_RC>(act_lo + t * 128u, w_lo,
+                                                                                                  d0 + t * 64u);
+            issue_tile<MODE, 64, 1, 2, true, 16, 0, 0, 2 * E3_ARR, 8 * E3_ARR, RC_SHORTCUT_B_OFF, WHI_RC>(act_lo + t * 128u, w_lo,
+                                                                                                   d0 + 128u + t * 64u);
+        }
+    } else {
+#pragma unroll 1
+        for (uint32_t t = 0; t < T3; ++t)
+            issue_tile<MODE, 64, 3, 4, true, 0, 16, 32, S3_CH, 8 * S3_CH, 0, WHI_S3>(act_lo + t * 128u, w_lo, d0 + t * 64u);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(352, 1) readconv_tc_kernel(const __grid_constant__ TcParams prm) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
+    const int lane = threadIdx.x & 31;
+    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
+    const uint32_t bar0 = ptx::smem_u32(smem + OFF_BAR);
+    // barriers: 0,1 w_full[slot]  2,3 w_empty[slot]  4,5 act_ready[group]  6,7 acc_full[group]
+    auto bar = [&](int k) { return bar0 + 8u * k; };
+    volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(bar(0), 1); ptx::mbar_init(bar(1), 1);
+        ptx::mbar_init(bar(2), 2); ptx::mbar_init(bar(3), 2);          // released by both groups' issuers
+        ptx::mbar_init(bar(4), 128); ptx::mbar_init(bar(5), 128);
+        ptx::mbar_init(bar(6), 1); ptx::mbar_init(bar(7), 1);
+        ptx::fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < N_BIAS; i += blockDim.x) s_bias[i] = __ldg(prm.bias + i);
+    {   // every byte an MMA can read must hold a finite bf16 (zero weights multiply the padding channels)
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (uint32_t i = threadIdx.x; i < OFF_BIAS / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (warp == 8) {
+        ptx::tmem_alloc(ptx::smem_u32(smem + OFF_TMEM), 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
+    const long long R = prm.n_reads;
+
+    if (warp < 8) {
+        // ===================================================== epilogue warpgroups (group g = warp / 4)
+        const int g = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127, wrow = wq * 32;
+        uint8_t* act = smem + OFF_ACT + g * ACT_BYTES;
+        const uint32_t tl = tmem_base + ((uint32_t)wrow << 16) + g * 256;
+        uint32_t acc_n = 0;
+        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+            const long long r0 = ((long long)item * 2 + g) * G;
+            const int n = (int)max(0LL, min((long long)G, R - r0));
+            if (n <= 0) continue;
+            load_input(act, prm.reads, r0, n, prm.channels, prm.layout, tid);
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async();
+            ptx::mbar_arrive(bar(4 + g));
+            float* gout = prm.out + r0 * (long long)(LOUT * COUT);
+#pragma unroll 1
+            for (int ph = 0; ph < N_PHASES; ++ph) {
+                ptx::mbar_wait(bar(6 + g), acc_n & 1);
+                ++acc_n;
+                ptx::tc_fence_after();
+                float* dbg = (prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * 2 + g) * (1024 * 64) : nullptr;
+                if (ph == 0) {
+                    epi_conv<MODE, 16, T1, P1, LV1, false, false, false, OUT_NAT, 0>(
+                        act, tl, 16, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane);
+                } else if (ph == 1) {
+                    epi_conv<MODE, 16, T1, P1, LV2, false, false, false, OUT_EO, 0>(
+                        act, tl, 16, s_bias + B_L2, nullptr, n, A2_ARR, 4 * A2_ARR, nullptr, dbg, wrow, lane);
+                } else if (ph == 2) {
+                    epi_pool<MODE>(act, tl, s_bias + B_L3, n, g, wq, lane, dbg);
+                } else if (ph < 9) {
+                    const float* b = s_bias + B_S2 + (ph - 3) * 32;
+                    if ((ph - 3) % 2 == 0)
+                        epi_conv<MODE, 32, T2, P2, LV3, false, false, false, OUT_NAT, 1>(
+                            act, tl, 32, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane);
+                    else if (ph < 8)
+                        epi_conv<MODE, 32, T2, P2, LV3, true, false, true, OUT_NAT, 1>(
+                            act, tl, 32, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane);
+                    else
+                        epi_conv<MODE, 32, T2, P2, LV3, true, false, false, OUT_EO, 1>(
+                            act, tl, 32, b, nullptr, n, E3_ARR, 8 * E3_ARR, nullptr, dbg, wrow, lane);
+                } else if (ph == 9) {
+                    epi_conv<MODE, 64, T3, P3, LV4, false, false, false, OUT_NAT, 1>(
+                        act, tl, 64, s_bias + B_RCA, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane);
+                } else if (ph == 10) {
+                    epi_conv<MODE, 64, T3, P3, LV4, true, true, true, OUT_NAT, 1>(
+                        act, tl, 64, s_bias + B_RCB, s_bias + B_RCS, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane);
+                } else {
+                    const float* b = s_bias + B_S3 + (ph - 11) * 64;
+                    if ((ph - 11) % 2 == 0)
+                        epi_conv<MODE, 64, T3, P3, LV4, false, false, false, OUT_NAT, 1>(
+                            act, tl, 64, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane);
+                    else if (ph < 16)
+                        epi_conv<MODE, 64, T3, P3, LV4, true, false, true, OUT_NAT, 1>(
+                            act, tl, 64, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane);
+                    else
+                        epi_conv<MODE, 64, T3, P3, LV4, true, false, false, OUT_GLOBAL, 1>(
+                            act, tl, 64, b, nullptr, n, 0, 0, gout, dbg, wrow, lane);
+                }
+                if (ph + 1 < N_PHASES) {
+                    ptx::tc_fence_before();
+                    ptx::fence_proxy_async();
+                    ptx::mbar_arrive(bar(4 + g));
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ===================================================== MMA issuers: warp 8 -> group 0, warp 9 -> group 1.
+        // The whole warp runs the (warp-uniform) loop; one elected lane issues each tcgen05.mma / commit.
+        const int g = warp - 8;
+        uint32_t w_n = 0, ar_n = 0;
+        const uint32_t act_lo = (ptx::smem_u32(smem + OFF_ACT) + g * ACT_BYTES) >> 4;
+        const uint32_t w0_lo = ptx::smem_u32(smem + OFF_W) >> 4;
+        const uint32_t d0 = tmem_base + g * 256;
+        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+            const int n = (int)max(0LL, min((long long)G, R - ((long long)item * 2 + g) * G));
+#pragma unroll 1
+            for (int ph = 0; ph < N_PHASES; ++ph) {
+                const uint32_t slot = w_n & 1u;
+                // Both issuers wait for the slot (even one whose group is empty in this item): the slot is
+                // released only when both have passed it, which keeps them in lockstep with the producer.
+                ptx::mbar_wait(bar(slot), (w_n >> 1) & 1u);              // this layer's weights have landed
+                if (n > 0) {
+                    ptx::mbar_wait(bar(4 + g), ar_n & 1u);              // this group's operand is written
+                    ++ar_n;
+                    ptx::tc_fence_after();
+                    issue_phase<MODE>(ph, act_lo, w0_lo + slot * (WSLOT_BYTES >> 4), d0);
+                    ptx::tc_commit(bar(6 + g));                          // accumulators ready -> epilogue
+                    ptx::tc_commit(bar(2 + slot));                       // weight slot no longer read by this group
+                } else if (lane == 0) {
+                    ptx::mbar_arrive(bar(2 + slot));
+                }
+                __syncwarp();
+                ++w_n;
+            }
+        }
+    } else {
+        // ===================================================== weight producer (one thread, bulk async copies)
+        if (lane == 0) {
+            uint32_t w_n = 0;
+            const uint32_t w0 = ptx::smem_u32(smem + OFF_W);
+            for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+#pragma unroll 1
+                for (int ph = 0; ph < N_PHASES; ++ph) {
+                    const uint32_t slot = w_n & 1u;
+                    ptx::mbar_wait(bar(2 + slot), ((w_n >> 1) & 1u) ^ 1u);
+                    const uint32_t bytes = prm.w_bytes[ph];
+                    ptx::mbar_expect_tx(bar(slot), bytes);
+                    const uint8_t* src = prm.weights + prm.w_src[ph];
+                    for (uint32_t o = 0; o < bytes; o += 8192u)
+                        ptx::bulk_g2s(w0 + slot * WSLOT_BYTES + o, src + o, min(8192u, bytes - o), bar(slot));
+                    ++w_n;
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 8) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+inline uint16_t bf16_rne(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+inline float bf16_to_float(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+struct HostConv {
+    const float* w;   // [k*cin][cout]  (row = tap*cin + ci)
+    const float* b;
+    int cin, cout, k;
+};
+
+}  // namespace tc
+
+struct ReadConvTC {
+    tc::TcParams prm;
+    uint8_t* d_weights = nullptr;
+    float* d_bias = nullptr;
+    int mode = 3;
+    int sm_count = 148;
+};
+
+// Checks that `net` is the read_convolver architecture this kernel is specialised for and packs its weights.
+// `d_base` / `h_base`: device and host copies of the same float array the ConvDesc pointers index into.
+static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const float* d_base, const float* h_base,
+                                      int channels, int feature_length, int precision, std::string& err) {
+    using namespace tc;
+    if (precision != HELLO_PREC_BF16X3 && precision != HELLO_PREC_BF16) { err = "unknown tensor-core precision"; return nullptr; }
+    if (feature_length != LIN || channels < 1 || channels > 8) { err = "tensor-core read convolver needs L=150, C<=8"; return nullptr; }
+    auto is_conv = [&](const LayerDesc& L, int cin, int cout, int k, int s, int p) {
+        return L.kind == KIND_CONV && L.a.cin == cin && L.a.cout == cout && L.a.k == k && L.a.stride == s && L.a.pad == p && L.a.relu;
+    };
+    auto is_res = [&](const LayerDesc& L, int cin, int cout, int s, bool sc) {
+        return L.kind == KIND_RES && L.a.cin == cin && L.a.cout == cout && L.a.k == 3 && L.a.stride == s && L.a.pad == 1 &&
+               L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&
+               (L.has_shortcut != 0) == sc && (!sc || (L.s.cin == cin && L.s.cout == cout && L.s.k == 1 && L.s.stride == s && L.s.pad == 0));
+    };
+    bool ok = net.size() == 11 && is_conv(net[0], channels, 16, 3, 1, 0) && is_conv(net[1], 16, 16, 3, 1, 0) &&
+              is_conv(net[2], 16, 32, 3, 1, 0) && net[3].kind == KIND_MAXPOOL && net[3].a.k == 3 && net[3].a.stride == 2;
+    for (int i = 4; ok && i < 7; ++i) ok = is_res(net[i], 32, 32, 1, false);
+    ok = ok && is_res(net[7], 32, 64, 2, true);
+    for (int i = 8; ok && i < 11; ++i) ok = is_res(net[i], 64, 64, 1, false);
+    if (!ok) { err = "layer table is not the 16-16-32 / 3xRes32 / Res32->64(s2) / 3xRes64 read convolver"; return nullptr; }
+
+    const int parts = precision == HELLO_PREC_BF16X3 ? 2 : 1;
+    auto hc = [&](const ConvDesc& c) { return HostConv{h_base + (c.w - d_base), h_base + (c.b - d_base), c.cin, c.cout, c.k}; };
+    std::vector<uint8_t> blob;
+    std::vector<float> bias(N_BIAS, 0.f);
+    ReadConvTC* t = new ReadConvTC();
+    t->mode = precision == HELLO_PREC_BF16X3 ? 3 : 1;
+    std::memset(&t->prm, 0, sizeof(t->prm));
+
+    // One B unit = [2 chunks][n][8] bf16 for (tap, k16 step j): element (chunk c, row n, e) = W[n][ci = 16j+8c+e][tap].
+    // `stem1` packs layer 1 instead: unit u covers real taps 2u (chunk 0) and 2u+1 (chunk 1), e = channel (zero padded).
+    auto pack_phase = [&](int ph, std::vector<std::pair<HostConv, bool>> convs) {
+        std::vector<uint16_t> hi, lo;
+        for (auto& cv : convs) {
+            const HostConv& c = cv.first;
+            const bool stem1 = cv.second;
+            const int units_t = stem1 ? 2 : c.k, k16 = stem1 ? 1 : c.cin / 16;
+            for (int tp = 0; tp < units_t; ++tp)
+                for (int j = 0; j < k16; ++j)
+                    for (int ch = 0; ch < 2; ++ch)
+                        for (int n = 0; n < c.cout; ++n)
+                            for (int e = 0; e < 8; ++e) {
+                                float w = 0.f;
+                                if (stem1) {
+                                    const int tap = 2 * tp + ch;
+                                    if (tap < c.k && e < c.cin) w = c.w[(size_t)(tap * c.cin + e) * c.cout + n];
+                                } else {
+                                    const int ci = 16 * j + 8 * ch + e;
+                                    w = c.w[(size_t)(tp * c.cin + ci) * c.cout + n];
+                                }
+                                const uint16_t h = bf16_rne(w);
+                                hi.push_back(h);
+                                lo.push_back(bf16_rne(w - bf16_to_float(h)));
+                            }
+        }
+        t->prm.w_src[ph] = (uint32_t)blob.size();
+        t->prm.w_bytes[ph] = (uint32_t)(hi.size() * 2 * parts);
+        const uint32_t w_bytes = t->prm.w_bytes[ph];
+        const uint32_t expect_hi = ph == 0 ? WHI_L1 : ph == 1 ? WHI_L2 : ph == 2 ? WHI_L3 : ph < 9 ? WHI_S2 : ph == 9 ? WHI_RC : WHI_S3;
+        if (hi.size() * 2 != expect_hi) return false;
+        const uint8_t* ph_ = reinterpret_cast<const uint8_t*>(hi.data());
+        blob.insert(blob.end(), ph_, ph_ + hi.size() * 2);
+        if (parts == 2) {
+            const uint8_t* pl = reinterpret_cast<const uint8_t*>(lo.data());
+            blob.insert(blob.end(), pl, pl + lo.size() * 2);
+        }
+        return w_bytes <= WSLOT_BYTES && w_bytes % 16 == 0;
+    };
+    auto copy_bias = [&](const HostConv& c, int off) { for (int i = 0; i < c.cout; ++i) bias[off + i] = c.b[i]; };
+
+    bool fit = true;
+    // stem
+    fit &= pack_phase(0, {{hc(net[0].a), true}});
+    copy_bias(hc(net[0].a), B_L1);
+    fit &= pack_phase(1, {{hc(net[1].a), false}});
+    copy_bias(hc(net[1].a), B_L2);
+    fit &= pack_phase(2, {{hc(net[2].a), false}});
+    copy_bias(hc(net[2].a), B_L3);
+    // three residual blocks at 32 channels
+    for (int r = 0; r < 3; ++r) {
+        const LayerDesc& L = net[4 + r];
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int ph = 3 + 2 * r + h2;
+            const HostConv c = hc(h2 ? L.b : L.a);
+            fit &= pack_phase(ph, {{c, false}});
+            copy_bias(c, B_S2 + (ph - 3) * 32);
+        }
+    }
+    // stride-2 block 32 -> 64: conv_a and the 1x1 shortcut read the de-interleaved stage-2 output
+    fit &= pack_phase(9, {{hc(net[7].a), false}, {hc(net[7].s), false}});
+    copy_bias(hc(net[7].a), B_RCA);
+    copy_bias(hc(net[7].s), B_RCS);
+    fit &= pack_phase(10, {{hc(net[7].b), false}});
+    copy_bias(hc(net[7].b), B_RCB);
+    for (int r = 0; r < 3; ++r) {
+        const LayerDesc& L = net[8 + r];
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int ph = 11 + 2 * r + h2;
+            const HostConv c = hc(h2 ? L.b : L.a);
+            fit &= pack_phase(ph, {{c, false}});
+            copy_bias(c, B_S3 + (ph - 11) * 64);
+        }
+    }
+    if (!fit) { err = "a layer's weights do not fit the shared-memory weight slot"; delete t; return nullptr; }
+
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { err = "cudaGetDeviceProperties failed"; delete t; return nullptr; }
+    t->sm_count = prop.multiProcessorCount;
+    if ((size_t)prop.sharedMemPerBlockOptin < SMEM_BYTES) { err = "device has too little shared memory per block"; delete t; return nullptr; }
+    if (cudaMalloc(&t->d_weights, blob.size()) != cudaSuccess || cudaMalloc(&t->d_bias, N_BIAS * 4) != cudaSuccess ||
+        cudaMemcpy(t->d_weights, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(t->d_bias, bias.data(), N_BIAS * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        err = "allocating the packed bf16 weights failed";
+        if (t->d_weights) cudaFree(t->d_weights);
+        if (t->d_bias) cudaFree(t->d_bias);
+        delete t;
+        return nullptr;
+    }
+    cudaError_t e = t->mode == 3
+        ? cudaFuncSetAttribute(readconv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)
+        : cudaFuncSetAttribute(readconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) {
+        err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+        cudaFree(t->d_weights); cudaFree(t->d_bias); delete t;
+        return nullptr;
+    }
+    t->prm.weights = t->d_weights;
+    t->prm.bias = t->d_bias;
+    t->prm.channels = channels;
+    return t;
+}
+
+// out: fp32 [n_reads, 36, 64] channel-last.  dbg (optional): fp32 [ceil(n_reads/6), 1024, 64] dump of the epilogue
+// values of layer phase `dbg_phase` (test hook).
+static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long long n_reads, int layout, float* out,
+                                      cudaStream_t st, float* dbg = nullptr, int dbg_phase = -1) {
+    if (n_reads <= 0) return cudaSuccess;
+    tc::TcParams prm = t->prm;
+    prm.reads = reads;
+    prm.n_reads = n_reads;
+    prm.layout = layout;
+    prm.out = out;
+    prm.dbg = dbg;
+    prm.dbg_phase = dbg_phase;
+    const long long items = (n_reads + 2 * tc::G - 1) / (2 * tc::G);
+    if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
+    prm.n_items = (int)items;
+    const int grid = (int)std::min<long long>(items, t->sm_count);
+    if (t->mode == 3)
+        tc::readconv_tc_kernel<3><<<grid, 352, tc::SMEM_BYTES, st>>>(prm);
+    else
+        tc::readconv_tc_kernel<1><<<grid, 352, tc::SMEM_BYTES, st>>>(prm);
+    return cudaGetLastError();
+}
+
+static void readconv_tc_destroy(ReadConvTC* t) {
+    if (!t) return;
+    if (t->d_weights) cudaFree(t->d_weights);
+    if (t->d_bias) cudaFree(t->d_bias);
+    delete t;
+}
 
 }  // namespace hello

@@ -39,3 +39,34 @@ def flat_result(cfg, res):
         experts, meta = res
         return torch.stack([e.reshape(-1) for e in experts]), meta
     return res.reshape(1, -1), None
+
+
+def readconv_phase_reference(cfg, params, reads_rlc, tech=0):
+    """Post-activation fp32 values of the 17 layer phases of the read convolver (oracle layers), each [R, C, L]:
+    0-1 stem convs, 2 stem conv 3 + max-pool, then (conv_a, block output) of the seven residual blocks."""
+    import torch.nn.functional as F
+    from oracle import hello_oracle as O
+    net = O.OracleModel(cfg, params).nets["read_convolver%d" % tech]
+    L = net.layers
+    x = reads_rlc.transpose(1, 2).float()
+    outs = []
+    with torch.no_grad():
+        x = net._conv(x, L[0][1], L[0][2]); outs.append(x)
+        x = net._conv(x, L[1][1], L[1][2]); outs.append(x)
+        x = F.max_pool1d(net._conv(x, L[2][1], L[2][2]), 3, 2, 0); outs.append(x)
+        for li in range(4, 11):
+            _, layer, (wa, wb, ws) = L[li]
+            t = net._conv(x, layer.conv_a, wa); outs.append(t)
+            sh = net._conv(x, layer.conv_s, ws) if ws is not None else x
+            x = net._conv(t, layer.conv_b, wb) + sh; outs.append(x)
+    return outs
+
+
+def readconv_phase_from_dump(dump, phase, n_reads, length):
+    """Undo the kernel's row packing: dump [groups, 1024, 64] -> [R, C, L] for one phase (include/hello_moe.h)."""
+    pitch, ch = (160, 16) if phase < 2 else ((80, 32) if phase < 9 else (40, 64))
+    out = torch.zeros((n_reads, ch, length))
+    for r in range(n_reads):
+        g, i = divmod(r, 6)
+        out[r] = dump[g, i * pitch:i * pitch + length, :ch].t()
+    return out

@@ -3,15 +3,20 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import GOLDEN_CASES, flat_result, load_golden, params_for
+from helpers import (GOLDEN_CASES, flat_result, load_golden, params_for, readconv_phase_from_dump,
+                     readconv_phase_reference)
 from hello_b200 import arch, synth, weights
 
 pytestmark = pytest.mark.gpu
 
 # Floating-point tolerance (north_star: "max abs error <= 1e-3 in fp32 accumulate").  fp32 mode is plain fp32
 # FMA with a different summation order than oneDNN's, so it lands far inside that.
+# bf16x3 runs the read convolver on tcgen05 with hi+lo bf16 operands (3 MMAs, fp32 accumulate): ~1e-5 relative per
+# layer.  bf16 (single MMA) is the "fast" mode, reported separately and only checked loosely.
 TOL_LOGIT = {"fp32": 2e-4, "bf16x3": 1e-3}
 TOL_PROB = {"fp32": 5e-5, "bf16x3": 5e-4}
+TC_LAYER_REL = {"bf16x3": 5e-5, "bf16": 4e-2}
+WIDE = ("hybrid_no_ensemble_wide",)        # 2x channels: no tensor-core read convolver, fp32 only
 DEV = "cuda:0"
 
 
@@ -83,29 +88,84 @@ def test_combiner_and_meta_networks(gpu):
     assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
 
 
+# ------------------------------------------------------------------------------------- fused tcgen05 read convolver
+@pytest.mark.parametrize("precision,name", [("bf16x3", "single_tech"), ("bf16x3", "single_tech_hp"),
+                                            ("bf16", "single_tech")])
+def test_readconv_tc_every_layer(gpu, precision, name):
+    """Each of the 17 layer phases of the fused kernel against the oracle's fp32 layer outputs."""
+    cfg = arch.CONFIGS[name]
+    pl = synth.make_pileups(4, coverage=9, channels=cfg.read_cin, seed=21)
+    reads = pl.reads[0][:31]                       # 2 full pairs of 6-read groups + a ragged tail
+    eng = net_for(gpu, cfg, precision).engine
+    ref = readconv_phase_reference(cfg, params_for(cfg), reads)
+    for ph in range(17):
+        out, dump = eng.readconv_debug(reads, ph)
+        got = readconv_phase_from_dump(dump.cpu(), ph, reads.shape[0], ref[ph].shape[2])
+        scale = max(1.0, ref[ph].abs().max().item())
+        err = (got - ref[ph]).abs().max().item()
+        assert err < TC_LAYER_REL[precision] * scale, (ph, err, scale)
+    err = (out.cpu().transpose(1, 2) - ref[-1]).abs().max().item()
+    assert err < TC_LAYER_REL[precision] * max(1.0, ref[-1].abs().max().item())
+
+
+@pytest.mark.parametrize("n_reads", [1, 5, 6, 7, 12, 13, 151])
+def test_readconv_tc_ragged_counts_and_layouts(gpu, n_reads):
+    """Any number of reads (partial groups, partial group pairs, more items than one wave needs) in both layouts,
+    bit-identical to each other and equal to the fp32 CUDA-core path within the bf16x3 tolerance."""
+    from hello_b200 import _lib
+    cfg = arch.CONFIGS["single_tech"]
+    g = torch.Generator().manual_seed(n_reads)
+    pl = synth.make_pileups(40, coverage=6, channels=cfg.read_cin, seed=300 + n_reads)
+    reads = pl.reads[0][:n_reads]
+    assert reads.shape[0] == n_reads
+    tcn = net_for(gpu, cfg, "bf16x3").engine
+    a, _ = tcn.readconv_debug(reads, -1, _lib.LAYOUT_RLC)
+    b, _ = tcn.readconv_debug(reads.transpose(1, 2).contiguous(), -1, _lib.LAYOUT_RCL)
+    assert torch.equal(a, b)
+    c = tcn.run_net("read_convolver0", reads, _lib.LAYOUT_RLC)
+    assert torch.equal(a, c), "run_net must route the read convolver through the same tensor-core kernel"
+    ref = net_for(gpu, cfg, "fp32").engine.run_net("read_convolver0", reads, _lib.LAYOUT_RLC)
+    scale = max(1.0, ref.abs().max().item())
+    assert (a - ref).abs().max().item() < TC_LAYER_REL["bf16x3"] * scale
+
+
+def test_readconv_tc_is_deterministic(gpu):
+    cfg = arch.CONFIGS["single_tech"]
+    pl = synth.make_pileups(200, coverage=10, channels=cfg.read_cin, seed=8)
+    eng = net_for(gpu, cfg, "bf16x3").engine
+    a, _ = eng.readconv_debug(pl.reads[0])
+    b, _ = eng.readconv_debug(pl.reads[0])
+    assert torch.equal(a, b)
+
+
 # ------------------------------------------------------------------------------------------------ whole forward
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_forward_matches_reference_golden(gpu, case):
+def test_forward_matches_reference_golden(gpu, case, precision):
     """Same weights + same inputs as the reference run that produced tests/golden/*.npz."""
     cfg, pl, g = load_golden(case)
     assert weights.params_digest(params_for(cfg)) == str(g["digest"])
-    net = net_for(gpu, cfg)
+    if precision != "fp32" and cfg.name in WIDE:
+        with pytest.raises(Exception, match="read convolver"):
+            net_for(gpu, cfg, precision)
+        return
+    net = net_for(gpu, cfg, precision)
     tensors, naps, nrpa, ref_seg = pl.forward_args()
     res = net.forward(tensors, naps, nrpa, ref_seg)
     logits, meta = flat_result(cfg, res)
-    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=TOL_LOGIT["fp32"])
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=TOL_LOGIT[precision])
     if meta is not None:
-        np.testing.assert_allclose(meta.numpy(), g["meta"], rtol=0, atol=TOL_PROB["fp32"])
+        np.testing.assert_allclose(meta.numpy(), g["meta"], rtol=0, atol=TOL_PROB[precision])
     r = net.last_result
-    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], rtol=0, atol=TOL_PROB["fp32"])
-    np.testing.assert_allclose(r.pair_prob[1:].cpu().numpy(), g["pair_experts"], rtol=0, atol=TOL_PROB["fp32"])
-    np.testing.assert_allclose(r.meta.cpu().numpy(), g["site_meta"], rtol=0, atol=TOL_PROB["fp32"])
+    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], rtol=0, atol=TOL_PROB[precision])
+    np.testing.assert_allclose(r.pair_prob[1:].cpu().numpy(), g["pair_experts"], rtol=0, atol=TOL_PROB[precision])
+    np.testing.assert_allclose(r.meta.cpu().numpy(), g["site_meta"], rtol=0, atol=TOL_PROB[precision])
     # float64 re-mix of prepareVcf.py
     mix64 = (g["pair_experts"].astype(np.float64) *
              np.repeat(g["site_meta"].astype(np.float64), np.diff(r.pair_off.numpy()), axis=0).T).sum(0)
-    np.testing.assert_allclose(r.pair_mix64.cpu().numpy(), mix64, rtol=0, atol=TOL_PROB["fp32"])
+    np.testing.assert_allclose(r.pair_mix64.cpu().numpy(), mix64, rtol=0, atol=TOL_PROB[precision])
     # genotype call: bit-exact wherever the reference's own top-2 margin exceeds the posterior tolerance
-    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB["fp32"])
+    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB[precision])
 
 
 def check_calls(result, ref_mixed, ref_best, tol):
@@ -122,27 +182,28 @@ def check_calls(result, ref_mixed, ref_best, tol):
     return n_tight
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
 @pytest.mark.parametrize("name", ["single_tech", "hybrid_ensemble2", "hybrid_full", "hybrid_no_ensemble"])
-def test_forward_matches_oracle_seeded(gpu, name):
+def test_forward_matches_oracle_seeded(gpu, name, precision):
     from oracle import hello_oracle as O
     cfg = arch.CONFIGS[name]
     pl = synth.make_pileups(24, coverage=14, channels=cfg.read_cin, seed=77)
-    net = net_for(gpu, cfg)
+    net = net_for(gpu, cfg, precision)
     res = net.forward(*pl.forward_args())
     ref = oracle_for(cfg).forward(*pl.forward_args())
     lg, mg = flat_result(cfg, res)
     lr, mr = flat_result(cfg, ref)
-    assert (lg - lr).abs().max().item() < TOL_LOGIT["fp32"]
+    assert (lg - lr).abs().max().item() < TOL_LOGIT[precision]
     if mr is not None:
-        assert (mg - mr).abs().max().item() < TOL_PROB["fp32"]
+        assert (mg - mr).abs().max().item() < TOL_PROB[precision]
     post = O.batched_posteriors(cfg, ref, pl.num_alleles_per_site())
     mixed = torch.cat([p[0] for p in post]).numpy()
     best = np.array([p[3] for p in post], np.int32)
     r = net.last_result
-    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=TOL_PROB["fp32"])
-    check_calls(r, mixed, best, TOL_PROB["fp32"])
+    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=TOL_PROB[precision])
+    check_calls(r, mixed, best, TOL_PROB[precision])
     np.testing.assert_allclose(r.best_prob.cpu().numpy(), np.array([p[4] for p in post], np.float32), rtol=0,
-                               atol=TOL_PROB["fp32"])
+                               atol=TOL_PROB[precision])
 
 
 def test_strict_drop_in_wrapper_call(gpu):
