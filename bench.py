@@ -44,7 +44,11 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="illumina_30x", choices=sorted(WORKLOADS))
     ap.add_argument("--sites", type=int, default=1_000_000, help="sites per GPU (weak scaling)")
-    ap.add_argument("--precision", default=os.environ.get("HELLO_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("HELLO_PRECISION", "bf16x3"),
+                    choices=["bf16x3", "bf16", "fp32"],
+                    help="bf16x3 (default): read convolver on tcgen05 with hi+lo bf16 operands, fp32 accumulate, "
+                         "posteriors within 1e-3 of the reference; bf16: single-MMA fast mode; fp32: CUDA cores only")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of per-site results")
     ap.add_argument("--workspace-gb", type=float, default=6.0)
     ap.add_argument("--chunk-sites", type=int, default=0, help="cap on sites per internal chunk (0 = auto)")
     ap.add_argument("--e2e-chunk-sites", type=int, default=32768)
@@ -220,7 +224,7 @@ def generate_on_device(cfg, cov, n_sites, device, seed, gen_chunk=16384):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from hello_b200 import _lib, arch, model, weights
+    from hello_b200 import _lib, arch, model, shard, weights
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -261,9 +265,20 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    gather = world > 1 and not args.no_gather
+
+    def step():
+        """One pass of the hot path over this rank's shard; with N>1 the per-site results are then gathered over
+        NCCL (the only collective of the path -- nothing is exchanged inside the forward)."""
+        engine.run(batch, result)
+        if gather:
+            return shard.gather_site_results(result.best_pair, result.best_prob, result.meta, result.pair_prob,
+                                             result.pair_mix64, result.logits)
+        return None
+
     # ---- value: inputs resident in HBM ---------------------------------------------------------------------------
     for _ in range(args.warmup):
-        engine.run(batch, result)
+        step()
     barrier()
     engine.profile_enable(True)
     sampler = ClockSampler(local)
@@ -272,7 +287,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        engine.run(batch, result)
+        step()
     ev1.record()
     barrier()
     clocks = sampler.stop()
@@ -314,17 +329,31 @@ def run_ours(args):
     tensor_peak = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback (B200_PROFILING.md, sustained)"
     achieved = flops_read * args.steps / (rc_ms / 1e3) / 1e12 if rc_ms > 0 else None
+    traffic, traffic_src = None, None
+    try:   # dram bytes per read of the dominant kernel, from the committed `ncu --set full` capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "readconv_tc_summary.json")))
+        if args.precision in prof and rc_regions > 0:
+            traffic = prof[args.precision]["dram_bytes_per_read"] * sum(R) * args.steps / rc_regions
+            traffic_src = prof[args.precision]["source"]
+    except Exception:
+        pass
     roofline = {
         "kernel": "read convolver stage (%s)" % ("readconv_tc" if args.precision != "fp32" else
                                                 "conv1d_fp32_kernel x19 + maxpool per chunk"),
         "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
-        "frac": (achieved / tensor_peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "frac": (achieved / tensor_peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": peak_src,
+        "algorithmic_flops_per_launch": flops_read * args.steps / rc_regions if rc_regions else None,
+        "ms_per_launch": rc_ms / rc_regions if rc_regions else None,
         "algorithmic_flops_per_read": list(f_read), "reads_per_step": R,
         "stage_ms_per_step": rc_ms / max(args.steps, 1), "regions_per_step": rc_regions / max(args.steps, 1),
         "stage_share_of_step": rc_ms / ms_total if ms_total > 0 else None,
-        "note": ("fp32 mode runs the convolutions on CUDA cores (FFMA); the fraction is quoted against the bf16 "
-                 "tensor-core peak the north star targets" if args.precision == "fp32" else
-                 "bf16x3 issues 3 MMAs per algorithmic MAC: ceiling = 1/3 of the tensor peak"),
+        "note": {"fp32": "fp32 mode runs the convolutions on CUDA cores (FFMA); the fraction is quoted against the bf16 "
+                         "tensor-core peak the north star targets",
+                 "bf16x3": "one fused tcgen05 kernel per chunk; bf16x3 issues 3 MMAs per algorithmic MAC (hi*hi + hi*lo + "
+                           "lo*hi, fp32 accumulate), so the ceiling of `frac` is 1/3 by construction",
+                 "bf16": "one fused tcgen05 kernel per chunk; single bf16 MMA per MAC (fast mode, ~1e-1 logit error)"
+                 }[args.precision],
     }
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -344,7 +373,8 @@ def run_ours(args):
         "config": {"workload": "%s_%dk_sites_per_gpu" % (args.workload, args.sites // 1000), "model": cfg_name,
                    "weights": "random-init (seed 13), shipped blobs are git-lfs pointers", "sites_per_gpu": S,
                    "alleles_per_gpu": A, "reads_per_gpu": R, "coverage": cov, "precision": args.precision,
-                   "partition": "sites sharded across ranks, no data-path collective",
+                   "partition": "sites sharded across ranks, no collective inside the forward" +
+                                (", NCCL all_gather of per-site results each step" if gather else ""),
                    "l2": "inputs (%.1f GB per step) are far larger than L2; no flush needed" % input_gb,
                    "flops_per_step_per_gpu": flops_step},
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -15,14 +15,14 @@
 //   Stride-2 layers (MaxPool1d(3,2), the stride-2 residual block) read an even/odd de-interleaved copy that the
 //   previous epilogue writes, which turns stride 2 back into unit row shifts.
 //
-// Pipeline (one CTA per SM, 11 warps)
-//   warps 0-3 / 4-7  epilogue of read group 0 / 1: TMEM -> registers (bias, ReLU, residual, max-pool), split to
-//                    bf16 hi (+lo), write the next layer's operand back to shared memory IN PLACE, keep the fp32
-//                    residual stream in TMEM.
-//   warps 8 / 9      MMA issuer of group 0 / 1: fully unrolled tcgen05.mma sequences (operand offsets are
-//                    immediates), one elected lane issues.  The tensor pipe works on one group while the CUDA
-//                    cores run the other group's epilogue.
-//   warp 10          one thread streams the weights of the next layer from L2 into a 2-slot ring with
+// Pipeline (one CTA per SM, 21 warps, four independent groups of 3 reads in flight)
+//   warps 0-15       epilogue warpgroup of read group warp/4: TMEM -> registers (bias, ReLU, residual, max-pool),
+//                    split to bf16 hi (+lo), write the next layer's operand back to shared memory IN PLACE, keep
+//                    the fp32 residual stream in TMEM.
+//   warps 16-19      MMA issuer of group warp-16: fully unrolled tcgen05.mma sequences (operand offsets are
+//                    immediates, uniform datapath), one elected lane issues.  The tensor pipe works on some groups
+//                    while the CUDA cores run the other groups' epilogues.
+//   warp 20          one thread streams the weights of the next layer from L2 into a 2-slot ring with
 //                    cp.async.bulk (TMA unit) while the current layer computes.
 //   Precision: HELLO_PREC_BF16X3 splits activations and weights into bf16 hi+lo and issues hi*hi + hi*lo + lo*hi
 //   (fp32 accumulate) -> ~2^-17 relative error per product; HELLO_PREC_BF16 issues hi*hi only.
@@ -39,10 +39,12 @@
 namespace hello {
 namespace tc {
 
-constexpr int G = 6;                           // reads per group (two groups in flight per CTA)
+constexpr int G = 3;                           // reads per group
+constexpr int NG = 4;                          // groups in flight per CTA (one item = NG*G = 12 reads)
 constexpr int P1 = 160, P2 = 80, P3 = 40;      // row pitch of one read at the three resolutions
 constexpr int ROWS1 = G * P1, ROWS2 = G * P2, ROWS3 = G * P3;
-constexpr int T1 = 8, T2 = 4, T3 = 2;          // 128-row MMA tiles per group
+constexpr int T1 = 4, T2 = 2, T3 = 1;          // 128-row MMA tiles per group
+constexpr uint32_t RES_COL = 64;               // TMEM columns [0,64) of a group: accumulators, [64,128): fp32 residual
 constexpr int LIN = 150, LV1 = 148, LV2 = 146, LV3 = 71, LV4 = 36;   // valid lengths
 constexpr int LOUT = 36, COUT = 64;
 constexpr int N_PHASES = 17;
@@ -55,19 +57,22 @@ constexpr uint32_t A2_ARR = (ROWS2 + 2) * 16;     // layer-2 output: (chunk, par
 constexpr uint32_t S2_CH = (ROWS2 + 2) * 16;      // 32-channel stage: 4 chunks, lead zero row
 constexpr uint32_t E3_ARR = (ROWS3 + 2) * 16;     // stage-2 output de-interleaved: (chunk, parity), pitch 40, lead row
 constexpr uint32_t S3_CH = (ROWS3 + 2) * 16;      // 64-channel stage: 8 chunks, lead zero row
-constexpr uint32_t XCHG_OFF = 61952;              // 16 x 32 floats for the max-pool row exchange
-constexpr uint32_t ACT_BYTES = 64000;
+constexpr uint32_t XCHG_OFF = 16 * S3_CH;         // T2*4 x 32 floats for the max-pool row exchange
+constexpr uint32_t ACT_BYTES = XCHG_OFF + T2 * 4 * 128;
 constexpr uint32_t WSLOT_BYTES = 49152;
 
 constexpr uint32_t OFF_ACT = 0;
-constexpr uint32_t OFF_W = 2 * ACT_BYTES;
+constexpr uint32_t OFF_W = NG * ACT_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_W + 2 * WSLOT_BYTES;
 constexpr uint32_t OFF_BAR = OFF_BIAS + N_BIAS * 4;
-constexpr uint32_t OFF_TMEM = OFF_BAR + 8 * 8;
+constexpr uint32_t N_BARS = 4 + 2 * NG;           // w_full[2], w_empty[2], act_ready[NG], acc_full[NG]
+constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(2 * A1_CH * 2 <= XCHG_OFF && 8 * A2_ARR <= XCHG_OFF && 8 * S2_CH <= XCHG_OFF &&
               16 * E3_ARR <= XCHG_OFF && 16 * S3_CH <= XCHG_OFF && 2 * X_STRIDE <= XCHG_OFF, "activation layouts");
+static_assert(T1 * 128 >= ROWS1 && T2 * 128 >= ROWS2 && T3 * 128 >= ROWS3, "tiles cover the packed rows");
+static_assert(T1 * 16 <= RES_COL && T2 * 32 <= RES_COL && T3 * 64 <= RES_COL && NG * 2 * RES_COL <= 512, "TMEM budget");
 
 // bias table (floats)
 constexpr int B_L1 = 0, B_L2 = 16, B_L3 = 32, B_S2 = 64, B_RCA = 256, B_RCS = 320, B_RCB = 384, B_S3 = 448;
@@ -154,7 +159,7 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, int d_stride
             float v[CB];
             float r[RESID ? CB : 1];
             ptx::tmem_ld<CB>(tl + tile * d_stride + cb * CB, v);
-            if (RESID) ptx::tmem_ld<CB>(tl + 128 + tile * N + cb * CB, r);
+            if (RESID) ptx::tmem_ld<CB>(tl + RES_COL + tile * N + cb * CB, r);
             ptx::tmem_wait_ld();
 #pragma unroll
             for (int c = 0; c < CB; ++c) {
@@ -162,7 +167,7 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, int d_stride
                 if (RESID) x += RES_BIAS ? (r[c] + bias2[cb * CB + c]) : r[c];
                 v[c] = valid ? x : 0.f;
             }
-            if (WRITE_RESID) ptx::tmem_st32(tl + 128 + tile * N + cb * CB, v);
+            if (WRITE_RESID) ptx::tmem_st32(tl + RES_COL + tile * N + cb * CB, v);
             if (dbg) {
 #pragma unroll
                 for (int c = 0; c < CB; ++c) dbg[m * 64 + cb * CB + c] = v[c];
@@ -223,14 +228,15 @@ __device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float*
         const int i = m / P2, p = m - i * P2;
         const bool valid = (i < n_reads) && (p < LV3);
         const int nxt = tile * 4 + wq + 1;
+        constexpr int N_SLICES = T2 * 4;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
             float e1 = __shfl_down_sync(0xffffffffu, e[c], 1);
-            if (lane == 31) e1 = nxt < 16 ? xchg[nxt * 32 + c] : e[c];
+            if (lane == 31) e1 = nxt < N_SLICES ? xchg[nxt * 32 + c] : e[c];
             const float x = fmaxf(fmaxf(fmaxf(e[c], o[c]), e1) + bias[c], 0.f);
             o[c] = valid ? x : 0.f;
         }
-        ptx::tmem_st32(tl + 128 + tile * 32, o);
+        ptx::tmem_st32(tl + RES_COL + tile * 32, o);
         if (dbg) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) dbg[m * 64 + c] = o[c];
@@ -309,7 +315,7 @@ __device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_
             issue_tile<MODE, 64, 3, 2, true, E3_ARR, 16, E3_ARR + 16, 2 * E3_ARR, 8 * E3_ARR, 0, WHI_RC>(act_lo + t * 128u, w_lo,
                                                                                                   d0 + t * 64u);
             issue_tile<MODE, 64, 1, 2, true, 16, 0, 0, 2 * E3_ARR, 8 * E3_ARR, RC_SHORTCUT_B_OFF, WHI_RC>(act_lo + t * 128u, w_lo,
-                                                                                                   d0 + 128u + t * 64u);
+                                                                                                   d0 + RES_COL + t * 64u);
         }
     } else {
 #pragma unroll 1
@@ -319,21 +325,21 @@ __device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(352, 1) readconv_tc_kernel(const __grid_constant__ TcParams prm) {
+__global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const __grid_constant__ TcParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
     const int lane = threadIdx.x & 31;
     float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
     const uint32_t bar0 = ptx::smem_u32(smem + OFF_BAR);
-    // barriers: 0,1 w_full[slot]  2,3 w_empty[slot]  4,5 act_ready[group]  6,7 acc_full[group]
+    // barriers: 0,1 w_full[slot]  2,3 w_empty[slot]  4.. act_ready[group]  4+NG.. acc_full[group]
     auto bar = [&](int k) { return bar0 + 8u * k; };
+    constexpr int BAR_ACT = 4, BAR_ACC = 4 + NG;
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(bar(0), 1); ptx::mbar_init(bar(1), 1);
-        ptx::mbar_init(bar(2), 2); ptx::mbar_init(bar(3), 2);          // released by both groups' issuers
-        ptx::mbar_init(bar(4), 128); ptx::mbar_init(bar(5), 128);
-        ptx::mbar_init(bar(6), 1); ptx::mbar_init(bar(7), 1);
+        ptx::mbar_init(bar(2), NG); ptx::mbar_init(bar(3), NG);        // released by every group's issuer
+        for (int g = 0; g < NG; ++g) { ptx::mbar_init(bar(BAR_ACT + g), 128); ptx::mbar_init(bar(BAR_ACC + g), 1); }
         ptx::fence_mbar_init();
     }
     for (int i = threadIdx.x; i < N_BIAS; i += blockDim.x) s_bias[i] = __ldg(prm.bias + i);
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(352, 1) readconv_tc_kernel(const __grid_consta
         uint4* z = reinterpret_cast<uint4*>(smem);
         for (uint32_t i = threadIdx.x; i < OFF_BIAS / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (warp == 8) {
+    if (warp == 4 * NG) {
         ptx::tmem_alloc(ptx::smem_u32(smem + OFF_TMEM), 512);
         ptx::tmem_relinquish();
     }
@@ -352,27 +358,27 @@ __global__ void __launch_bounds__(352, 1) readconv_tc_kernel(const __grid_consta
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
     const long long R = prm.n_reads;
 
-    if (warp < 8) {
+    if (warp < 4 * NG) {
         // ===================================================== epilogue warpgroups (group g = warp / 4)
         const int g = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127, wrow = wq * 32;
         uint8_t* act = smem + OFF_ACT + g * ACT_BYTES;
-        const uint32_t tl = tmem_base + ((uint32_t)wrow << 16) + g * 256;
+        const uint32_t tl = tmem_base + ((uint32_t)wrow << 16) + g * (2 * RES_COL);
         uint32_t acc_n = 0;
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-            const long long r0 = ((long long)item * 2 + g) * G;
+            const long long r0 = ((long long)item * NG + g) * G;
             const int n = (int)max(0LL, min((long long)G, R - r0));
             if (n <= 0) continue;
             load_input(act, prm.reads, r0, n, prm.channels, prm.layout, tid);
             ptx::tc_fence_before();
             ptx::fence_proxy_async();
-            ptx::mbar_arrive(bar(4 + g));
+            ptx::mbar_arrive(bar(BAR_ACT + g));
             float* gout = prm.out + r0 * (long long)(LOUT * COUT);
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
-                ptx::mbar_wait(bar(6 + g), acc_n & 1);
+                ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
                 ++acc_n;
                 ptx::tc_fence_after();
-                float* dbg = (prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * 2 + g) * (1024 * 64) : nullptr;
+                float* dbg = (prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * NG + g) * (T1 * 128 * 64) : nullptr;
                 if (ph == 0) {
                     epi_conv<MODE, 16, T1, P1, LV1, false, false, false, OUT_NAT, 0>(
                         act, tl, 16, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane);
@@ -413,20 +419,20 @@ __global__ void __launch_bounds__(352, 1) readconv_tc_kernel(const __grid_consta
                 if (ph + 1 < N_PHASES) {
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
-                    ptx::mbar_arrive(bar(4 + g));
+                    ptx::mbar_arrive(bar(BAR_ACT + g));
                 }
             }
         }
-    } else if (warp < 10) {
-        // ===================================================== MMA issuers: warp 8 -> group 0, warp 9 -> group 1.
+    } else if (warp < 5 * NG) {
+        // ===================================================== MMA issuers: warp 4*NG + g serves group g.
         // The whole warp runs the (warp-uniform) loop; one elected lane issues each tcgen05.mma / commit.
-        const int g = warp - 8;
+        const int g = warp - 4 * NG;
         uint32_t w_n = 0, ar_n = 0;
         const uint32_t act_lo = (ptx::smem_u32(smem + OFF_ACT) + g * ACT_BYTES) >> 4;
         const uint32_t w0_lo = ptx::smem_u32(smem + OFF_W) >> 4;
-        const uint32_t d0 = tmem_base + g * 256;
+        const uint32_t d0 = tmem_base + g * (2 * RES_COL);
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-            const int n = (int)max(0LL, min((long long)G, R - ((long long)item * 2 + g) * G));
+            const int n = (int)max(0LL, min((long long)G, R - ((long long)item * NG + g) * G));
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
                 const uint32_t slot = w_n & 1u;
@@ -434,11 +440,11 @@ __global__ void __launch_bounds__(352, 1) readconv_tc_kernel(const __grid_consta
                 // released only when both have passed it, which keeps them in lockstep with the producer.
                 ptx::mbar_wait(bar(slot), (w_n >> 1) & 1u);              // this layer's weights have landed
                 if (n > 0) {
-                    ptx::mbar_wait(bar(4 + g), ar_n & 1u);              // this group's operand is written
+                    ptx::mbar_wait(bar(BAR_ACT + g), ar_n & 1u);         // this group's operand is written
                     ++ar_n;
                     ptx::tc_fence_after();
                     issue_phase<MODE>(ph, act_lo, w0_lo + slot * (WSLOT_BYTES >> 4), d0);
-                    ptx::tc_commit(bar(6 + g));                          // accumulators ready -> epilogue
+                    ptx::tc_commit(bar(BAR_ACC + g));                    // accumulators ready -> epilogue
                     ptx::tc_commit(bar(2 + slot));                       // weight slot no longer read by this group
                 } else if (lane == 0) {
                     ptx::mbar_arrive(bar(2 + slot));
@@ -469,7 +475,7 @@ __global__ void __launch_bounds__(352, 1) readconv_tc_kernel(const __grid_consta
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 8) ptx::tmem_dealloc(tmem_base, 512);
+    if (warp == 4 * NG) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -637,7 +643,7 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     return t;
 }
 
-// out: fp32 [n_reads, 36, 64] channel-last.  dbg (optional): fp32 [ceil(n_reads/6), 1024, 64] dump of the epilogue
+// out: fp32 [n_reads, 36, 64] channel-last.  dbg (optional): fp32 [ceil(n_reads/3), 512, 64] dump of the epilogue
 // values of layer phase `dbg_phase` (test hook).
 static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long long n_reads, int layout, float* out,
                                       cudaStream_t st, float* dbg = nullptr, int dbg_phase = -1) {
@@ -649,14 +655,14 @@ static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long 
     prm.out = out;
     prm.dbg = dbg;
     prm.dbg_phase = dbg_phase;
-    const long long items = (n_reads + 2 * tc::G - 1) / (2 * tc::G);
+    const long long items = (n_reads + tc::NG * tc::G - 1) / (tc::NG * tc::G);
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
     prm.n_items = (int)items;
     const int grid = (int)std::min<long long>(items, t->sm_count);
     if (t->mode == 3)
-        tc::readconv_tc_kernel<3><<<grid, 352, tc::SMEM_BYTES, st>>>(prm);
+        tc::readconv_tc_kernel<3><<<grid, (tc::NG * 5 + 1) * 32, tc::SMEM_BYTES, st>>>(prm);
     else
-        tc::readconv_tc_kernel<1><<<grid, 352, tc::SMEM_BYTES, st>>>(prm);
+        tc::readconv_tc_kernel<1><<<grid, (tc::NG * 5 + 1) * 32, tc::SMEM_BYTES, st>>>(prm);
     return cudaGetLastError();
 }
 

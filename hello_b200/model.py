@@ -301,13 +301,13 @@ class MoEEngine:
 
     def readconv_debug(self, reads: torch.Tensor, phase: int = -1, layout: int = _lib.LAYOUT_RLC, tech: int = 0):
         """Test hook: the fused tensor-core read convolver alone.  Returns (features [R,36,64], dump or None) where the
-        dump holds the post-activation values of layer phase `phase` as [ceil(R/6), 1024, 64] (include/hello_moe.h)."""
+        dump holds the post-activation values of layer phase `phase` as [ceil(R/3), 512, 64] (include/hello_moe.h)."""
         reads = reads.contiguous().to(self.device)
         n = reads.shape[0]
         out = torch.empty((n, 36, 64), dtype=torch.float32, device=self.device)
         dbg = None
         if phase >= 0:
-            dbg = torch.zeros(((n + 5) // 6, 1024, 64), dtype=torch.float32, device=self.device)
+            dbg = torch.zeros(((n + 2) // 3, 512, 64), dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             rc = self.lib.hello_moe_readconv_debug(self.handle, tech, reads.data_ptr(), n, layout, phase, out.data_ptr(),

@@ -63,10 +63,10 @@ def readconv_phase_reference(cfg, params, reads_rlc, tech=0):
 
 
 def readconv_phase_from_dump(dump, phase, n_reads, length):
-    """Undo the kernel's row packing: dump [groups, 1024, 64] -> [R, C, L] for one phase (include/hello_moe.h)."""
+    """Undo the kernel's row packing: dump [groups, 512, 64] -> [R, C, L] for one phase (include/hello_moe.h)."""
     pitch, ch = (160, 16) if phase < 2 else ((80, 32) if phase < 9 else (40, 64))
     out = torch.zeros((n_reads, ch, length))
     for r in range(n_reads):
-        g, i = divmod(r, 6)
+        g, i = divmod(r, 3)
         out[r] = dump[g, i * pitch:i * pitch + length, :ch].t()
     return out

@@ -1,0 +1,121 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/hello_moe.h declares, the ctypes
+structs match the header, the product path refuses to run without a GPU, and the host-side packing logic."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import params_for
+from hello_b200 import _lib, arch, synth, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hello_moe.h")
+
+
+def header_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hello_moe_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    g.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = header_functions()
+    assert len(names) >= 11
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(names) == set(_lib.EXPORTS), "binding and header disagree on the exported functions"
+    lib.hello_moe_abi_version.restype = ctypes.c_int
+    assert lib.hello_moe_abi_version() == _lib.ABI_VERSION
+
+
+def test_ctypes_structs_match_header_layout():
+    # hello_cfg: 12 int32; hello_batch: 4 int64 + 2 int32 + 11 pointers; hello_result: 6 pointers
+    assert ctypes.sizeof(_lib.HelloCfg) == 12 * 4
+    assert ctypes.sizeof(_lib.HelloBatch) == 4 * 8 + 2 * 4 + 11 * 8
+    assert ctypes.sizeof(_lib.HelloResult) == 6 * 8
+    text = open(HEADER).read()
+    for field in ("struct_size", "n_tech", "read_channels", "xattn_present", "has_combiners", "meta_kind",
+                  "feature_length", "precision", "max_chunk_sites"):
+        assert field in text
+    assert [f[0] for f in _lib.HelloCfg._fields_] == ["struct_size", "n_tech", "read_channels", "xattn_present",
+                                                      "has_combiners", "meta_kind", "feature_length", "precision",
+                                                      "max_chunk_sites"]
+
+
+def test_create_rejects_bad_arguments_without_touching_a_gpu():
+    lib = _lib.load()
+    handle = ctypes.c_void_p()
+    cfg = _lib.HelloCfg()
+    cfg.struct_size = 4                       # wrong size -> HELLO_ERR_ARG before any CUDA call
+    buf = (ctypes.c_char * 256)()
+    assert lib.hello_moe_create(buf, 256, ctypes.byref(cfg), 0, ctypes.byref(handle)) == -1
+    assert b"struct_size" in lib.hello_moe_last_error(None)
+    assert lib.hello_moe_launch_count(None) == 0
+    assert lib.hello_moe_workspace_bytes(None, 1, 0, 1, 1) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_a_gpu():
+    from hello_b200 import model
+    cfg = arch.CONFIGS["single_tech"]
+    with pytest.raises(_lib.HelloMoEError):
+        model.MoEEngine(cfg, params_for(cfg))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hello_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+@pytest.mark.parametrize("name", sorted(arch.CONFIGS))
+def test_blob_roundtrip(name):
+    """pack_blob: header, layer records and folded weights are where hello_moe_create expects them."""
+    cfg = arch.CONFIGS[name]
+    params = params_for(cfg)
+    blob = weights.pack_blob(cfg, params)
+    magic, version, n_slots, rec_off, n_rec, data_off, n_floats = struct.unpack_from("<8sIIQQQQ", blob, 0)
+    assert magic == weights.BLOB_MAGIC and version == 1 and n_slots == 10
+    assert rec_off == 128 and data_off == rec_off + n_rec * 128 and data_off % 16 == 0
+    assert len(blob) == data_off + 4 * n_floats
+    first = struct.unpack_from("<10I", blob, 48)
+    count = struct.unpack_from("<10I", blob, 88)
+    nets = cfg.networks()
+    for net, nid in weights.NET_IDS.items():
+        n_layers = len([l for l in nets.get(net, []) if not isinstance(l, arch.Front)])
+        assert count[nid] == n_layers
+    # first conv of read_convolver0: folded weight g*v/|v| stored as [k*cin, cout]
+    rec = np.frombuffer(blob, np.int32, 32, rec_off + first[0] * 128)
+    cin, cout, k = rec[2], rec[3], rec[4]
+    data = np.frombuffer(blob, np.float32, n_floats, data_off)
+    w = data[rec[8]:rec[8] + k * cin * cout].reshape(k * cin, cout)
+    v = params["read_convolver0.network.0.conv1d.weight_v"].numpy().astype(np.float64)
+    g = params["read_convolver0.network.0.conv1d.weight_g"].numpy().astype(np.float64)
+    ref = g * v / np.sqrt((v ** 2).sum(axis=(1, 2), keepdims=True))
+    np.testing.assert_allclose(w, ref.transpose(2, 1, 0).reshape(k * cin, cout), rtol=2e-6, atol=1e-7)
+
+
+def test_cfg_from_state_dict_recognises_every_wiring():
+    for name, cfg in arch.CONFIGS.items():
+        assert weights.cfg_from_state_dict(params_for(cfg)).name == name
+
+
+def test_synthetic_pileups_follow_the_codebook():
+    pl = synth.make_pileups(50, coverage=12, channels=(7,), seed=5)
+    r = pl.reads[0]
+    assert r.dtype == torch.uint8 and r.shape[1:] == (150, 7)
+    assert set(np.unique(r[..., 0].numpy())) <= {0, 30, 100, 180, 250}
+    assert set(np.unique(r[..., 4].numpy())) <= {0, 70, 240}
+    assert set(np.unique(r[..., 6].numpy())) <= {0, 120, 240}
+    sao, aro = pl.site_allele_off.numpy(), pl.allele_read_off[0].numpy()
+    assert sao[0] == 0 and aro[0] == 0 and aro[-1] == r.shape[0] and (np.diff(sao) >= 1).all() and (np.diff(aro) >= 1).all()
