@@ -20,6 +20,7 @@ EXPORTS = (
     "hello_moe_abi_version", "hello_moe_create", "hello_moe_destroy", "hello_moe_last_error",
     "hello_moe_workspace_bytes", "hello_moe_forward", "hello_moe_launch_count", "hello_moe_run_net",
     "hello_moe_profile_enable", "hello_moe_profile_collect", "hello_moe_readconv_debug",
+    "hello_moe_headconv_debug",
 )
 
 
@@ -90,6 +91,9 @@ def load():
     lib.hello_moe_readconv_debug.restype = C.c_int
     lib.hello_moe_readconv_debug.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
                                              C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hello_moe_headconv_debug.restype = C.c_int
+    lib.hello_moe_headconv_debug.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
     if lib.hello_moe_abi_version() != ABI_VERSION:
         raise HelloMoEError("libhello_moe.so ABI %d != binding ABI %d; rebuild" % (lib.hello_moe_abi_version(),
                                                                                  ABI_VERSION))

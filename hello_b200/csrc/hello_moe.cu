@@ -16,6 +16,7 @@
 #include "conv_fp32.cuh"
 #include "misc_kernels.cuh"
 #include "readconv_tc.cuh"
+#include "headconv_tc.cuh"
 
 using namespace hello;
 
@@ -57,6 +58,7 @@ struct hello_moe {
     int read_len = 0, read_ch = 0;   // read convolver output (36, 64)
     int comp_len = 0, comp_ch = 0;   // compressor output (18, 128)
     ReadConvTC* tc[2] = {nullptr, nullptr};
+    HeadConvTC* head[N_NETS] = {};   // fused tcgen05 compressor / xattn / meta_convolver (tensor-core precisions)
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;            // pairs (start, stop), created lazily
     size_t ev_used = 0;
@@ -208,6 +210,14 @@ struct Runner {
         return status == HELLO_OK;
     }
 
+    // fused tcgen05 head (headconv_tc.cuh): compressor / xattn (with in_s: 2a - s front end) / meta_convolver
+    bool head(HeadConvTC* t, const float* in_a, const float* in_s, const int32_t* site_idx, long long n, float* out,
+              long long out_stride, int softmax) {
+        if (dry || n == 0) return true;
+        h->launches++;
+        return check(headconv_tc_launch(t, in_a, in_s, site_idx, n, out, out_stride, softmax, st), "headconv_tc");
+    }
+
     bool segsum(const float* x, float* out, const int32_t* off, long long n_groups, int row_base, long long elems) {
         if (dry || n_groups == 0) return true;
         const int e4 = (int)(elems / 4);
@@ -307,13 +317,21 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
             return false;
         ar.release(m2);
         // compressor (:125)
-        if (!run.run_net(h->nets[NET_CMP0 + t], view_cl(a_feat, h->read_len, h->read_ch), na, c_t[t], nullptr))
+        if (h->head[NET_CMP0 + t]) {
+            if (!run.head(h->head[NET_CMP0 + t], a_feat, nullptr, nullptr, na, c_t[t], 0, 0)) return false;
+        } else if (!run.run_net(h->nets[NET_CMP0 + t], view_cl(a_feat, h->read_len, h->read_ch), na, c_t[t], nullptr)) {
             return false;
+        }
         ar.release(m1);
         // alleles -> sites on the compressed features (:142-147)
         if (!run.segsum(c_t[t], s_t[t], dry ? nullptr : in->d_site_allele_off + ck.s0, ns, (int)ck.a0, comp_e))
             return false;
-        if (cfg.xattn_present[t]) {
+        if (cfg.xattn_present[t] && h->head[NET_X0 + t]) {
+            // 2a - s is formed by the kernel's operand loader
+            if (!run.head(h->head[NET_X0 + t], c_t[t], s_t[t], site_idx, na,
+                          dry ? nullptr : out->d_logits + (long long)t * A_total + ck.a0, 1, 0))
+                return false;
+        } else if (cfg.xattn_present[t]) {
             const size_t m3 = ar.mark();
             float* x = ar.allocf(na * comp_e);
             if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
@@ -341,15 +359,25 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         if (!run.concat2(s_t[0], s_t[1], cat, ns * h->comp_len, cc, cc)) return false;
         if (!run.run_net(h->nets[NET_CB1], view_cl(cat, h->comp_len, 2 * cc), ns, s2, nullptr)) return false;
         ar.release(m);
-        float* x = ar.allocf(na * comp_e);
-        if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
-        if (!run.two_a_minus_s(c2, s2, site_idx, x, na, comp_e)) return false;
-        Runner::GapOut g{dry ? nullptr : out->d_logits + 2LL * A_total + ck.a0, 1, 0};
-        if (!run.run_net(h->nets[NET_X2], view_cl(x, h->comp_len, cc), na, nullptr, &g)) return false;
-        ar.release(m);
+        if (h->head[NET_X2]) {
+            if (!run.head(h->head[NET_X2], c2, s2, site_idx, na, dry ? nullptr : out->d_logits + 2LL * A_total + ck.a0, 1, 0))
+                return false;
+        } else {
+            float* x = ar.allocf(na * comp_e);
+            if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
+            if (!run.two_a_minus_s(c2, s2, site_idx, x, na, comp_e)) return false;
+            Runner::GapOut g{dry ? nullptr : out->d_logits + 2LL * A_total + ck.a0, 1, 0};
+            if (!run.run_net(h->nets[NET_X2], view_cl(x, h->comp_len, cc), na, nullptr, &g)) return false;
+            ar.release(m);
+        }
         if (cfg.meta_kind == HELLO_META_SITE) {
-            Runner::GapOut gm{dry ? nullptr : out->d_meta + 3 * ck.s0, 3, 1};
-            if (!run.run_net(h->nets[NET_META], view_cl(s2, h->comp_len, cc), ns, nullptr, &gm)) return false;
+            if (h->head[NET_META]) {
+                if (!run.head(h->head[NET_META], s2, nullptr, nullptr, ns, dry ? nullptr : out->d_meta + 3 * ck.s0, 3, 1))
+                    return false;
+            } else {
+                Runner::GapOut gm{dry ? nullptr : out->d_meta + 3 * ck.s0, 3, 1};
+                if (!run.run_net(h->nets[NET_META], view_cl(s2, h->comp_len, cc), ns, nullptr, &gm)) return false;
+            }
             meta_done = true;
         }
     }
@@ -529,6 +557,22 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
             }
         }
     }
+    if (cfg->precision != HELLO_PREC_FP32) {
+        // compressor / xattn / meta_convolver as fused tcgen05 kernels
+        std::vector<int> want;
+        for (int t = 0; t < cfg->n_tech; ++t) want.push_back(NET_CMP0 + t);
+        for (int e3 = 0; e3 < 3; ++e3) if (cfg->xattn_present[e3]) want.push_back(NET_X0 + e3);
+        if (cfg->meta_kind == HELLO_META_SITE) want.push_back(NET_META);
+        for (int id : want) {
+            std::string terr;
+            h->head[id] = headconv_tc_create(h->nets[id], h->d_weights, h->h_weights.data(), cfg->precision, terr);
+            if (!h->head[id]) {
+                g_create_error = "hello_moe_create: tensor-core head network: " + terr;
+                hello_moe_destroy(h);
+                return HELLO_ERR_UNSUPPORTED;
+            }
+        }
+    }
     *out = h;
     return HELLO_OK;
 }
@@ -537,6 +581,7 @@ void hello_moe_destroy(hello_moe* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (int t = 0; t < 2; ++t) readconv_tc_destroy(h->tc[t]);
+    for (int n = 0; n < N_NETS; ++n) headconv_tc_destroy(h->head[n]);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->d_weights) cudaFree(h->d_weights);
     delete h;
@@ -691,6 +736,10 @@ int hello_moe_run_net(hello_moe* h, int net_id, const void* d_in, int64_t n_item
         }
         return HELLO_OK;
     }
+    if (h->head[net_id]) {
+        run.head(h->head[net_id], static_cast<const float*>(d_in), nullptr, nullptr, n_items, d_out, co, 0);
+        return run.status;
+    }
     const bool gap = net.back().kind == KIND_GAP_LINEAR;
     Runner::GapOut g{d_out, co, 0};
     run.run_net(net, v, n_items, gap ? nullptr : d_out, gap ? &g : nullptr);
@@ -709,6 +758,22 @@ int hello_moe_readconv_debug(hello_moe* h, int tech, const uint8_t* d_reads, int
                                d_dbg, d_dbg ? phase : -1);
     h->launches++;
     if (e != cudaSuccess) { h->err = std::string("readconv_tc: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }
+    return HELLO_OK;
+}
+
+int hello_moe_headconv_debug(hello_moe* h, int net_id, const float* d_in, int64_t n_items, int32_t phase, float* d_out,
+                             float* d_dbg, void* stream) {
+    if (!h) return HELLO_ERR_ARG;
+    h->err.clear();
+    if (net_id < 0 || net_id >= N_NETS || !h->head[net_id]) { h->err = "no tensor-core head for this network"; return HELLO_ERR_UNSUPPORTED; }
+    if (!d_in || !d_out || n_items < 0) { h->err = "bad buffers"; return HELLO_ERR_ARG; }
+    HeadConvTC* t = h->head[net_id];
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e == cudaSuccess)
+        e = headconv_tc_launch(t, d_in, nullptr, nullptr, n_items, d_out, t->prm.n_out > 0 ? t->prm.n_out : 0, 0,
+                               static_cast<cudaStream_t>(stream), d_dbg, d_dbg ? phase : -1);
+    h->launches++;
+    if (e != cudaSuccess) { h->err = std::string("headconv_tc: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }
     return HELLO_OK;
 }
 

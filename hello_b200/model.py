@@ -316,6 +316,27 @@ class MoEEngine:
         return out, dbg
 
 
+    def headconv_debug(self, net: str, x: torch.Tensor, phase: int = -1):
+        """Test hook: one fused tensor-core head network (compressor / xattn on a combined input / meta_convolver) on
+        fp32 channel-last items.  Returns (output, dump or None); the dump holds the post-activation values of layer
+        phase `phase` as [groups, 256, 256] (include/hello_moe.h)."""
+        nid = weights.NET_IDS[net]
+        x = x.contiguous().float().to(self.device)
+        n, lin, cin = x.shape
+        co, lo = arch.net_out_shape(self.cfg.networks()[net], lin)
+        out = torch.empty((n, lo, co), dtype=torch.float32, device=self.device)
+        per = 6 if cin == 64 else 12
+        dbg = None
+        if phase >= 0:
+            dbg = torch.zeros(((n + per - 1) // per, 256, 256), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.hello_moe_headconv_debug(self.handle, nid, x.data_ptr(), n, phase, out.data_ptr(),
+                                                   dbg.data_ptr() if dbg is not None else None, C.c_void_p(stream))
+        self._check(rc, "hello_moe_headconv_debug")
+        return out, dbg
+
+
 @dataclass
 class HostResult:
     """Per-site results in (pinned) host memory."""

@@ -53,8 +53,9 @@ enum { HELLO_META_NONE = 0,
        HELLO_META_REF = 2 };   /* architectures/meta_convolver_ref.py: input = one-hot reference segment      */
 
 enum { HELLO_PREC_FP32 = 0,    /* fp32 FMA everywhere (CUDA cores)                                            */
-       HELLO_PREC_BF16X3 = 1,  /* read convolver on tcgen05, operands split hi+lo bf16, 3 MMAs, fp32 accum   */
-       HELLO_PREC_BF16 = 2 };  /* read convolver on tcgen05, single bf16 operands, fp32 accum ("fast" mode)  */
+       HELLO_PREC_BF16X3 = 1,  /* read convolver, compressor, xattn and meta_convolver on tcgen05: operands split
+                                  into hi+lo bf16, 3 MMAs per product, fp32 accumulate                        */
+       HELLO_PREC_BF16 = 2 };  /* same kernels with single bf16 operands, fp32 accumulate ("fast" mode)       */
 
 /* Model wiring = which sub-networks MoEAttention holds (python/moe_attention_config_*.py). */
 typedef struct hello_cfg {
@@ -150,6 +151,15 @@ int hello_moe_run_net(hello_moe* h, int net_id, const void* d_in, int64_t n_item
  * fp32 [ceil(n_reads/3), 512, 64]: row index = packed row of the 3-read group (pitch 160/80/40), 64 = channel slots. */
 int hello_moe_readconv_debug(hello_moe* h, int tech, const uint8_t* d_reads, int64_t n_reads, int32_t input_layout,
                              int32_t phase, float* d_out, float* d_dbg, void* stream);
+
+/* Test hook for the fused tensor-core head networks (HELLO_PREC_BF16X3 / HELLO_PREC_BF16 handles only; net_id 2,3
+ * compressor, 4,5,6 xattn on an already combined 2a-s input, 9 meta_convolver): run the kernel on n_items fp32
+ * channel-last items and, when d_dbg is not NULL, dump the post-activation values of layer phase `phase`
+ * (0: 1x1 conv, 1-2: stride-2 block conv a / block output, 3-6: the two identity blocks) as fp32
+ * [groups, 256, 256]: a group is 6 (compressor) or 12 items, row = packed row of the group (pitch 40 / 20 in phase 0,
+ * half of it afterwards), column = channel. d_out as for hello_moe_run_net. */
+int hello_moe_headconv_debug(hello_moe* h, int net_id, const float* d_in, int64_t n_items, int32_t phase, float* d_out,
+                             float* d_dbg, void* stream);
 
 #ifdef __cplusplus
 }

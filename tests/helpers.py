@@ -70,3 +70,32 @@ def readconv_phase_from_dump(dump, phase, n_reads, length):
         g, i = divmod(r, 3)
         out[r] = dump[g, i * pitch:i * pitch + length, :ch].t()
     return out
+
+
+def head_phase_reference(cfg, params, net_name, x_lc):
+    """Post-activation fp32 values of the 7 layer phases of a fused head network (oracle layers), each [n, C, L]:
+    0 the 1x1 conv, then (conv_a, block output) of the three residual blocks.  x_lc: [n, L, C] channel-last."""
+    from oracle import hello_oracle as O
+    net = O.OracleModel(cfg, params).nets[net_name]
+    L = net.layers
+    x = x_lc.transpose(1, 2).float()
+    outs = []
+    with torch.no_grad():
+        x = net._conv(x, L[0][1], L[0][2]); outs.append(x)
+        for li in range(1, 4):
+            _, layer, (wa, wb, ws) = L[li]
+            t = net._conv(x, layer.conv_a, wa); outs.append(t)
+            sh = net._conv(x, layer.conv_s, ws) if ws is not None else x
+            x = net._conv(t, layer.conv_b, wb) + sh; outs.append(x)
+    return outs
+
+
+def head_phase_from_dump(dump, phase, n_items, cin, ch, length):
+    """Undo the head kernel's row packing: dump [groups, 256, 256] -> [n, C, L] for one phase (include/hello_moe.h)."""
+    per = 6 if cin == 64 else 12
+    pitch = (40 if cin == 64 else 20) // (1 if phase == 0 else 2)
+    out = torch.zeros((n_items, ch, length))
+    for r in range(n_items):
+        g, i = divmod(r, per)
+        out[r] = dump[g, i * pitch:i * pitch + length, :ch].t()
+    return out

@@ -3,8 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (GOLDEN_CASES, flat_result, load_golden, params_for, readconv_phase_from_dump,
-                     readconv_phase_reference)
+from helpers import (GOLDEN_CASES, flat_result, head_phase_from_dump, head_phase_reference, load_golden, params_for,
+                     readconv_phase_from_dump, readconv_phase_reference)
 from hello_b200 import arch, synth, weights
 
 pytestmark = pytest.mark.gpu
@@ -136,6 +136,51 @@ def test_readconv_tc_is_deterministic(gpu):
     a, _ = eng.readconv_debug(pl.reads[0])
     b, _ = eng.readconv_debug(pl.reads[0])
     assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------- fused tcgen05 head networks
+HEAD_CASES = [("single_tech", "compressor0", (15, 36, 64)), ("single_tech", "xattn0", (29, 18, 128)),
+              ("hybrid_full", "meta", (14, 18, 128)), ("hybrid_full", "xattn2", (3, 18, 128))]
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("cfg_name,net_name,shape", HEAD_CASES)
+def test_headconv_tc_every_layer(gpu, cfg_name, net_name, shape, precision):
+    """Each of the 7 layer phases of the fused head kernel against the oracle's fp32 layer outputs, then the
+    network output (features, logit, or the meta head's pre-softmax linear output)."""
+    cfg = arch.CONFIGS[cfg_name]
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(shape, generator=g) * 40).float()
+    eng = net_for(gpu, cfg, precision).engine
+    ref = head_phase_reference(cfg, params_for(cfg), net_name, x)
+    for ph in range(7):
+        out, dump = eng.headconv_debug(net_name, x, ph)
+        got = head_phase_from_dump(dump.cpu(), ph, shape[0], shape[2], ref[ph].shape[1], ref[ph].shape[2])
+        scale = max(1.0, ref[ph].abs().max().item())
+        err = (got - ref[ph]).abs().max().item()
+        assert err < TC_LAYER_REL[precision] * scale, (ph, err, scale)
+    full = oracle_for(cfg).nets[net_name](x.transpose(1, 2))
+    got = out.cpu().transpose(1, 2) if full.dim() == 3 else out.cpu().reshape(full.shape)
+    scale = max(1.0, ref[-1].abs().max().item())
+    assert (got - full).abs().max().item() < TC_LAYER_REL[precision] * scale
+
+
+@pytest.mark.parametrize("n_items", [1, 5, 6, 7, 12, 13, 25, 1801])
+def test_headconv_tc_ragged_counts(gpu, n_items):
+    """Any item count (partial groups, an empty second group, several waves of work items): run_net routes the
+    head networks through the tensor-core kernel and agrees with the fp32 CUDA-core path."""
+    cfg = arch.CONFIGS["single_tech"]
+    g = torch.Generator().manual_seed(n_items)
+    tcn, f32 = net_for(gpu, cfg, "bf16x3").engine, net_for(gpu, cfg, "fp32").engine
+    for net_name, shape in (("compressor0", (n_items, 36, 64)), ("xattn0", (n_items, 18, 128))):
+        x = (torch.randn(shape, generator=g) * 30).float()
+        a = tcn.run_net(net_name, x)
+        b, _ = tcn.headconv_debug(net_name, x)
+        assert torch.equal(a, b)
+        ref = f32.run_net(net_name, x)
+        scale = max(1.0, ref.abs().max().item()) if net_name.startswith("compressor") else 200.0
+        assert (a - ref).abs().max().item() < TC_LAYER_REL["bf16x3"] * scale, net_name
+        assert torch.equal(a, tcn.run_net(net_name, x)), "deterministic"
 
 
 # ------------------------------------------------------------------------------------------------ whole forward
