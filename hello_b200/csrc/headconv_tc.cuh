@@ -92,10 +92,6 @@ struct HeadParams {
 
 enum { OUT_NAT = 0, OUT_EO = 1, OUT_FINAL = 2 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // fp32 rows of one group -> phase-0 operand (bf16 hi + lo chunk arrays); invalid rows are written as zeros
 template <int MODE, int C>
 __device__ __forceinline__ void load_input(uint8_t* act, const HeadParams& prm, long long i0, int n, int tid) {
@@ -420,6 +416,8 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
             const bool active = n_items > i0;
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
+                // (no turn-taking between the two compressor groups as in the read convolver: a layer's weights do not
+                // fit the ring, and both groups must drain every ring slot before it can be refilled)
                 if (active) {
                     ptx::mbar_wait(bar(BAR_ACT + g), ar_n & 1u);
                     ++ar_n;
@@ -446,10 +444,10 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                     if (nx < n_items) {
                         const long long cnt = min((long long)(NGRP * G), n_items - nx);
                         const uint32_t per = Gm::L * C * 4;
-                        prefetch_l2(prm.in_a + nx * (Gm::L * C), (uint32_t)cnt * per);
+                        ptx::prefetch_l2(prm.in_a + nx * (Gm::L * C), (uint32_t)cnt * per);
                         if (prm.in_s) {
                             const long long s0 = __ldg(prm.site_idx + nx), s1 = __ldg(prm.site_idx + nx + cnt - 1);
-                            prefetch_l2(prm.in_s + s0 * (Gm::L * C), (uint32_t)(s1 - s0 + 1) * per);
+                            ptx::prefetch_l2(prm.in_s + s0 * (Gm::L * C), (uint32_t)(s1 - s0 + 1) * per);
                         }
                     }
                 }

@@ -65,7 +65,7 @@ constexpr uint32_t OFF_ACT = 0;
 constexpr uint32_t OFF_W = NG * ACT_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_W + 2 * WSLOT_BYTES;
 constexpr uint32_t OFF_BAR = OFF_BIAS + N_BIAS * 4;
-constexpr uint32_t N_BARS = 4 + 2 * NG;           // w_full[2], w_empty[2], act_ready[NG], acc_full[NG]
+constexpr uint32_t N_BARS = 4 + 3 * NG;           // w_full[2], w_empty[2], act_ready[NG], acc_full[NG], token[NG]
 constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -229,10 +229,14 @@ __device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float*
         const bool valid = (i < n_reads) && (p < LV3);
         const int nxt = tile * 4 + wq + 1;
         constexpr int N_SLICES = T2 * 4;
+        // row m+1 of the last lane lives in the next warp slice: lane c fetches its column-c value once and
+        // broadcasts it (the very last row of the group is padding, any finite value will do)
+        const float xv = xchg[(nxt < N_SLICES ? nxt : 0) * 32 + lane];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-            float e1 = __shfl_down_sync(0xffffffffu, e[c], 1);
-            if (lane == 31) e1 = nxt < N_SLICES ? xchg[nxt * 32 + c] : e[c];
+            const float dn = __shfl_down_sync(0xffffffffu, e[c], 1);
+            const float nb = __shfl_sync(0xffffffffu, xv, c);
+            const float e1 = lane == 31 ? nb : dn;
             const float x = fmaxf(fmaxf(fmaxf(e[c], o[c]), e1) + bias[c], 0.f);
             o[c] = valid ? x : 0.f;
         }
@@ -262,16 +266,19 @@ __device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float*
 // so one MMA costs two integer adds plus the issue.  Runs on a converged warp with warp-uniform values.
 //   AO0..2  byte offset of the A operand of each tap (row shift / even-odd array selection)
 //   A_LBO   distance between 8-channel chunk arrays;  A_LO / W_LO  distance to the "lo" copies
-template <int MODE, int N, int NTAPS, int K16, bool A_HAS_LO, uint32_t AO0, uint32_t AO1, uint32_t AO2, uint32_t A_LBO,
-          uint32_t A_LO, uint32_t B_OFF, uint32_t W_LO>
+//   PART 0: every operand combination except the last (hi*hi);  PART 1: hi*hi only.  The issuer hands the tensor-pipe
+//   token to the next group between the two parts, so the hand-over latency hides behind this group's last third.
+template <int MODE, int PART, int N, int NTAPS, int K16, bool A_HAS_LO, uint32_t AO0, uint32_t AO1, uint32_t AO2,
+          uint32_t A_LBO, uint32_t A_LO, uint32_t B_OFF, uint32_t W_LO>
 __device__ __forceinline__ void issue_tile(uint32_t act_lo, uint32_t w_lo, uint32_t d) {
     constexpr uint32_t AO[3] = {AO0 >> 4, AO1 >> 4, AO2 >> 4};
     constexpr int NC = MODE == 3 ? (A_HAS_LO ? 3 : 2) : 1;
+    constexpr int C_HI = PART == 0 ? NC - 1 : 0, C_LO = PART == 0 ? 1 : 0;
     constexpr uint32_t idesc = ptx::idesc_bf16_m128(N);
     const uint32_t a0 = act_lo | (((A_LBO >> 4) & 0x3FFFu) << 16);
     const uint32_t b0 = (w_lo + (B_OFF >> 4)) | ((((uint32_t)N * 16u) >> 4) << 16);
 #pragma unroll
-    for (int combo = NC - 1; combo >= 0; --combo) {          // small terms first: lo*hi, hi*lo, then hi*hi
+    for (int combo = C_HI; combo >= C_LO; --combo) {         // small terms first: lo*hi, hi*lo, then hi*hi
 #pragma unroll
         for (int t = 0; t < NTAPS; ++t) {
 #pragma unroll
@@ -285,43 +292,53 @@ __device__ __forceinline__ void issue_tile(uint32_t act_lo, uint32_t w_lo, uint3
 }
 
 // All MMAs of layer phase `ph` for one group.  act_lo / w_lo: shared-memory addresses >> 4; d0: TMEM base of the group.
-template <int MODE>
+template <int MODE, int PART>
 __device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_lo, uint32_t d0) {
     if (ph == 0) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T1; ++t)
-            issue_tile<MODE, 16, 2, 1, false, 0, 32, 0, X_STRIDE, 0, 0, WHI_L1>(act_lo + t * 128u, w_lo, d0 + t * 16u);
+            issue_tile<MODE, PART, 16, 2, 1, false, 0, 32, 0, X_STRIDE, 0, 0, WHI_L1>(act_lo + t * 128u, w_lo, d0 + t * 16u);
     } else if (ph == 1) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T1; ++t)
-            issue_tile<MODE, 16, 3, 1, true, 0, 16, 32, A1_CH, 2 * A1_CH, 0, WHI_L2>(act_lo + t * 128u, w_lo, d0 + t * 16u);
+            issue_tile<MODE, PART, 16, 3, 1, true, 0, 16, 32, A1_CH, 2 * A1_CH, 0, WHI_L2>(act_lo + t * 128u, w_lo, d0 + t * 16u);
     } else if (ph == 2) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T2; ++t) {
             // E[m] = conv at position 2p (taps: even[p], odd[p], even[p+1]);  O[m] = conv at 2p+1
-            issue_tile<MODE, 32, 3, 1, true, 0, A2_ARR, 16, 2 * A2_ARR, 4 * A2_ARR, 0, WHI_L3>(act_lo + t * 128u, w_lo, d0 + t * 64u);
-            issue_tile<MODE, 32, 3, 1, true, A2_ARR, 16, A2_ARR + 16, 2 * A2_ARR, 4 * A2_ARR, 0, WHI_L3>(act_lo + t * 128u, w_lo,
+            issue_tile<MODE, PART, 32, 3, 1, true, 0, A2_ARR, 16, 2 * A2_ARR, 4 * A2_ARR, 0, WHI_L3>(act_lo + t * 128u, w_lo, d0 + t * 64u);
+            issue_tile<MODE, PART, 32, 3, 1, true, A2_ARR, 16, A2_ARR + 16, 2 * A2_ARR, 4 * A2_ARR, 0, WHI_L3>(act_lo + t * 128u, w_lo,
                                                                                                       d0 + t * 64u + 32u);
         }
     } else if (ph < 9) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T2; ++t)
-            issue_tile<MODE, 32, 3, 2, true, 0, 16, 32, S2_CH, 4 * S2_CH, 0, WHI_S2>(act_lo + t * 128u, w_lo, d0 + t * 32u);
+            issue_tile<MODE, PART, 32, 3, 2, true, 0, 16, 32, S2_CH, 4 * S2_CH, 0, WHI_S2>(act_lo + t * 128u, w_lo, d0 + t * 32u);
     } else if (ph == 9) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T3; ++t) {
             // stride 2: x[2p-1], x[2p], x[2p+1] = odd[p-1], even[p], odd[p]; the 1x1 shortcut reads even[p] and
             // accumulates straight into the residual columns
-            issue_tile<MODE, 64, 3, 2, true, E3_ARR, 16, E3_ARR + 16, 2 * E3_ARR, 8 * E3_ARR, 0, WHI_RC>(act_lo + t * 128u, w_lo,
+            issue_tile<MODE, PART, 64, 3, 2, true, E3_ARR, 16, E3_ARR + 16, 2 * E3_ARR, 8 * E3_ARR, 0, WHI_RC>(act_lo + t * 128u, w_lo,
                                                                                                   d0 + t * 64u);
-            issue_tile<MODE, 64, 1, 2, true, 16, 0, 0, 2 * E3_ARR, 8 * E3_ARR, RC_SHORTCUT_B_OFF, WHI_RC>(act_lo + t * 128u, w_lo,
+            issue_tile<MODE, PART, 64, 1, 2, true, 16, 0, 0, 2 * E3_ARR, 8 * E3_ARR, RC_SHORTCUT_B_OFF, WHI_RC>(act_lo + t * 128u, w_lo,
                                                                                                    d0 + RES_COL + t * 64u);
         }
     } else {
 #pragma unroll 1
         for (uint32_t t = 0; t < T3; ++t)
-            issue_tile<MODE, 64, 3, 4, true, 0, 16, 32, S3_CH, 8 * S3_CH, 0, WHI_S3>(act_lo + t * 128u, w_lo, d0 + t * 64u);
+            issue_tile<MODE, PART, 64, 3, 4, true, 0, 16, 32, S3_CH, 8 * S3_CH, 0, WHI_S3>(act_lo + t * 128u, w_lo, d0 + t * 64u);
     }
+}
+
+// Timeline hook (dbg_phase == TRACE_PHASE): CTA 0 stamps clock64() for its first TRACE_ITEMS work items into the debug
+// buffer as int64 [item][group][phase][4] = {issue start, issue end, accumulators seen by the epilogue, epilogue end}.
+constexpr int TRACE_PHASE = -2, TRACE_ITEMS = 16;
+__device__ __forceinline__ long long* trace_slot(const TcParams& prm, int item, int g) {
+    if (!prm.dbg || prm.dbg_phase != TRACE_PHASE || blockIdx.x != 0) return nullptr;
+    const int li = item / (int)gridDim.x;
+    if (li >= TRACE_ITEMS) return nullptr;
+    return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * NG + g) * N_PHASES) * 4;
 }
 
 template <int MODE>
@@ -331,16 +348,19 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
     const int lane = threadIdx.x & 31;
     float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
     const uint32_t bar0 = ptx::smem_u32(smem + OFF_BAR);
-    // barriers: 0,1 w_full[slot]  2,3 w_empty[slot]  4.. act_ready[group]  4+NG.. acc_full[group]
+    // barriers: 0,1 w_full[slot]  2,3 w_empty[slot]  4.. act_ready[group]  4+NG.. acc_full[group]  4+2NG.. token[group]
     auto bar = [&](int k) { return bar0 + 8u * k; };
-    constexpr int BAR_ACT = 4, BAR_ACC = 4 + NG;
+    constexpr int BAR_ACT = 4, BAR_ACC = 4 + NG, BAR_TOK = 4 + 2 * NG;
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(bar(0), 1); ptx::mbar_init(bar(1), 1);
         ptx::mbar_init(bar(2), NG); ptx::mbar_init(bar(3), NG);        // released by every group's issuer
-        for (int g = 0; g < NG; ++g) { ptx::mbar_init(bar(BAR_ACT + g), 128); ptx::mbar_init(bar(BAR_ACC + g), 1); }
+        for (int g = 0; g < NG; ++g) {
+            ptx::mbar_init(bar(BAR_ACT + g), 128); ptx::mbar_init(bar(BAR_ACC + g), 1); ptx::mbar_init(bar(BAR_TOK + g), 1);
+        }
         ptx::fence_mbar_init();
+        ptx::mbar_arrive(bar(BAR_TOK));                                // group 0 issues first
     }
     for (int i = threadIdx.x; i < N_BIAS; i += blockDim.x) s_bias[i] = __ldg(prm.bias + i);
     {   // every byte an MMA can read must hold a finite bf16 (zero weights multiply the padding channels)
@@ -373,11 +393,13 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
             ptx::fence_proxy_async();
             ptx::mbar_arrive(bar(BAR_ACT + g));
             float* gout = prm.out + r0 * (long long)(LOUT * COUT);
+            long long* tr = trace_slot(prm, item, g);
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
                 ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
                 ++acc_n;
                 ptx::tc_fence_after();
+                if (tr && tid == 0) tr[ph * 4 + 2] = clock64();
                 float* dbg = (prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * NG + g) * (T1 * 128 * 64) : nullptr;
                 if (ph == 0) {
                     epi_conv<MODE, 16, T1, P1, LV1, false, false, false, OUT_NAT, 0>(
@@ -416,6 +438,7 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
                         epi_conv<MODE, 64, T3, P3, LV4, true, false, false, OUT_GLOBAL, 1>(
                             act, tl, 64, b, nullptr, n, 0, 0, gout, dbg, wrow, lane);
                 }
+                if (tr && tid == 0) tr[ph * 4 + 3] = clock64();
                 if (ph + 1 < N_PHASES) {
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
@@ -427,12 +450,13 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
         // ===================================================== MMA issuers: warp 4*NG + g serves group g.
         // The whole warp runs the (warp-uniform) loop; one elected lane issues each tcgen05.mma / commit.
         const int g = warp - 4 * NG;
-        uint32_t w_n = 0, ar_n = 0;
+        uint32_t w_n = 0, ar_n = 0, tok_n = 0;
         const uint32_t act_lo = (ptx::smem_u32(smem + OFF_ACT) + g * ACT_BYTES) >> 4;
         const uint32_t w0_lo = ptx::smem_u32(smem + OFF_W) >> 4;
         const uint32_t d0 = tmem_base + g * (2 * RES_COL);
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
             const int n = (int)max(0LL, min((long long)G, R - ((long long)item * NG + g) * G));
+            long long* tr = trace_slot(prm, item, g);
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
                 const uint32_t slot = w_n & 1u;
@@ -442,12 +466,32 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
                 if (n > 0) {
                     ptx::mbar_wait(bar(BAR_ACT + g), ar_n & 1u);         // this group's operand is written
                     ++ar_n;
+                }
+                // The groups take turns on the tensor pipe (token passed round-robin): one group's layer executes
+                // as a block and its epilogue then overlaps the other groups' MMAs.  Without the turn order the
+                // four issue streams interleave in the pipe's FIFO, all accumulators complete together and all
+                // epilogues run together with the tensor pipe idle.
+                ptx::mbar_wait(bar(BAR_TOK + g), tok_n & 1u);
+                ++tok_n;
+                if (n > 0) {
                     ptx::tc_fence_after();
-                    issue_phase<MODE>(ph, act_lo, w0_lo + slot * (WSLOT_BYTES >> 4), d0);
+                    if (tr && lane == 0) tr[ph * 4 + 0] = clock64();
+                    const uint32_t w_lo = w0_lo + slot * (WSLOT_BYTES >> 4);
+                    if (MODE == 3) {
+                        issue_phase<MODE, 0>(ph, act_lo, w_lo, d0);
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(bar(BAR_TOK + (g + 1) % NG));
+                        __syncwarp();
+                    }
+                    issue_phase<MODE, 1>(ph, act_lo, w_lo, d0);
                     ptx::tc_commit(bar(BAR_ACC + g));                    // accumulators ready -> epilogue
                     ptx::tc_commit(bar(2 + slot));                       // weight slot no longer read by this group
+                    if (tr && lane == 0) tr[ph * 4 + 1] = clock64();
+                    __syncwarp();
+                    if (MODE != 3 && lane == 0) ptx::mbar_arrive(bar(BAR_TOK + (g + 1) % NG));
                 } else if (lane == 0) {
                     ptx::mbar_arrive(bar(2 + slot));
+                    ptx::mbar_arrive(bar(BAR_TOK + (g + 1) % NG));
                 }
                 __syncwarp();
                 ++w_n;
@@ -459,6 +503,15 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
             uint32_t w_n = 0;
             const uint32_t w0 = ptx::smem_u32(smem + OFF_W);
             for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+                {   // pull the next work item's pileup rows into L2 while this one computes
+                    const long long nr0 = (long long)(item + gridDim.x) * (NG * G);
+                    if (nr0 < R) {
+                        const long long bytes = min((long long)(NG * G), R - nr0) * (LIN * prm.channels);
+                        const uint8_t* p = prm.reads + nr0 * (LIN * prm.channels);
+                        const uint8_t* p16 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(15));
+                        ptx::prefetch_l2(p16, (uint32_t)(((p - p16) + bytes) & ~15LL));
+                    }
+                }
 #pragma unroll 1
                 for (int ph = 0; ph < N_PHASES; ++ph) {
                     const uint32_t slot = w_n & 1u;
