@@ -15,17 +15,24 @@
 //   Stride-2 layers (MaxPool1d(3,2), the stride-2 residual block) read an even/odd de-interleaved copy that the
 //   previous epilogue writes, which turns stride 2 back into unit row shifts.
 //
-// Pipeline (one CTA per SM, 21 warps, four independent groups of 3 reads in flight)
-//   warps 0-15       epilogue warpgroup of read group warp/4: TMEM -> registers (bias, ReLU, residual, max-pool),
-//                    split to bf16 hi (+lo), write the next layer's operand back to shared memory IN PLACE, keep
-//                    the fp32 residual stream in TMEM.
-//   warps 16-19      MMA issuer of group warp-16: fully unrolled tcgen05.mma sequences (operand offsets are
-//                    immediates, uniform datapath), one elected lane issues.  The tensor pipe works on some groups
-//                    while the CUDA cores run the other groups' epilogues.
-//   warp 20          one thread streams the weights of the next layer from L2 into a 2-slot ring with
+// Pipeline (one CTA per SM, 16 warps, three independent groups of 3 reads in flight)
+//   warps 0-11       epilogue warpgroup of read group warp/4 (thread = packed row = TMEM lane): TMEM -> registers
+//                    (bias, ReLU, residual, max-pool), split to bf16 hi (+lo), write the next layer's operand back
+//                    to shared memory IN PLACE.  The fp32 residual stream stays on chip: half of its 64 columns in
+//                    the thread's registers, half in TMEM.
+//   warps 12-14      MMA issuer of group warp-12: fully unrolled tcgen05.mma sequences (operand offsets are
+//                    immediates, uniform datapath), one elected lane issues.  The groups take turns on the tensor
+//                    pipe (token, handed over before a layer's last tap), so one group's layer executes as a block
+//                    while the other groups' epilogues run on the CUDA cores.
+//   warp 15          one thread streams the weights of the next layer from L2 into a 2-slot ring with
 //                    cp.async.bulk (TMA unit) while the current layer computes.
-//   Precision: HELLO_PREC_BF16X3 splits activations and weights into bf16 hi+lo and issues hi*hi + hi*lo + lo*hi
-//   (fp32 accumulate) -> ~2^-17 relative error per product; HELLO_PREC_BF16 issues hi*hi only.
+//   Precision: HELLO_PREC_BF16X3 splits activations and weights into bf16 hi+lo (fp32 accumulate, ~2^-17 relative
+//   error per product).  tcgen05.mma with both operands in shared memory costs (4096 + 32*N)/128 cycles for a
+//   128 x N x 16 tile (measured, tools/mma_bench.cu): the 4 KB activation operand dominates at N = 16..64.  The
+//   three products are therefore issued as TWO instructions: A_hi x [W_hi | W_lo] (the weight halves stacked
+//   along N, accumulators D_hh | D_hl) and A_lo x W_hi (into D_hh); the epilogue adds the two halves.  That takes
+//   128 accumulator columns per group, which is why only three groups (3 x 160 TMEM columns) are in flight and
+//   half of the residual moved to registers.  HELLO_PREC_BF16 issues A_hi x W_hi only.
 #pragma once
 #include <algorithm>
 #include <cstring>
@@ -40,15 +47,20 @@ namespace hello {
 namespace tc {
 
 constexpr int G = 3;                           // reads per group
-constexpr int NG = 4;                          // groups in flight per CTA (one item = NG*G = 12 reads)
+constexpr int NG = 3;                          // groups in flight per CTA (one item = NG*G = 9 reads)
+constexpr int EW = 4;                          // epilogue warps per group (one per TMEM lane quadrant)
 constexpr int P1 = 160, P2 = 80, P3 = 40;      // row pitch of one read at the three resolutions
 constexpr int ROWS1 = G * P1, ROWS2 = G * P2, ROWS3 = G * P3;
 constexpr int T1 = 4, T2 = 2, T3 = 1;          // 128-row MMA tiles per group
-constexpr uint32_t RES_COL = 64;               // TMEM columns [0,64) of a group: accumulators, [64,128): fp32 residual
+// TMEM columns of a group: [0,128) accumulators, [128,160) the second half of the fp32 residual stream (the first half
+// lives in the epilogue threads' registers: 3 x 192 columns would not fit the 512 of an SM)
+constexpr uint32_t RES_COL = 128;
+constexpr uint32_t GRP_COLS = 160;
 constexpr int LIN = 150, LV1 = 148, LV2 = 146, LV3 = 71, LV4 = 36;   // valid lengths
 constexpr int LOUT = 36, COUT = 64;
 constexpr int N_PHASES = 17;
 constexpr int N_BIAS = 832;
+constexpr int THREADS = (NG * EW + NG + 1) * 32;
 
 // byte layout of one group's activation buffer (offsets relative to its base)
 constexpr uint32_t X_STRIDE = (ROWS1 + 8) * 16;   // layer-1 operand: X0[m] = x[m], X1[m] = x[m+1]  (8 ch, hi only)
@@ -72,7 +84,8 @@ static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 static_assert(2 * A1_CH * 2 <= XCHG_OFF && 8 * A2_ARR <= XCHG_OFF && 8 * S2_CH <= XCHG_OFF &&
               16 * E3_ARR <= XCHG_OFF && 16 * S3_CH <= XCHG_OFF && 2 * X_STRIDE <= XCHG_OFF, "activation layouts");
 static_assert(T1 * 128 >= ROWS1 && T2 * 128 >= ROWS2 && T3 * 128 >= ROWS3, "tiles cover the packed rows");
-static_assert(T1 * 16 <= RES_COL && T2 * 32 <= RES_COL && T3 * 64 <= RES_COL && NG * 2 * RES_COL <= 512, "TMEM budget");
+static_assert(T1 * 32 <= RES_COL && T2 * 64 <= RES_COL && T3 * 128 <= RES_COL && RES_COL + 32 <= GRP_COLS &&
+              NG * GRP_COLS <= 512, "TMEM budget");
 
 // bias table (floats)
 constexpr int B_L1 = 0, B_L2 = 16, B_L3 = 32, B_S2 = 64, B_RCA = 256, B_RCS = 320, B_RCB = 384, B_S3 = 448;
@@ -90,10 +103,10 @@ struct TcParams {
     int n_items, channels, layout, dbg_phase;
 };
 
-// bytes of the bf16 "hi" weights of each phase kind (the "lo" copy follows at this offset in the slot)
-constexpr uint32_t WHI_L1 = 2 * 16 * 32, WHI_L2 = 3 * 16 * 32, WHI_L3 = 3 * 32 * 32, WHI_S2 = 6 * 32 * 32,
-                   WHI_RC = 8 * 64 * 32, WHI_S3 = 12 * 64 * 32;
-constexpr uint32_t RC_SHORTCUT_B_OFF = 6 * 64 * 32;
+// Packed weights.  One B unit covers one tap and 16 input channels: [2 chunks of 8 channels][rows][8 bf16] with
+// rows = the N "hi" weight rows followed (bf16x3 only) by the N "lo" rows.  Units of a phase are stored tap-major.
+template <int MODE> __host__ __device__ constexpr uint32_t unit_bytes(int n) { return (MODE == 3 ? 2u : 1u) * n * 32u; }
+constexpr int UNITS_L1 = 2, UNITS_L2 = 3, UNITS_L3 = 3, UNITS_S2 = 6, UNITS_RC = 8, UNITS_S3 = 12;
 
 enum { OUT_NAT = 0, OUT_EO = 1, OUT_GLOBAL = 2 };
 
@@ -118,7 +131,7 @@ __device__ __forceinline__ void store_chunk8(uint8_t* p, uint32_t lo_delta, cons
 // uint8 pileup rows of one group -> layer-1 operand (two row-shifted copies, bf16, channels padded to 8)
 __device__ __forceinline__ void load_input(uint8_t* act, const uint8_t* __restrict__ reads, long long r0, int n_reads,
                                            int C, int layout, int tid) {
-    for (int m = tid; m < ROWS1 + 8; m += 128) {
+    for (int m = tid; m < ROWS1 + 8; m += EW * 32) {
         const int i = m / P1, p = m - i * P1;
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (i < n_reads && p < LIN) {
@@ -140,53 +153,75 @@ __device__ __forceinline__ void load_input(uint8_t* act, const uint8_t* __restri
     if (tid == 0) *reinterpret_cast<uint4*>(act + X_STRIDE + (uint32_t)(ROWS1 + 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
 }
 
-// Epilogue of one convolution for one group.  Thread = row (TMEM lane); loops over tiles and 32-column blocks.
-//   y = relu(acc + bias) [+ resid (+ bias2)], invalid rows forced to zero, written as the next operand.
-template <int MODE, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID, int OUT,
-          int LEAD>
-__device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, int d_stride, const float* bias,
-                                         const float* bias2, int n_reads, uint32_t out_stride, uint32_t out_lo,
-                                         float* __restrict__ gout, float* __restrict__ dbg, int wrow, int lane) {
-    constexpr int CB = N < 32 ? N : 32;
+// Epilogue of one convolution for one group.  Thread = row (TMEM lane).  The accumulator tiles are cut into four
+// blocks of 16 columns (TILES * N / 16 == 4 for every layer).  The fp32 residual of blocks 0-1 lives in `rr`
+// (registers), that of blocks 2-3 in TMEM.
+//   y = relu(acc_hh [+ acc_hl] + bias) [+ resid (+ bias2)], invalid rows forced to zero, written as the next operand.
+//   STACK: the layer was issued in the stacked form (two accumulator halves per tile).
+//   MOVE_SC (stride-2 block): the shortcut accumulators sit next to conv a's in columns [64,128); move them to
+//   the residual storage before the next layer reuses the accumulator columns.
+template <int MODE, bool STACK, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID,
+          bool MOVE_SC, int OUT, int LEAD>
+__device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float* bias, const float* bias2, int n_reads,
+                                         uint32_t out_stride, uint32_t out_lo, float* __restrict__ gout,
+                                         float* __restrict__ dbg, int wrow, int lane, float (&rr)[32]) {
+    static_assert(TILES * N == 64, "four 16-column blocks per layer");
     constexpr int ROWS = G * PITCH;
-    for (int tile = 0; tile < TILES; ++tile) {
+    constexpr int BPT = N / 16;                       // blocks per tile
+    constexpr bool TWO = MODE == 3 && STACK;
+    constexpr uint32_t TILE_COLS = TWO ? 2 * N : N;
+#pragma unroll
+    for (int blk = 0; blk < 4; ++blk) {
+        const int tile = blk / BPT, c0 = (blk - tile * BPT) * 16;
         const int m = tile * 128 + wrow + lane;
         const int i = m / PITCH, p = m - i * PITCH;
         const bool valid = (i < n_reads) && (p < LVALID);
         const bool in_buf = m < ROWS;
+        float v[16];
+        float w[TWO ? 16 : 1];
+        float r[(RESID || MOVE_SC) ? 16 : 1];
+        ptx::tmem_ld16(tl + tile * TILE_COLS + c0, v);
+        if (TWO) ptx::tmem_ld16(tl + tile * TILE_COLS + N + c0, w);
+        if (RESID && blk >= 2) ptx::tmem_ld16(tl + RES_COL + (blk - 2) * 16, r);
+        if (MOVE_SC) ptx::tmem_ld16(tl + 64 + c0, r);
+        ptx::tmem_wait_ld();
+        if (RESID && blk < 2) {
 #pragma unroll
-        for (int cb = 0; cb < N / CB; ++cb) {
-            float v[CB];
-            float r[RESID ? CB : 1];
-            ptx::tmem_ld<CB>(tl + tile * d_stride + cb * CB, v);
-            if (RESID) ptx::tmem_ld<CB>(tl + RES_COL + tile * N + cb * CB, r);
-            ptx::tmem_wait_ld();
+            for (int c = 0; c < 16; ++c) r[c] = rr[blk * 16 + c];
+        }
 #pragma unroll
-            for (int c = 0; c < CB; ++c) {
-                float x = fmaxf(v[c] + bias[cb * CB + c], 0.f);
-                if (RESID) x += RES_BIAS ? (r[c] + bias2[cb * CB + c]) : r[c];
-                v[c] = valid ? x : 0.f;
+        for (int c = 0; c < 16; ++c) {
+            float x = TWO ? v[c] + w[c] : v[c];
+            x = fmaxf(x + bias[c0 + c], 0.f);
+            if (RESID) x += RES_BIAS ? (r[c] + bias2[c0 + c]) : r[c];
+            v[c] = valid ? x : 0.f;
+        }
+        if (WRITE_RESID || MOVE_SC) {
+            if (blk < 2) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) rr[blk * 16 + c] = MOVE_SC ? r[c] : v[c];
+            } else {
+                ptx::tmem_st16(tl + RES_COL + (blk - 2) * 16, MOVE_SC ? r : v);
             }
-            if (WRITE_RESID) ptx::tmem_st32(tl + RES_COL + tile * N + cb * CB, v);
-            if (dbg) {
+        }
+        if (dbg) {
 #pragma unroll
-                for (int c = 0; c < CB; ++c) dbg[m * 64 + cb * CB + c] = v[c];
+            for (int c = 0; c < 16; ++c) dbg[m * 64 + c0 + c] = v[c];
+        }
+        if (OUT == OUT_GLOBAL) {
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(gout + ((long long)i * LOUT + p) * COUT + c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
             }
-            if (OUT == OUT_GLOBAL) {
-                if (valid) {
-                    float4* dst = reinterpret_cast<float4*>(gout + ((long long)i * LOUT + p) * COUT + cb * CB);
+        } else if (in_buf) {
 #pragma unroll
-                    for (int q = 0; q < CB / 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                }
-            } else if (in_buf) {
-#pragma unroll
-                for (int q = 0; q < CB / 8; ++q) {
-                    const int c8 = cb * (CB / 8) + q;
-                    uint8_t* dst = OUT == OUT_NAT
-                                       ? act + c8 * out_stride + (uint32_t)(m + LEAD) * 16
-                                       : act + (c8 * 2 + (m & 1)) * out_stride + (uint32_t)((m >> 1) + LEAD) * 16;
-                    store_chunk8<MODE>(dst, out_lo, v + 8 * q);
-                }
+            for (int q = 0; q < 2; ++q) {
+                const int c8 = c0 / 8 + q;
+                uint8_t* dst = OUT == OUT_NAT
+                                   ? act + c8 * out_stride + (uint32_t)(m + LEAD) * 16
+                                   : act + (c8 * 2 + (m & 1)) * out_stride + (uint32_t)((m >> 1) + LEAD) * 16;
+                store_chunk8<MODE>(dst, out_lo, v + 8 * q);
             }
         }
     }
@@ -199,15 +234,18 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, int d_stride
             if (MODE == 3) *reinterpret_cast<uint4*>(act + a * out_stride + out_lo) = z;
         }
     }
-    if (WRITE_RESID) ptx::tmem_wait_st();
+    if (WRITE_RESID || MOVE_SC) ptx::tmem_wait_st();
 }
 
-// Epilogue of stem conv 3 fused with MaxPool1d(3,2): E[m] = conv(2p), O[m] = conv(2p+1) sit in two accumulators,
-// conv(2p+2) = E[m+1] comes from the neighbouring lane (shared-memory exchange across warp / tile borders).
+// Epilogue of stem conv 3 fused with MaxPool1d(3,2): E[m] = conv(2p), O[m] = conv(2p+1) sit in two accumulators
+// (each the sum of its three operand products), conv(2p+2) = E[m+1] comes from the neighbouring lane (shared-memory
+// exchange across warp / tile borders).  Starts the residual stream: tile 0 -> registers, tile 1 -> TMEM.
 template <int MODE>
 __device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float* bias, int n_reads, int g, int wq,
-                                         int lane, float* __restrict__ dbg) {
+                                         int lane, float* __restrict__ dbg, float (&rr)[32]) {
     float* xchg = reinterpret_cast<float*>(act + XCHG_OFF);
+    constexpr int N_SLICES = T2 * 4;
+#pragma unroll
     for (int tile = 0; tile < T2; ++tile) {
         float e[32];
         ptx::tmem_ld32(tl + tile * 64, e);
@@ -218,37 +256,45 @@ __device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float*
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
         }
     }
-    ptx::named_bar_sync(1 + g, 128);
-    for (int tile = T2 - 1; tile >= 0; --tile) {     // descending: the residual columns alias later tiles' accumulators
-        float e[32], o[32];
-        ptx::tmem_ld32(tl + tile * 64, e);
-        ptx::tmem_ld32(tl + tile * 64 + 32, o);
-        ptx::tmem_wait_ld();
+    ptx::named_bar_sync(1 + g, EW * 32);
+#pragma unroll
+    for (int tile = 0; tile < T2; ++tile) {
         const int m = tile * 128 + wq * 32 + lane;
         const int i = m / P2, p = m - i * P2;
         const bool valid = (i < n_reads) && (p < LV3);
         const int nxt = tile * 4 + wq + 1;
-        constexpr int N_SLICES = T2 * 4;
         // row m+1 of the last lane lives in the next warp slice: lane c fetches its column-c value once and
         // broadcasts it (the very last row of the group is padding, any finite value will do)
         const float xv = xchg[(nxt < N_SLICES ? nxt : 0) * 32 + lane];
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const float dn = __shfl_down_sync(0xffffffffu, e[c], 1);
-            const float nb = __shfl_sync(0xffffffffu, xv, c);
-            const float e1 = lane == 31 ? nb : dn;
-            const float x = fmaxf(fmaxf(fmaxf(e[c], o[c]), e1) + bias[c], 0.f);
-            o[c] = valid ? x : 0.f;
-        }
-        ptx::tmem_st32(tl + RES_COL + tile * 32, o);
-        if (dbg) {
+        for (int hb = 0; hb < 2; ++hb) {
+            float e[16], o[16];
+            ptx::tmem_ld16(tl + tile * 64 + hb * 16, e);
+            ptx::tmem_ld16(tl + tile * 64 + 32 + hb * 16, o);
+            ptx::tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) dbg[m * 64 + c] = o[c];
-        }
-        if (m < ROWS2) {
+            for (int c = 0; c < 16; ++c) {
+                const float dn = __shfl_down_sync(0xffffffffu, e[c], 1);
+                const float nb = __shfl_sync(0xffffffffu, xv, hb * 16 + c);
+                const float e1 = lane == 31 ? nb : dn;
+                const float x = fmaxf(fmaxf(fmaxf(e[c], o[c]), e1) + bias[hb * 16 + c], 0.f);
+                o[c] = valid ? x : 0.f;
+            }
+            if (tile == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                store_chunk8<MODE>(act + q * S2_CH + (uint32_t)(m + 1) * 16, 4 * S2_CH, o + 8 * q);
+                for (int c = 0; c < 16; ++c) rr[hb * 16 + c] = o[c];
+            } else {
+                ptx::tmem_st16(tl + RES_COL + hb * 16, o);
+            }
+            if (dbg) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) dbg[m * 64 + hb * 16 + c] = o[c];
+            }
+            if (m < ROWS2) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+                    store_chunk8<MODE>(act + (hb * 2 + q) * S2_CH + (uint32_t)(m + 1) * 16, 4 * S2_CH, o + 8 * q);
+            }
         }
     }
     if (wq == 0 && lane == 0) {
@@ -265,27 +311,38 @@ __device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float*
 // All tcgen05.mma of one 128-row tile of one convolution, fully unrolled: every operand offset is an immediate,
 // so one MMA costs two integer adds plus the issue.  Runs on a converged warp with warp-uniform values.
 //   AO0..2  byte offset of the A operand of each tap (row shift / even-odd array selection)
-//   A_LBO   distance between 8-channel chunk arrays;  A_LO / W_LO  distance to the "lo" copies
-//   PART 0: every operand combination except the last (hi*hi);  PART 1: hi*hi only.  The issuer hands the tensor-pipe
-//   token to the next group between the two parts, so the hand-over latency hides behind this group's last third.
-template <int MODE, int PART, int N, int NTAPS, int K16, bool A_HAS_LO, uint32_t AO0, uint32_t AO1, uint32_t AO2,
-          uint32_t A_LBO, uint32_t A_LO, uint32_t B_OFF, uint32_t W_LO>
+//   A_LBO   distance between 8-channel chunk arrays;  A_LO  distance to the "lo" copy of the activations
+//   STACK   bf16x3 as two instructions: A_hi x [W_hi | W_lo] -> D[0,2N), A_lo x W_hi -> D[0,N);
+//           otherwise three instructions into D[0,N) (used where the accumulator columns are scarce)
+//   PART 0: every tap but the last;  PART 1: the last tap.  The issuer hands the tensor-pipe token to the other
+//   group between the two parts, so the hand-over latency hides behind this group's last third.
+template <int MODE, int PART, bool STACK, int N, int NTAPS, int K16, bool A_HAS_LO, uint32_t AO0, uint32_t AO1,
+          uint32_t AO2, uint32_t A_LBO, uint32_t A_LO, uint32_t B_UNIT0>
 __device__ __forceinline__ void issue_tile(uint32_t act_lo, uint32_t w_lo, uint32_t d) {
     constexpr uint32_t AO[3] = {AO0 >> 4, AO1 >> 4, AO2 >> 4};
-    constexpr int NC = MODE == 3 ? (A_HAS_LO ? 3 : 2) : 1;
-    constexpr int C_HI = PART == 0 ? NC - 1 : 0, C_LO = PART == 0 ? 1 : 0;
-    constexpr uint32_t idesc = ptx::idesc_bf16_m128(N);
+    constexpr uint32_t BROWS = MODE == 3 ? 2 * N : N;
+    constexpr uint32_t UNIT = BROWS * 32;
+    constexpr uint32_t idesc_n = ptx::idesc_bf16_m128(N);
+    constexpr uint32_t idesc_2n = ptx::idesc_bf16_m128(2 * N);
+    constexpr int T_BEGIN = PART == 0 ? 0 : NTAPS - 1, T_END = PART == 0 ? NTAPS - 1 : NTAPS;
     const uint32_t a0 = act_lo | (((A_LBO >> 4) & 0x3FFFu) << 16);
-    const uint32_t b0 = (w_lo + (B_OFF >> 4)) | ((((uint32_t)N * 16u) >> 4) << 16);
+    const uint32_t b0 = (w_lo + ((B_UNIT0 * UNIT) >> 4)) | (((BROWS * 16u) >> 4) << 16);
 #pragma unroll
-    for (int combo = C_HI; combo >= C_LO; --combo) {         // small terms first: lo*hi, hi*lo, then hi*hi
+    for (int t = T_BEGIN; t < T_END; ++t) {
 #pragma unroll
-        for (int t = 0; t < NTAPS; ++t) {
-#pragma unroll
-            for (int j = 0; j < K16; ++j) {
-                const uint32_t a = a0 + AO[t] + (combo == 2 ? (A_LO >> 4) : 0u) + (uint32_t)j * ((2u * A_LBO) >> 4);
-                const uint32_t b = b0 + (combo == 1 ? (W_LO >> 4) : 0u) + (uint32_t)(t * K16 + j) * (((uint32_t)N * 32u) >> 4);
-                ptx::mma_bf16_ss(d, a, b, idesc, (combo == NC - 1 && t == 0 && j == 0) ? 0u : 1u);
+        for (int j = 0; j < K16; ++j) {
+            const uint32_t a = a0 + AO[t] + (uint32_t)j * ((2u * A_LBO) >> 4);
+            const uint32_t b = b0 + (uint32_t)(t * K16 + j) * (UNIT >> 4);
+            const uint32_t acc = (t == 0 && j == 0) ? 0u : 1u;
+            if (MODE != 3) {
+                ptx::mma_bf16_ss(d, a, b, idesc_n, acc);
+            } else if (STACK) {
+                ptx::mma_bf16_ss(d, a, b, idesc_2n, acc);
+                if (A_HAS_LO) ptx::mma_bf16_ss(d, a + (A_LO >> 4), b, idesc_n, 1u);
+            } else {
+                ptx::mma_bf16_ss(d, a, b, idesc_n, acc);
+                ptx::mma_bf16_ss(d, a, b + ((N * 16u) >> 4), idesc_n, 1u);
+                if (A_HAS_LO) ptx::mma_bf16_ss(d, a + (A_LO >> 4), b, idesc_n, 1u);
             }
         }
     }
@@ -294,40 +351,35 @@ __device__ __forceinline__ void issue_tile(uint32_t act_lo, uint32_t w_lo, uint3
 // All MMAs of layer phase `ph` for one group.  act_lo / w_lo: shared-memory addresses >> 4; d0: TMEM base of the group.
 template <int MODE, int PART>
 __device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_lo, uint32_t d0) {
+    constexpr uint32_t TC16 = MODE == 3 ? 32 : 16, TC32 = MODE == 3 ? 64 : 32;   // accumulator columns per tile
     if (ph == 0) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T1; ++t)
-            issue_tile<MODE, PART, 16, 2, 1, false, 0, 32, 0, X_STRIDE, 0, 0, WHI_L1>(act_lo + t * 128u, w_lo, d0 + t * 16u);
+            issue_tile<MODE, PART, true, 16, 2, 1, false, 0, 32, 0, X_STRIDE, 0, 0>(act_lo + t * 128u, w_lo, d0 + t * TC16);
     } else if (ph == 1) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T1; ++t)
-            issue_tile<MODE, PART, 16, 3, 1, true, 0, 16, 32, A1_CH, 2 * A1_CH, 0, WHI_L2>(act_lo + t * 128u, w_lo, d0 + t * 16u);
+            issue_tile<MODE, PART, true, 16, 3, 1, true, 0, 16, 32, A1_CH, 2 * A1_CH, 0>(act_lo + t * 128u, w_lo, d0 + t * TC16);
     } else if (ph == 2) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T2; ++t) {
-            // E[m] = conv at position 2p (taps: even[p], odd[p], even[p+1]);  O[m] = conv at 2p+1
-            issue_tile<MODE, PART, 32, 3, 1, true, 0, A2_ARR, 16, 2 * A2_ARR, 4 * A2_ARR, 0, WHI_L3>(act_lo + t * 128u, w_lo, d0 + t * 64u);
-            issue_tile<MODE, PART, 32, 3, 1, true, A2_ARR, 16, A2_ARR + 16, 2 * A2_ARR, 4 * A2_ARR, 0, WHI_L3>(act_lo + t * 128u, w_lo,
-                                                                                                      d0 + t * 64u + 32u);
+            // E[m] = conv at position 2p (taps: even[p], odd[p], even[p+1]);  O[m] = conv at 2p+1.  Two accumulators
+            // per tile already fill the group's columns, so the three products go into the same 32 columns.
+            issue_tile<MODE, PART, false, 32, 3, 1, true, 0, A2_ARR, 16, 2 * A2_ARR, 4 * A2_ARR, 0>(act_lo + t * 128u, w_lo, d0 + t * 64u);
+            issue_tile<MODE, PART, false, 32, 3, 1, true, A2_ARR, 16, A2_ARR + 16, 2 * A2_ARR, 4 * A2_ARR, 0>(act_lo + t * 128u, w_lo,
+                                                                                                         d0 + t * 64u + 32u);
         }
     } else if (ph < 9) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T2; ++t)
-            issue_tile<MODE, PART, 32, 3, 2, true, 0, 16, 32, S2_CH, 4 * S2_CH, 0, WHI_S2>(act_lo + t * 128u, w_lo, d0 + t * 32u);
+            issue_tile<MODE, PART, true, 32, 3, 2, true, 0, 16, 32, S2_CH, 4 * S2_CH, 0>(act_lo + t * 128u, w_lo, d0 + t * TC32);
     } else if (ph == 9) {
-#pragma unroll 1
-        for (uint32_t t = 0; t < T3; ++t) {
-            // stride 2: x[2p-1], x[2p], x[2p+1] = odd[p-1], even[p], odd[p]; the 1x1 shortcut reads even[p] and
-            // accumulates straight into the residual columns
-            issue_tile<MODE, PART, 64, 3, 2, true, E3_ARR, 16, E3_ARR + 16, 2 * E3_ARR, 8 * E3_ARR, 0, WHI_RC>(act_lo + t * 128u, w_lo,
-                                                                                                  d0 + t * 64u);
-            issue_tile<MODE, PART, 64, 1, 2, true, 16, 0, 0, 2 * E3_ARR, 8 * E3_ARR, RC_SHORTCUT_B_OFF, WHI_RC>(act_lo + t * 128u, w_lo,
-                                                                                                   d0 + RES_COL + t * 64u);
-        }
+        // stride 2: x[2p-1], x[2p], x[2p+1] = odd[p-1], even[p], odd[p]; the 1x1 shortcut reads even[p].  Both results
+        // must sit in the accumulator columns at once (conv a in [0,64), shortcut in [64,128)): unstacked form.
+        issue_tile<MODE, PART, false, 64, 3, 2, true, E3_ARR, 16, E3_ARR + 16, 2 * E3_ARR, 8 * E3_ARR, 0>(act_lo, w_lo, d0);
+        issue_tile<MODE, PART, false, 64, 1, 2, true, 16, 0, 0, 2 * E3_ARR, 8 * E3_ARR, 6>(act_lo, w_lo, d0 + 64u);
     } else {
-#pragma unroll 1
-        for (uint32_t t = 0; t < T3; ++t)
-            issue_tile<MODE, PART, 64, 3, 4, true, 0, 16, 32, S3_CH, 8 * S3_CH, 0, WHI_S3>(act_lo + t * 128u, w_lo, d0 + t * 64u);
+        issue_tile<MODE, PART, true, 64, 3, 4, true, 0, 16, 32, S3_CH, 8 * S3_CH, 0>(act_lo, w_lo, d0);
     }
 }
 
@@ -342,7 +394,7 @@ __device__ __forceinline__ long long* trace_slot(const TcParams& prm, int item, 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const __grid_constant__ TcParams prm) {
+__global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_constant__ TcParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
     const int lane = threadIdx.x & 31;
@@ -351,13 +403,14 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
     // barriers: 0,1 w_full[slot]  2,3 w_empty[slot]  4.. act_ready[group]  4+NG.. acc_full[group]  4+2NG.. token[group]
     auto bar = [&](int k) { return bar0 + 8u * k; };
     constexpr int BAR_ACT = 4, BAR_ACC = 4 + NG, BAR_TOK = 4 + 2 * NG;
+    constexpr int W_EPI = NG * EW;                                             // epilogue warps
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(bar(0), 1); ptx::mbar_init(bar(1), 1);
         ptx::mbar_init(bar(2), NG); ptx::mbar_init(bar(3), NG);        // released by every group's issuer
         for (int g = 0; g < NG; ++g) {
-            ptx::mbar_init(bar(BAR_ACT + g), 128); ptx::mbar_init(bar(BAR_ACC + g), 1); ptx::mbar_init(bar(BAR_TOK + g), 1);
+            ptx::mbar_init(bar(BAR_ACT + g), EW * 32); ptx::mbar_init(bar(BAR_ACC + g), 1); ptx::mbar_init(bar(BAR_TOK + g), 1);
         }
         ptx::fence_mbar_init();
         ptx::mbar_arrive(bar(BAR_TOK));                                // group 0 issues first
@@ -367,7 +420,7 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
         uint4* z = reinterpret_cast<uint4*>(smem);
         for (uint32_t i = threadIdx.x; i < OFF_BIAS / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (warp == 4 * NG) {
+    if (warp == W_EPI + NG) {
         ptx::tmem_alloc(ptx::smem_u32(smem + OFF_TMEM), 512);
         ptx::tmem_relinquish();
     }
@@ -378,12 +431,16 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
     const long long R = prm.n_reads;
 
-    if (warp < 4 * NG) {
-        // ===================================================== epilogue warpgroups (group g = warp / 4)
-        const int g = warp >> 2, wq = warp & 3, tid = threadIdx.x & 127, wrow = wq * 32;
+    if (warp < W_EPI) {
+        // ===================================================== epilogue warps (group g = warp / EW)
+        const int g = warp / EW, wq = warp & 3, wrow = wq * 32;
+        const int tid = threadIdx.x - g * (EW * 32);
         uint8_t* act = smem + OFF_ACT + g * ACT_BYTES;
-        const uint32_t tl = tmem_base + ((uint32_t)wrow << 16) + g * (2 * RES_COL);
+        const uint32_t tl = tmem_base + ((uint32_t)wrow << 16) + g * GRP_COLS;
         uint32_t acc_n = 0;
+        float rr[32];                                  // first half of this row's fp32 residual stream
+#pragma unroll
+        for (int c = 0; c < 32; ++c) rr[c] = 0.f;
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
             const long long r0 = ((long long)item * NG + g) * G;
             const int n = (int)max(0LL, min((long long)G, R - r0));
@@ -402,41 +459,41 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
                 if (tr && tid == 0) tr[ph * 4 + 2] = clock64();
                 float* dbg = (prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * NG + g) * (T1 * 128 * 64) : nullptr;
                 if (ph == 0) {
-                    epi_conv<MODE, 16, T1, P1, LV1, false, false, false, OUT_NAT, 0>(
-                        act, tl, 16, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane);
+                    epi_conv<MODE, true, 16, T1, P1, LV1, false, false, false, false, OUT_NAT, 0>(
+                        act, tl, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr);
                 } else if (ph == 1) {
-                    epi_conv<MODE, 16, T1, P1, LV2, false, false, false, OUT_EO, 0>(
-                        act, tl, 16, s_bias + B_L2, nullptr, n, A2_ARR, 4 * A2_ARR, nullptr, dbg, wrow, lane);
+                    epi_conv<MODE, true, 16, T1, P1, LV2, false, false, false, false, OUT_EO, 0>(
+                        act, tl, s_bias + B_L2, nullptr, n, A2_ARR, 4 * A2_ARR, nullptr, dbg, wrow, lane, rr);
                 } else if (ph == 2) {
-                    epi_pool<MODE>(act, tl, s_bias + B_L3, n, g, wq, lane, dbg);
+                    epi_pool<MODE>(act, tl, s_bias + B_L3, n, g, wq, lane, dbg, rr);
                 } else if (ph < 9) {
                     const float* b = s_bias + B_S2 + (ph - 3) * 32;
                     if ((ph - 3) % 2 == 0)
-                        epi_conv<MODE, 32, T2, P2, LV3, false, false, false, OUT_NAT, 1>(
-                            act, tl, 32, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane);
+                        epi_conv<MODE, true, 32, T2, P2, LV3, false, false, false, false, OUT_NAT, 1>(
+                            act, tl, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr);
                     else if (ph < 8)
-                        epi_conv<MODE, 32, T2, P2, LV3, true, false, true, OUT_NAT, 1>(
-                            act, tl, 32, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane);
+                        epi_conv<MODE, true, 32, T2, P2, LV3, true, false, true, false, OUT_NAT, 1>(
+                            act, tl, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr);
                     else
-                        epi_conv<MODE, 32, T2, P2, LV3, true, false, false, OUT_EO, 1>(
-                            act, tl, 32, b, nullptr, n, E3_ARR, 8 * E3_ARR, nullptr, dbg, wrow, lane);
+                        epi_conv<MODE, true, 32, T2, P2, LV3, true, false, false, false, OUT_EO, 1>(
+                            act, tl, b, nullptr, n, E3_ARR, 8 * E3_ARR, nullptr, dbg, wrow, lane, rr);
                 } else if (ph == 9) {
-                    epi_conv<MODE, 64, T3, P3, LV4, false, false, false, OUT_NAT, 1>(
-                        act, tl, 64, s_bias + B_RCA, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane);
+                    epi_conv<MODE, false, 64, T3, P3, LV4, false, false, false, true, OUT_NAT, 1>(
+                        act, tl, s_bias + B_RCA, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr);
                 } else if (ph == 10) {
-                    epi_conv<MODE, 64, T3, P3, LV4, true, true, true, OUT_NAT, 1>(
-                        act, tl, 64, s_bias + B_RCB, s_bias + B_RCS, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane);
+                    epi_conv<MODE, true, 64, T3, P3, LV4, true, true, true, false, OUT_NAT, 1>(
+                        act, tl, s_bias + B_RCB, s_bias + B_RCS, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr);
                 } else {
                     const float* b = s_bias + B_S3 + (ph - 11) * 64;
                     if ((ph - 11) % 2 == 0)
-                        epi_conv<MODE, 64, T3, P3, LV4, false, false, false, OUT_NAT, 1>(
-                            act, tl, 64, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane);
+                        epi_conv<MODE, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1>(
+                            act, tl, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr);
                     else if (ph < 16)
-                        epi_conv<MODE, 64, T3, P3, LV4, true, false, true, OUT_NAT, 1>(
-                            act, tl, 64, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane);
+                        epi_conv<MODE, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1>(
+                            act, tl, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr);
                     else
-                        epi_conv<MODE, 64, T3, P3, LV4, true, false, false, OUT_GLOBAL, 1>(
-                            act, tl, 64, b, nullptr, n, 0, 0, gout, dbg, wrow, lane);
+                        epi_conv<MODE, true, 64, T3, P3, LV4, true, false, false, false, OUT_GLOBAL, 1>(
+                            act, tl, b, nullptr, n, 0, 0, gout, dbg, wrow, lane, rr);
                 }
                 if (tr && tid == 0) tr[ph * 4 + 3] = clock64();
                 if (ph + 1 < N_PHASES) {
@@ -446,30 +503,30 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
                 }
             }
         }
-    } else if (warp < 5 * NG) {
-        // ===================================================== MMA issuers: warp 4*NG + g serves group g.
+    } else if (warp < W_EPI + NG) {
+        // ===================================================== MMA issuers: warp W_EPI + g serves group g.
         // The whole warp runs the (warp-uniform) loop; one elected lane issues each tcgen05.mma / commit.
-        const int g = warp - 4 * NG;
+        const int g = warp - W_EPI;
         uint32_t w_n = 0, ar_n = 0, tok_n = 0;
         const uint32_t act_lo = (ptx::smem_u32(smem + OFF_ACT) + g * ACT_BYTES) >> 4;
         const uint32_t w0_lo = ptx::smem_u32(smem + OFF_W) >> 4;
-        const uint32_t d0 = tmem_base + g * (2 * RES_COL);
+        const uint32_t d0 = tmem_base + g * GRP_COLS;
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
             const int n = (int)max(0LL, min((long long)G, R - ((long long)item * NG + g) * G));
             long long* tr = trace_slot(prm, item, g);
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
                 const uint32_t slot = w_n & 1u;
-                // Both issuers wait for the slot (even one whose group is empty in this item): the slot is
-                // released only when both have passed it, which keeps them in lockstep with the producer.
+                // Every issuer waits for the slot (even one whose group is empty in this item): the slot is released
+                // only when all have passed it, which keeps them in lockstep with the producer.
                 ptx::mbar_wait(bar(slot), (w_n >> 1) & 1u);              // this layer's weights have landed
                 if (n > 0) {
                     ptx::mbar_wait(bar(BAR_ACT + g), ar_n & 1u);         // this group's operand is written
                     ++ar_n;
                 }
                 // The groups take turns on the tensor pipe (token passed round-robin): one group's layer executes
-                // as a block and its epilogue then overlaps the other groups' MMAs.  Without the turn order the
-                // four issue streams interleave in the pipe's FIFO, all accumulators complete together and all
+                // as a block and its epilogue then overlaps the other group's MMAs.  Without the turn order the
+                // issue streams interleave in the pipe's FIFO, all accumulators complete together and all
                 // epilogues run together with the tensor pipe idle.
                 ptx::mbar_wait(bar(BAR_TOK + g), tok_n & 1u);
                 ++tok_n;
@@ -477,18 +534,14 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
                     ptx::tc_fence_after();
                     if (tr && lane == 0) tr[ph * 4 + 0] = clock64();
                     const uint32_t w_lo = w0_lo + slot * (WSLOT_BYTES >> 4);
-                    if (MODE == 3) {
-                        issue_phase<MODE, 0>(ph, act_lo, w_lo, d0);
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(bar(BAR_TOK + (g + 1) % NG));
-                        __syncwarp();
-                    }
+                    issue_phase<MODE, 0>(ph, act_lo, w_lo, d0);
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(bar(BAR_TOK + (g + 1) % NG));
+                    __syncwarp();
                     issue_phase<MODE, 1>(ph, act_lo, w_lo, d0);
                     ptx::tc_commit(bar(BAR_ACC + g));                    // accumulators ready -> epilogue
                     ptx::tc_commit(bar(2 + slot));                       // weight slot no longer read by this group
                     if (tr && lane == 0) tr[ph * 4 + 1] = clock64();
-                    __syncwarp();
-                    if (MODE != 3 && lane == 0) ptx::mbar_arrive(bar(BAR_TOK + (g + 1) % NG));
                 } else if (lane == 0) {
                     ptx::mbar_arrive(bar(2 + slot));
                     ptx::mbar_arrive(bar(BAR_TOK + (g + 1) % NG));
@@ -528,7 +581,7 @@ __global__ void __launch_bounds__((NG * 5 + 1) * 32, 1) readconv_tc_kernel(const
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 4 * NG) ptx::tmem_dealloc(tmem_base, 512);
+    if (warp == W_EPI + NG) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -591,54 +644,51 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     t->mode = precision == HELLO_PREC_BF16X3 ? 3 : 1;
     std::memset(&t->prm, 0, sizeof(t->prm));
 
-    // One B unit = [2 chunks][n][8] bf16 for (tap, k16 step j): element (chunk c, row n, e) = W[n][ci = 16j+8c+e][tap].
+    // One B unit covers (tap, k16 step j): [2 chunks][rows][8] bf16, rows = the cout "hi" rows followed (bf16x3) by the
+    // cout "lo" rows; element (chunk c, row n, e) = W[n][ci = 16j+8c+e][tap].
     // `stem1` packs layer 1 instead: unit u covers real taps 2u (chunk 0) and 2u+1 (chunk 1), e = channel (zero padded).
-    auto pack_phase = [&](int ph, std::vector<std::pair<HostConv, bool>> convs) {
-        std::vector<uint16_t> hi, lo;
+    auto pack_phase = [&](int ph, std::vector<std::pair<HostConv, bool>> convs, int expect_units) {
+        std::vector<uint16_t> buf;
+        int units = 0, cout = convs[0].first.cout;
         for (auto& cv : convs) {
             const HostConv& c = cv.first;
             const bool stem1 = cv.second;
+            if (c.cout != cout) return false;
             const int units_t = stem1 ? 2 : c.k, k16 = stem1 ? 1 : c.cin / 16;
             for (int tp = 0; tp < units_t; ++tp)
-                for (int j = 0; j < k16; ++j)
+                for (int j = 0; j < k16; ++j, ++units)
                     for (int ch = 0; ch < 2; ++ch)
-                        for (int n = 0; n < c.cout; ++n)
-                            for (int e = 0; e < 8; ++e) {
-                                float w = 0.f;
-                                if (stem1) {
-                                    const int tap = 2 * tp + ch;
-                                    if (tap < c.k && e < c.cin) w = c.w[(size_t)(tap * c.cin + e) * c.cout + n];
-                                } else {
-                                    const int ci = 16 * j + 8 * ch + e;
-                                    w = c.w[(size_t)(tp * c.cin + ci) * c.cout + n];
+                        for (int part = 0; part < parts; ++part)
+                            for (int n = 0; n < c.cout; ++n)
+                                for (int e = 0; e < 8; ++e) {
+                                    float w = 0.f;
+                                    if (stem1) {
+                                        const int tap = 2 * tp + ch;
+                                        if (tap < c.k && e < c.cin) w = c.w[(size_t)(tap * c.cin + e) * c.cout + n];
+                                    } else {
+                                        const int ci = 16 * j + 8 * ch + e;
+                                        w = c.w[(size_t)(tp * c.cin + ci) * c.cout + n];
+                                    }
+                                    const uint16_t h = bf16_rne(w);
+                                    buf.push_back(part == 0 ? h : bf16_rne(w - bf16_to_float(h)));
                                 }
-                                const uint16_t h = bf16_rne(w);
-                                hi.push_back(h);
-                                lo.push_back(bf16_rne(w - bf16_to_float(h)));
-                            }
         }
         t->prm.w_src[ph] = (uint32_t)blob.size();
-        t->prm.w_bytes[ph] = (uint32_t)(hi.size() * 2 * parts);
-        const uint32_t w_bytes = t->prm.w_bytes[ph];
-        const uint32_t expect_hi = ph == 0 ? WHI_L1 : ph == 1 ? WHI_L2 : ph == 2 ? WHI_L3 : ph < 9 ? WHI_S2 : ph == 9 ? WHI_RC : WHI_S3;
-        if (hi.size() * 2 != expect_hi) return false;
-        const uint8_t* ph_ = reinterpret_cast<const uint8_t*>(hi.data());
-        blob.insert(blob.end(), ph_, ph_ + hi.size() * 2);
-        if (parts == 2) {
-            const uint8_t* pl = reinterpret_cast<const uint8_t*>(lo.data());
-            blob.insert(blob.end(), pl, pl + lo.size() * 2);
-        }
-        return w_bytes <= WSLOT_BYTES && w_bytes % 16 == 0;
+        t->prm.w_bytes[ph] = (uint32_t)(buf.size() * 2);
+        const uint8_t* pb = reinterpret_cast<const uint8_t*>(buf.data());
+        blob.insert(blob.end(), pb, pb + buf.size() * 2);
+        return units == expect_units && t->prm.w_bytes[ph] == (uint32_t)(units * parts * cout * 32) &&
+               t->prm.w_bytes[ph] <= WSLOT_BYTES && t->prm.w_bytes[ph] % 16 == 0;
     };
     auto copy_bias = [&](const HostConv& c, int off) { for (int i = 0; i < c.cout; ++i) bias[off + i] = c.b[i]; };
 
     bool fit = true;
     // stem
-    fit &= pack_phase(0, {{hc(net[0].a), true}});
+    fit &= pack_phase(0, {{hc(net[0].a), true}}, UNITS_L1);
     copy_bias(hc(net[0].a), B_L1);
-    fit &= pack_phase(1, {{hc(net[1].a), false}});
+    fit &= pack_phase(1, {{hc(net[1].a), false}}, UNITS_L2);
     copy_bias(hc(net[1].a), B_L2);
-    fit &= pack_phase(2, {{hc(net[2].a), false}});
+    fit &= pack_phase(2, {{hc(net[2].a), false}}, UNITS_L3);
     copy_bias(hc(net[2].a), B_L3);
     // three residual blocks at 32 channels
     for (int r = 0; r < 3; ++r) {
@@ -646,22 +696,22 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
         for (int h2 = 0; h2 < 2; ++h2) {
             const int ph = 3 + 2 * r + h2;
             const HostConv c = hc(h2 ? L.b : L.a);
-            fit &= pack_phase(ph, {{c, false}});
+            fit &= pack_phase(ph, {{c, false}}, UNITS_S2);
             copy_bias(c, B_S2 + (ph - 3) * 32);
         }
     }
     // stride-2 block 32 -> 64: conv_a and the 1x1 shortcut read the de-interleaved stage-2 output
-    fit &= pack_phase(9, {{hc(net[7].a), false}, {hc(net[7].s), false}});
+    fit &= pack_phase(9, {{hc(net[7].a), false}, {hc(net[7].s), false}}, UNITS_RC);
     copy_bias(hc(net[7].a), B_RCA);
     copy_bias(hc(net[7].s), B_RCS);
-    fit &= pack_phase(10, {{hc(net[7].b), false}});
+    fit &= pack_phase(10, {{hc(net[7].b), false}}, UNITS_S3);
     copy_bias(hc(net[7].b), B_RCB);
     for (int r = 0; r < 3; ++r) {
         const LayerDesc& L = net[8 + r];
         for (int h2 = 0; h2 < 2; ++h2) {
             const int ph = 11 + 2 * r + h2;
             const HostConv c = hc(h2 ? L.b : L.a);
-            fit &= pack_phase(ph, {{c, false}});
+            fit &= pack_phase(ph, {{c, false}}, UNITS_S3);
             copy_bias(c, B_S3 + (ph - 11) * 64);
         }
     }
@@ -713,9 +763,9 @@ static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long 
     prm.n_items = (int)items;
     const int grid = (int)std::min<long long>(items, t->sm_count);
     if (t->mode == 3)
-        tc::readconv_tc_kernel<3><<<grid, (tc::NG * 5 + 1) * 32, tc::SMEM_BYTES, st>>>(prm);
+        tc::readconv_tc_kernel<3><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
     else
-        tc::readconv_tc_kernel<1><<<grid, (tc::NG * 5 + 1) * 32, tc::SMEM_BYTES, st>>>(prm);
+        tc::readconv_tc_kernel<1><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
     return cudaGetLastError();
 }
 

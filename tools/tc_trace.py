@@ -16,14 +16,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from hello_b200 import arch, model, weights          # noqa: E402
 
-NG, NPH, ITEMS = 4, 17, 16
+NG, NPH, ITEMS = 3, 17, 16
 
 if __name__ == "__main__":
     prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
     per_cta = int(sys.argv[2]) if len(sys.argv) > 2 else 12
     cfg = arch.CONFIGS["single_tech"]
     eng = model.MoEEngine(cfg, weights.init_params(cfg, seed=13), device="cuda:0", precision=prec)
-    n = 148 * 12 * per_cta
+    n = 148 * 3 * NG * per_cta
     g = torch.Generator().manual_seed(1)
     reads = torch.randint(0, 256, (n, 150, 6), generator=g, dtype=torch.uint8).cuda()
     out = torch.empty((n, 36, 64), dtype=torch.float32, device="cuda")
