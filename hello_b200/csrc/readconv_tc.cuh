@@ -170,6 +170,19 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
     constexpr int BPT = N / 16;                       // blocks per tile
     constexpr bool TWO = MODE == 3 && STACK;
     constexpr uint32_t TILE_COLS = TWO ? 2 * N : N;
+    // Software pipeline over the four blocks: the TMEM loads of block b+1 are in flight while block b is packed and
+    // stored.
+    float v[16];
+    float w[TWO ? 16 : 1];
+    float r[(RESID || MOVE_SC) ? 16 : 1];
+    auto issue_loads = [&](int blk) {
+        const int tile = blk / BPT, c0 = (blk - tile * BPT) * 16;
+        ptx::tmem_ld16(tl + tile * TILE_COLS + c0, v);
+        if (TWO) ptx::tmem_ld16(tl + tile * TILE_COLS + N + c0, w);
+        if (RESID && blk >= 2) ptx::tmem_ld16(tl + RES_COL + (blk - 2) * 16, r);
+        if (MOVE_SC) ptx::tmem_ld16(tl + 64 + c0, r);
+    };
+    issue_loads(0);
 #pragma unroll
     for (int blk = 0; blk < 4; ++blk) {
         const int tile = blk / BPT, c0 = (blk - tile * BPT) * 16;
@@ -177,42 +190,36 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
         const int i = m / PITCH, p = m - i * PITCH;
         const bool valid = (i < n_reads) && (p < LVALID);
         const bool in_buf = m < ROWS;
-        float v[16];
-        float w[TWO ? 16 : 1];
-        float r[(RESID || MOVE_SC) ? 16 : 1];
-        ptx::tmem_ld16(tl + tile * TILE_COLS + c0, v);
-        if (TWO) ptx::tmem_ld16(tl + tile * TILE_COLS + N + c0, w);
-        if (RESID && blk >= 2) ptx::tmem_ld16(tl + RES_COL + (blk - 2) * 16, r);
-        if (MOVE_SC) ptx::tmem_ld16(tl + 64 + c0, r);
+        float x[16];
         ptx::tmem_wait_ld();
-        if (RESID && blk < 2) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) r[c] = rr[blk * 16 + c];
-        }
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-            float x = TWO ? v[c] + w[c] : v[c];
-            x = fmaxf(x + bias[c0 + c], 0.f);
-            if (RESID) x += RES_BIAS ? (r[c] + bias2[c0 + c]) : r[c];
-            v[c] = valid ? x : 0.f;
+            float y = TWO ? v[c] + w[c] : v[c];
+            y = fmaxf(y + bias[c0 + c], 0.f);
+            if (RESID) {
+                const float res = blk < 2 ? rr[(blk & 1) * 16 + c] : r[c];
+                y += RES_BIAS ? (res + bias2[c0 + c]) : res;
+            }
+            x[c] = valid ? y : 0.f;
         }
         if (WRITE_RESID || MOVE_SC) {
             if (blk < 2) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) rr[blk * 16 + c] = MOVE_SC ? r[c] : v[c];
+                for (int c = 0; c < 16; ++c) rr[(blk & 1) * 16 + c] = MOVE_SC ? r[c] : x[c];
             } else {
-                ptx::tmem_st16(tl + RES_COL + (blk - 2) * 16, MOVE_SC ? r : v);
+                ptx::tmem_st16(tl + RES_COL + (blk - 2) * 16, MOVE_SC ? r : x);
             }
         }
+        if (blk + 1 < 4) issue_loads(blk + 1);
         if (dbg) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) dbg[m * 64 + c0 + c] = v[c];
+            for (int c = 0; c < 16; ++c) dbg[m * 64 + c0 + c] = x[c];
         }
         if (OUT == OUT_GLOBAL) {
             if (valid) {
                 float4* dst = reinterpret_cast<float4*>(gout + ((long long)i * LOUT + p) * COUT + c0);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int q = 0; q < 4; ++q) dst[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
             }
         } else if (in_buf) {
 #pragma unroll
@@ -221,7 +228,7 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
                 uint8_t* dst = OUT == OUT_NAT
                                    ? act + c8 * out_stride + (uint32_t)(m + LEAD) * 16
                                    : act + (c8 * 2 + (m & 1)) * out_stride + (uint32_t)((m >> 1) + LEAD) * 16;
-                store_chunk8<MODE>(dst, out_lo, v + 8 * q);
+                store_chunk8<MODE>(dst, out_lo, x + 8 * q);
             }
         }
     }

@@ -36,18 +36,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Spin until the barrier phase with the given parity completes.  The loop lives inside the asm block so the
-// compiler keeps treating the surrounding control flow as warp-uniform (needed for the uniform-datapath MMA
-// issue code).  A wait that makes no progress for ~2 s (4e9 SM clocks) is a protocol bug: trap instead of
-// hanging the GPU.
+// Wait until the barrier phase with the given parity completes.  try_wait carries a suspend-time hint, so a waiting
+// warp sleeps in hardware until the phase flips instead of spinning through issue slots the working warps need
+// (a bare try_wait returned every ~130 cycles here and the wait loops executed as many instructions as the
+// epilogues).  The loop lives inside the asm block so the compiler keeps treating the surrounding control flow as
+// warp-uniform (needed for the uniform-datapath MMA issue code).  A wait that makes no progress for ~2 s (4e9 SM
+// clocks) is a protocol bug: trap instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t.reg .u64 t0, t1;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "mov.u64 t0, %%clock64;\n\t"
         "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra DONE;\n\t"
         "mov.u64 t1, %%clock64;\n\t"
         "sub.u64 t1, t1, t0;\n\t"
@@ -55,7 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@P1 bra LAB_WAIT;\n\t"
         "trap;\n\t"
         "DONE:\n\t}" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 
