@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhello_moe.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 LAYOUT_RCL, LAYOUT_RLC = 0, 1
 META_NONE, META_SITE, META_REF = 0, 1, 2
@@ -47,6 +47,7 @@ class HelloResult(C.Structure):
     _fields_ = [
         ("d_logits", C.c_void_p), ("d_meta", C.c_void_p), ("d_pair_prob", C.c_void_p),
         ("d_pair_mix64", C.c_void_p), ("d_best_pair", C.c_void_p), ("d_best_prob", C.c_void_p),
+        ("d_call_pair", C.c_void_p), ("d_call_qual", C.c_void_p), ("d_best_expert", C.c_void_p),
     ]
 
 

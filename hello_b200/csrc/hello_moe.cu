@@ -412,6 +412,9 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         pa.pair_mix64 = out->d_pair_mix64;
         pa.best_pair = out->d_best_pair;
         pa.best_prob = out->d_best_prob;
+        pa.call_pair = out->d_call_pair;
+        pa.call_qual = out->d_call_qual;
+        pa.best_expert = out->d_best_expert;
         pa.s_begin = ck.s0; pa.s_end = ck.s1;
         posterior_kernel<<<(unsigned)((ns * 32 + 255) / 256), 256, 0, run.st>>>(pa);
         if (!run.launched("posterior")) return false;

@@ -156,11 +156,27 @@ struct PosteriorArgs {
     double* pair_mix64;         // [P] or nullptr
     int32_t* best_pair;         // [S][2]
     float* best_prob;           // [S]
+    int32_t* call_pair;         // [S][5][2] or nullptr: argmax pair of mixed, e0, e1, e2, float64 re-mix
+    double* call_qual;          // [S][5] or nullptr
+    int32_t* best_expert;       // [S] or nullptr: np.argmax(meta)
     long long s_begin, s_end;
 };
 
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 
+// One candidate of the reference's `sorted([(v, k) ...], reverse=True)[0]` (caller_calling.py:702-705,
+// prepareVcf.py:59): largest value, ties to the greatest (allele_i, allele_j) key.
+struct TopCall {
+    double v;
+    int i, j, ri, rj;
+    __device__ __forceinline__ void offer(double ov, int oi, int oj, int ori, int orj) {
+        if (ov > v || (ov == v && (ori > ri || (ori == ri && orj > rj)))) { v = ov; i = oi; j = oj; ri = ori; rj = orj; }
+    }
+};
+
+// Five calls per site, as the final-call step makes them (prepareVcf.py:36-105, 142-175): 0 the wrapper's fp32
+// mixture (what caller_calling.py:702-735 calls), 1-3 each expert on its own, 4 the float64 re-mix ("mean").
+// QUAL = -10 log10(1 - min(p, 1 - 1e-8)) in float64 (prepareVcf.py:60-62).
 __global__ void posterior_kernel(const PosteriorArgs a) {
     const long long s = a.s_begin + (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
@@ -171,8 +187,9 @@ __global__ void posterior_kernel(const PosteriorArgs a) {
     const int n_pairs = n * (n + 1) / 2;
     const float m0 = a.meta[3 * s], m1 = a.meta[3 * s + 1], m2 = a.meta[3 * s + 2];
 
-    float best_v = -1.f;
-    int best_i = 0, best_j = 0, best_ri = -1, best_rj = -1;
+    TopCall top[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { top[k].v = -1.0; top[k].i = 0; top[k].j = 0; top[k].ri = -1; top[k].rj = -1; }
     for (int q = lane; q < n_pairs; q += 32) {
         // invert q -> (i, j): row i starts at i*n - i*(i-1)/2
         int i = 0, rem = q;
@@ -197,31 +214,42 @@ __global__ void posterior_kernel(const PosteriorArgs a) {
         a.pair_prob[a.pair_total + p0 + q] = pe[0];
         a.pair_prob[2 * a.pair_total + p0 + q] = pe[1];
         a.pair_prob[3 * a.pair_total + p0 + q] = pe[2];
-        if (a.pair_mix64) {
-            double d = __dadd_rn(0.0, __dmul_rn((double)pe[0], (double)m0));
-            d = __dadd_rn(d, __dmul_rn((double)pe[1], (double)m1));
-            d = __dadd_rn(d, __dmul_rn((double)pe[2], (double)m2));
-            a.pair_mix64[p0 + q] = d;
-        }
+        double d = __dadd_rn(0.0, __dmul_rn((double)pe[0], (double)m0));
+        d = __dadd_rn(d, __dmul_rn((double)pe[1], (double)m1));
+        d = __dadd_rn(d, __dmul_rn((double)pe[2], (double)m2));
+        if (a.pair_mix64) a.pair_mix64[p0 + q] = d;
         const int ri = a.allele_rank ? a.allele_rank[a0 + i] : i;
         const int rj = a.allele_rank ? a.allele_rank[a0 + j] : j;
-        const bool better = mixed > best_v || (mixed == best_v && (ri > best_ri || (ri == best_ri && rj > best_rj)));
-        if (better) { best_v = mixed; best_i = i; best_j = j; best_ri = ri; best_rj = rj; }
+        top[0].offer((double)mixed, i, j, ri, rj);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) top[1 + e].offer((double)pe[e], i, j, ri, rj);
+        top[4].offer(d, i, j, ri, rj);
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best_v, d);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, d);
-        const int oj = __shfl_xor_sync(0xffffffffu, best_j, d);
-        const int ori = __shfl_xor_sync(0xffffffffu, best_ri, d);
-        const int orj = __shfl_xor_sync(0xffffffffu, best_rj, d);
-        const bool better = ov > best_v || (ov == best_v && (ori > best_ri || (ori == best_ri && orj > best_rj)));
-        if (better) { best_v = ov; best_i = oi; best_j = oj; best_ri = ori; best_rj = orj; }
+    for (int k = 0; k < 5; ++k) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, top[k].v, d);
+            const int oi = __shfl_xor_sync(0xffffffffu, top[k].i, d);
+            const int oj = __shfl_xor_sync(0xffffffffu, top[k].j, d);
+            const int ori = __shfl_xor_sync(0xffffffffu, top[k].ri, d);
+            const int orj = __shfl_xor_sync(0xffffffffu, top[k].rj, d);
+            top[k].offer(ov, oi, oj, ori, orj);
+        }
     }
     if (lane == 0) {
-        a.best_pair[2 * s] = best_i;
-        a.best_pair[2 * s + 1] = best_j;
-        a.best_prob[s] = best_v;
+        a.best_pair[2 * s] = top[0].i;
+        a.best_pair[2 * s + 1] = top[0].j;
+        a.best_prob[s] = (float)top[0].v;
+        if (a.call_pair) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { a.call_pair[(s * 5 + k) * 2] = top[k].i; a.call_pair[(s * 5 + k) * 2 + 1] = top[k].j; }
+        }
+        if (a.call_qual) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) a.call_qual[s * 5 + k] = -10.0 * log10(1.0 - fmin(top[k].v, 1.0 - 1e-8));
+        }
+        if (a.best_expert) a.best_expert[s] = (m0 >= m1 && m0 >= m2) ? 0 : (m1 >= m2 ? 1 : 2);   // first maximum
     }
 }
 

@@ -71,9 +71,12 @@ class DeviceBatch:
     @staticmethod
     def from_host(reads: Sequence[torch.Tensor], layout: int, allele_read_off: Sequence[torch.Tensor],
                   site_allele_off: torch.Tensor, ref_onehot: Optional[torch.Tensor], device,
-                  allele_rank: Optional[torch.Tensor] = None, non_blocking: bool = True) -> "DeviceBatch":
+                  allele_rank: Optional[torch.Tensor] = None, non_blocking: bool = True,
+                  pin: bool = False) -> "DeviceBatch":
         dev = torch.device(device)
         pair_off = pair_offsets(site_allele_off)
+        if pin:
+            pair_off = pair_off.pin_memory()
         up = lambda t: t.to(dev, non_blocking=non_blocking)
         return DeviceBatch(
             reads=tuple(up(r.contiguous()) for r in reads), layout=layout,
@@ -99,10 +102,17 @@ class BatchResult:
     best_pair: torch.Tensor    # [S, 2]
     best_prob: torch.Tensor    # [S]
     pair_off: torch.Tensor     # [S+1] host
+    # the final-call step (prepareVcf.py:36-105,142-175): call 0 = fp32 mixture, 1-3 = experts, 4 = float64 re-mix
+    call_pair: torch.Tensor    # [S, 5, 2] int32
+    call_qual: torch.Tensor    # [S, 5]    float64  QUAL
+    best_expert: torch.Tensor  # [S]       int32    np.argmax(meta)
+
+    def tensors(self):
+        return (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob,
+                self.call_pair, self.call_qual, self.best_expert)
 
     def output_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in
-                   (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob))
+        return sum(t.numel() * t.element_size() for t in self.tensors())
 
 
 class MoEEngine:
@@ -193,7 +203,10 @@ class MoEEngine:
             pair_mix64=torch.empty((P,), dtype=torch.float64, device=dev),
             best_pair=torch.empty((S, 2), dtype=torch.int32, device=dev),
             best_prob=torch.empty((S,), dtype=torch.float32, device=dev),
-            pair_off=b.pair_off_h)
+            pair_off=b.pair_off_h,
+            call_pair=torch.empty((S, 5, 2), dtype=torch.int32, device=dev),
+            call_qual=torch.empty((S, 5), dtype=torch.float64, device=dev),
+            best_expert=torch.empty((S,), dtype=torch.int32, device=dev))
 
     def run(self, b: DeviceBatch, out: Optional[BatchResult] = None,
             workspace: Optional[torch.Tensor] = None) -> BatchResult:
@@ -233,6 +246,8 @@ class MoEEngine:
         hr.d_logits, hr.d_meta = out.logits.data_ptr(), out.meta.data_ptr()
         hr.d_pair_prob, hr.d_pair_mix64 = out.pair_prob.data_ptr(), out.pair_mix64.data_ptr()
         hr.d_best_pair, hr.d_best_prob = out.best_pair.data_ptr(), out.best_prob.data_ptr()
+        hr.d_call_pair, hr.d_call_qual = out.call_pair.data_ptr(), out.call_qual.data_ptr()
+        hr.d_best_expert = out.best_expert.data_ptr()
         ws = workspace if workspace is not None else \
             self._workspace(self.workspace_bytes(nr[0], nr[1], b.n_alleles, b.n_sites))
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -265,13 +280,20 @@ class MoEEngine:
                     self._ws2[i % 2] = None
                     self._ws2[i % 2] = torch.empty(want, dtype=torch.uint8, device=self.device)
                 res = self.run(db, workspace=self._ws2[i % 2])
-                out.logits[:, a0:a1].copy_(res.logits, non_blocking=True)
+                # row by row: every copy is contiguous on both sides, so none of them stages through a temporary
+                # (a strided device->host copy synchronises the stream and would serialise H2D with the kernels)
+                for e in range(3):
+                    out.logits[e, a0:a1].copy_(res.logits[e], non_blocking=True)
                 out.meta[s0:s1].copy_(res.meta, non_blocking=True)
-                out.pair_prob[:, p0:p1].copy_(res.pair_prob, non_blocking=True)
+                for e in range(4):
+                    out.pair_prob[e, p0:p1].copy_(res.pair_prob[e], non_blocking=True)
                 out.pair_mix64[p0:p1].copy_(res.pair_mix64, non_blocking=True)
                 out.best_pair[s0:s1].copy_(res.best_pair, non_blocking=True)
                 out.best_prob[s0:s1].copy_(res.best_prob, non_blocking=True)
-                for t in (res.logits, res.meta, res.pair_prob, res.pair_mix64, res.best_pair, res.best_prob) + \
+                out.call_pair[s0:s1].copy_(res.call_pair, non_blocking=True)
+                out.call_qual[s0:s1].copy_(res.call_qual, non_blocking=True)
+                out.best_expert[s0:s1].copy_(res.best_expert, non_blocking=True)
+                for t in res.tensors() + \
                         db.reads + db.allele_read_off_d + (db.site_allele_off_d, db.pair_off_d):
                     t.record_stream(st)
         for st in self._streams:
@@ -346,10 +368,14 @@ class HostResult:
     pair_mix64: torch.Tensor
     best_pair: torch.Tensor
     best_prob: torch.Tensor
+    call_pair: torch.Tensor
+    call_qual: torch.Tensor
+    best_expert: torch.Tensor
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in
-                   (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob))
+                   (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob,
+                    self.call_pair, self.call_qual, self.best_expert))
 
 
 class HostBatch:
@@ -383,7 +409,8 @@ class HostBatch:
             A, S, P = int(self.site_allele_off[-1]), self.n_sites, int(self.pair_off[-1])
             mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=self.pin)
             self._out = HostResult(mk((3, A), torch.float32), mk((S, 3), torch.float32), mk((4, P), torch.float32),
-                                   mk((P,), torch.float64), mk((S, 2), torch.int32), mk((S,), torch.float32))
+                                   mk((P,), torch.float64), mk((S, 2), torch.int32), mk((S,), torch.float32),
+                                   mk((S, 5, 2), torch.int32), mk((S, 5), torch.float64), mk((S,), torch.int32))
         return self._out
 
     def device_chunk(self, s0: int, s1: int, device):
@@ -391,13 +418,14 @@ class HostBatch:
         sao = self.site_allele_off
         a0, a1 = int(sao[s0]), int(sao[s1])
         reads, offs = [], []
+        pin = (lambda t: t.pin_memory()) if self.pin else (lambda t: t)   # small; pinned so the upload stays async
         for t, r in enumerate(self.reads):
             aro = self.allele_read_off[t]
             r0, r1 = int(aro[a0]), int(aro[a1])
             reads.append(r[r0:r1])
-            offs.append(aro[a0:a1 + 1] - r0)
+            offs.append(pin(aro[a0:a1 + 1] - r0))
         ref = self.ref_onehot[s0:s1] if self.ref_onehot is not None else None
-        db = DeviceBatch.from_host(reads, self.layout, offs, sao[s0:s1 + 1] - a0, ref, device)
+        db = DeviceBatch.from_host(reads, self.layout, offs, pin(sao[s0:s1 + 1] - a0), ref, device, pin=self.pin)
         return db, (a0, a1), (int(self.pair_off[s0]), int(self.pair_off[s1]))
 
 
@@ -473,6 +501,33 @@ class MoEAttentionB200:
     __call__ = forward
 
 
+CALL_NAMES = ("mixed", "expert0", "expert1", "expert2", "mean")
+
+
+def allele_ranks(alleles_per_site: Sequence[Sequence[str]]) -> torch.Tensor:
+    """Tie-break ranks for DeviceBatch.allele_rank: rank of every allele string inside its site's sorted order (the
+    reference's ``sorted([(v, k)...], reverse=True)[0]`` falls back on the allele strings when values tie)."""
+    out = []
+    for names in alleles_per_site:
+        order = sorted(range(len(names)), key=lambda i: names[i])
+        rank = [0] * len(names)
+        for r, i in enumerate(order):
+            rank[i] = r
+        out.extend(rank)
+    return torch.tensor(out, dtype=torch.int32)
+
+
+def final_calls(res: BatchResult, site: int, alleles: Sequence[str]) -> Dict[str, object]:
+    """The final-call step for one site from the kernel's per-site records (prepareVcf.py:142-166, caller_calling.py:
+    702-735): {"mixed" | "expert0..2" | "best" | "mean": ((allele_i, allele_j), QUAL)} and "choice" = np.argmax(meta)."""
+    cp = res.call_pair[site].cpu().tolist()
+    cq = res.call_qual[site].cpu().tolist()
+    out = {name: ((alleles[cp[k][0]], alleles[cp[k][1]]), cq[k]) for k, name in enumerate(CALL_NAMES)}
+    out["choice"] = int(res.best_expert[site])
+    out["best"] = out["expert%d" % out["choice"]]
+    return out
+
+
 class MoEMergedWrapperB200:
     """Drop-in for ``MoEMergedWrapperAdvanced``: ``network(featureDict, segment)`` for one site."""
 
@@ -511,9 +566,14 @@ class MoEMergedWrapperB200:
         keys = [(alleles[i], alleles[j]) for i in range(n) for j in range(i, n)]
         dicts = [{k: pp[row, q] for q, k in enumerate(keys)} for row in range(4)]
         self.last_call = (keys[self._pair_index(n, res.best_pair[0].tolist())], float(res.best_prob[0]))
+        self.last_alleles = alleles
         if self.providePredictions:
             return tuple(dicts) + (meta,)
         return dicts[0]
+
+    def final_calls(self) -> Dict[str, object]:
+        """Calls of the site scored last, as prepareVcf.vcfRecords would make them from its .features record."""
+        return final_calls(self.moeMerged.last_result, 0, self.last_alleles)
 
     @staticmethod
     def _pair_index(n: int, ij) -> int:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HELLO_MOE_ABI_VERSION 1
+#define HELLO_MOE_ABI_VERSION 2
 
 typedef enum hello_status {
     HELLO_OK = 0,
@@ -102,6 +102,12 @@ typedef struct hello_result {
     int32_t* d_best_pair; /* [S, 2]  argmax genotype (allele indices inside the site), ties broken as the
                                      reference does: greatest (allele_i, allele_j) key (caller_calling.py:702-705) */
     float* d_best_prob;   /* [S]     its probability */
+    /* The final-call step that follows the network (prepareVcf.py:36-105,142-175; caller_calling.py:702-735).  All
+     * three may be NULL.  Call k: 0 = the fp32 mixture above, 1..3 = expert k-1 alone, 4 = the float64 re-mix
+     * ("mean" record); the "best" record of prepareVcf is call 1 + d_best_expert[s]. */
+    int32_t* d_call_pair;   /* [S, 5, 2] argmax genotype of every call (same tie-break as d_best_pair)            */
+    double* d_call_qual;    /* [S, 5]    QUAL = -10 log10(1 - min(p, 1 - 1e-8)), float64 (prepareVcf.py:60-62)     */
+    int32_t* d_best_expert; /* [S]       np.argmax(meta) (prepareVcf.py:148,168)                                   */
 } hello_result;
 
 /* ABI version of the loaded library (== HELLO_MOE_ABI_VERSION). */

@@ -19,6 +19,9 @@ Reference lines followed:
   wrapper_forward     python/MixtureOfExpertsAdvanced.py:493-589
   call_genotype       python/caller_calling.py:702-705, 727-735
   remix_float64       python/prepareVcf.py:154-162
+  final_calls         python/prepareVcf.py:59-62 (callAlleles: selection, QUAL), 142-166 (experts, best, mean);
+                      pinned by tests/golden/final_calls.npz (made by oracle/gen_final_calls.py from the
+                      reference's own vcfRecords)
 """
 from __future__ import annotations
 
@@ -201,6 +204,24 @@ def call_genotype(pair_probs: Dict[Tuple[str, str], float]):
     value, key = sorted(((float(v), k) for k, v in pair_probs.items()), reverse=True)[0]
     qual = -10 * math.log10(1 - min(value, 1 - 1e-8))
     return key, value, qual
+
+
+def final_calls(expert_predictions, meta):
+    """The final-call step of prepareVcf.vcfRecords (:142-166) without the VCF text: for each expert's pair
+    probabilities, for the expert np.argmax(meta) picks ("best") and for the float64 re-mix ("mean"), the top
+    allele pair and QUAL exactly as callAlleles computes them (:59-62).  expert_predictions: three dicts
+    {(allele_i, allele_j): probability}; meta: three weights.  Returns {name: (top key, qual)} plus "choice"."""
+    def call(likelihoods):
+        likelihood, top = sorted([(float(v), k) for k, v in likelihoods.items()], reverse=True)[0]
+        likelihood = min(float(likelihood), 1 - 1e-8)
+        return top, -10 * math.log10(1 - likelihood)
+
+    experts = [call(d) for d in expert_predictions]
+    m = [float(x) for x in meta]
+    choice = max(range(3), key=lambda i: (m[i], -i))                 # np.argmax: first maximum
+    mean = {k: sum(float(expert_predictions[i][k]) * m[i] for i in range(3)) for k in expert_predictions[0]}
+    return {"expert0": experts[0], "expert1": experts[1], "expert2": experts[2], "best": experts[choice],
+            "mean": call(mean), "choice": choice}
 
 
 def remix_float64(per_expert, meta) -> List[float]:

@@ -36,10 +36,10 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_ctypes_structs_match_header_layout():
-    # hello_cfg: 12 int32; hello_batch: 4 int64 + 2 int32 + 11 pointers; hello_result: 6 pointers
+    # hello_cfg: 12 int32; hello_batch: 4 int64 + 2 int32 + 11 pointers; hello_result: 9 pointers
     assert ctypes.sizeof(_lib.HelloCfg) == 12 * 4
     assert ctypes.sizeof(_lib.HelloBatch) == 4 * 8 + 2 * 4 + 11 * 8
-    assert ctypes.sizeof(_lib.HelloResult) == 6 * 8
+    assert ctypes.sizeof(_lib.HelloResult) == 9 * 8
     text = open(HEADER).read()
     for field in ("struct_size", "n_tech", "read_channels", "xattn_present", "has_combiners", "meta_kind",
                   "feature_length", "precision", "max_chunk_sites"):

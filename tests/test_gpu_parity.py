@@ -279,6 +279,36 @@ def test_strict_drop_in_wrapper_call(gpu):
         assert isinstance(network(fd, seg), dict)
 
 
+def test_final_call_records(gpu):
+    """d_call_pair / d_call_qual / d_best_expert against the oracle's final-call step (itself pinned to the
+    reference's vcfRecords by tests/golden/final_calls.npz), evaluated on the kernel's own pair probabilities:
+    indices bit-exact, QUAL to double rounding."""
+    from oracle import hello_oracle as O
+    pool = ["G", "GA", "T", "C", "GTT", "A"]
+    for name in ("single_tech", "hybrid_full", "hybrid_ensemble2"):
+        cfg = arch.CONFIGS[name]
+        pl = synth.make_pileups(40, coverage=8, channels=cfg.read_cin, seed=123)
+        naps = pl.num_alleles_per_site()
+        names = [(pool[:n] if s % 2 == 0 else pool[:n][::-1]) for s, n in enumerate(naps)]
+        net = net_for(gpu, cfg, "bf16x3")
+        batch = gpu.DeviceBatch.from_host(pl.reads, 1, pl.allele_read_off, pl.site_allele_off, pl.ref_onehot, DEV,
+                                          allele_rank=gpu.allele_ranks(names))
+        r = net.engine.run(batch)
+        pp, meta, off = r.pair_prob.cpu(), r.meta.cpu(), r.pair_off.numpy()
+        for s, n in enumerate(naps):
+            pairs = [(names[s][i], names[s][j]) for i in range(n) for j in range(i, n)]
+            preds = [{pairs[q]: pp[1 + e, off[s] + q] for q in range(len(pairs))} for e in range(3)]
+            ref = O.final_calls(preds, meta[s])
+            got = gpu.final_calls(r, s, names[s])
+            assert got["choice"] == ref["choice"]
+            for key in ("expert0", "expert1", "expert2", "best", "mean"):
+                assert got[key][0] == ref[key][0], (name, s, key)
+                assert abs(got[key][1] - ref[key][1]) <= 1e-12 * max(1.0, abs(ref[key][1])), (name, s, key)
+            key, value, qual = O.call_genotype({pairs[q]: pp[0, off[s] + q] for q in range(len(pairs))})
+            assert got["mixed"][0] == key and abs(got["mixed"][1] - qual) <= 1e-12 * max(1.0, qual)
+            assert tuple(r.call_pair[s, 0].tolist()) == tuple(r.best_pair[s].tolist())
+
+
 # ------------------------------------------------------------------------------------------------ edge cases
 def test_chunking_does_not_change_results(gpu):
     cfg = arch.CONFIGS["single_tech"]

@@ -85,3 +85,26 @@ def test_call_rule_tie_break_and_quality():
     key, value, qual = O.call_genotype({("A", "A"): 1.0})
     assert abs(qual - 80.0) < 1e-6
     assert O.remix_float64([[0.5], [0.25], [0.125]], [0.5, 0.25, 0.25]) == [0.5 * 0.5 + 0.25 * 0.25 + 0.125 * 0.25]
+
+
+def test_final_calls_match_reference_vcfrecords():
+    """oracle.final_calls against records made by the reference's own prepareVcf.vcfRecords
+    (oracle/gen_final_calls.py): top allele pair of expert0/1/2, best, mean; QUAL; np.argmax(meta)."""
+    import os
+    from helpers import GOLDEN
+    from oracle import hello_oracle as O
+    g = np.load(os.path.join(GOLDEN, "final_calls.npz"))
+    names_all = [str(x) for x in g["names"]]
+    p0 = 0
+    for s, n in enumerate(g["n_alleles"]):
+        n = int(n)
+        names = [names_all[i] for i in g["allele_name_idx"][s, :n]]
+        pairs = [(names[i], names[j]) for i in range(n) for j in range(i, n)]
+        preds = [{pairs[q]: g["experts"][e, p0 + q] for q in range(len(pairs))} for e in range(3)]
+        got = O.final_calls(preds, g["meta"][s])
+        assert got["choice"] == int(g["best_expert"][s])
+        for c, key in enumerate(str(x) for x in g["calls"]):
+            top, qual = got[key]
+            assert (names.index(top[0]), names.index(top[1])) == tuple(g["call_pair"][s, c]), (s, key)
+            assert abs(qual - g["call_qual"][s, c]) <= 1e-12 * max(1.0, abs(qual)), (s, key)
+        p0 += len(pairs)
