@@ -17,6 +17,7 @@
 #include "misc_kernels.cuh"
 #include "readconv_tc.cuh"
 #include "headconv_tc.cuh"
+#include "combconv_tc.cuh"
 
 using namespace hello;
 
@@ -59,6 +60,7 @@ struct hello_moe {
     int comp_len = 0, comp_ch = 0;   // compressor output (18, 128)
     ReadConvTC* tc[2] = {nullptr, nullptr};
     HeadConvTC* head[N_NETS] = {};   // fused tcgen05 compressor / xattn / meta_convolver (tensor-core precisions)
+    CombConvTC* comb[2] = {nullptr, nullptr};   // fused tcgen05 combiner0 / combiner1
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;            // pairs (start, stop), created lazily
     size_t ev_used = 0;
@@ -218,6 +220,12 @@ struct Runner {
         return check(headconv_tc_launch(t, in_a, in_s, site_idx, n, out, out_stride, softmax, st), "headconv_tc");
     }
 
+    bool comb(CombConvTC* t, const float* in_a, const float* in_b, int stride, long long n, float* out) {
+        if (dry || n == 0) return true;
+        h->launches++;
+        return check(combconv_tc_launch(t, in_a, in_b, stride, n, out, st), "combconv_tc");
+    }
+
     bool segsum(const float* x, float* out, const int32_t* off, long long n_groups, int row_base, long long elems) {
         if (dry || n_groups == 0) return true;
         const int e4 = (int)(elems / 4);
@@ -349,16 +357,22 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         float* c2 = ar.allocf(na * comp_e);
         float* s2 = ar.allocf(ns * comp_e);
         size_t m = ar.mark();
-        float* cat = ar.allocf(na * comp_e * 2);
-        if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
-        if (!run.concat2(c_t[0], c_t[1], cat, na * h->comp_len, cc, cc)) return false;
-        if (!run.run_net(h->nets[NET_CB0], view_cl(cat, h->comp_len, 2 * cc), na, c2, nullptr)) return false;
-        ar.release(m);
-        cat = ar.allocf(ns * comp_e * 2);
-        if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
-        if (!run.concat2(s_t[0], s_t[1], cat, ns * h->comp_len, cc, cc)) return false;
-        if (!run.run_net(h->nets[NET_CB1], view_cl(cat, h->comp_len, 2 * cc), ns, s2, nullptr)) return false;
-        ar.release(m);
+        if (h->comb[0] && h->comb[1]) {
+            // the kernel reads the two technologies' tensors as the two K-halves: no concat buffer
+            if (!run.comb(h->comb[0], c_t[0], c_t[1], cc, na, c2)) return false;
+            if (!run.comb(h->comb[1], s_t[0], s_t[1], cc, ns, s2)) return false;
+        } else {
+            float* cat = ar.allocf(na * comp_e * 2);
+            if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
+            if (!run.concat2(c_t[0], c_t[1], cat, na * h->comp_len, cc, cc)) return false;
+            if (!run.run_net(h->nets[NET_CB0], view_cl(cat, h->comp_len, 2 * cc), na, c2, nullptr)) return false;
+            ar.release(m);
+            cat = ar.allocf(ns * comp_e * 2);
+            if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
+            if (!run.concat2(s_t[0], s_t[1], cat, ns * h->comp_len, cc, cc)) return false;
+            if (!run.run_net(h->nets[NET_CB1], view_cl(cat, h->comp_len, 2 * cc), ns, s2, nullptr)) return false;
+            ar.release(m);
+        }
         if (h->head[NET_X2]) {
             if (!run.head(h->head[NET_X2], c2, s2, site_idx, na, dry ? nullptr : out->d_logits + 2LL * A_total + ck.a0, 1, 0))
                 return false;
@@ -576,6 +590,17 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
             }
         }
     }
+    if (cfg->precision != HELLO_PREC_FP32 && cfg->has_combiners && cfg->xattn_present[2]) {
+        for (int k = 0; k < 2; ++k) {
+            std::string terr;
+            h->comb[k] = combconv_tc_create(h->nets[NET_CB0 + k], h->d_weights, h->h_weights.data(), cfg->precision, terr);
+            if (!h->comb[k]) {
+                g_create_error = "hello_moe_create: tensor-core combiner: " + terr;
+                hello_moe_destroy(h);
+                return HELLO_ERR_UNSUPPORTED;
+            }
+        }
+    }
     *out = h;
     return HELLO_OK;
 }
@@ -585,6 +610,7 @@ void hello_moe_destroy(hello_moe* h) {
     cudaSetDevice(h->device);
     for (int t = 0; t < 2; ++t) readconv_tc_destroy(h->tc[t]);
     for (int n = 0; n < N_NETS; ++n) headconv_tc_destroy(h->head[n]);
+    for (int k = 0; k < 2; ++k) combconv_tc_destroy(h->comb[k]);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->d_weights) cudaFree(h->d_weights);
     delete h;
@@ -743,6 +769,11 @@ int hello_moe_run_net(hello_moe* h, int net_id, const void* d_in, int64_t n_item
         run.head(h->head[net_id], static_cast<const float*>(d_in), nullptr, nullptr, n_items, d_out, co, 0);
         return run.status;
     }
+    if ((net_id == NET_CB0 || net_id == NET_CB1) && h->comb[net_id - NET_CB0]) {
+        const float* x = static_cast<const float*>(d_in);       // [n, 18, 256]: the two halves of every row
+        run.comb(h->comb[net_id - NET_CB0], x, x + cc::C_HALF, 2 * cc::C_HALF, n_items, d_out);
+        return run.status;
+    }
     const bool gap = net.back().kind == KIND_GAP_LINEAR;
     Runner::GapOut g{d_out, co, 0};
     run.run_net(net, v, n_items, gap ? nullptr : d_out, gap ? &g : nullptr);
@@ -768,8 +799,17 @@ int hello_moe_headconv_debug(hello_moe* h, int net_id, const float* d_in, int64_
                              float* d_dbg, void* stream) {
     if (!h) return HELLO_ERR_ARG;
     h->err.clear();
-    if (net_id < 0 || net_id >= N_NETS || !h->head[net_id]) { h->err = "no tensor-core head for this network"; return HELLO_ERR_UNSUPPORTED; }
     if (!d_in || !d_out || n_items < 0) { h->err = "bad buffers"; return HELLO_ERR_ARG; }
+    if ((net_id == NET_CB0 || net_id == NET_CB1) && h->comb[net_id - NET_CB0]) {
+        cudaError_t ec = cudaSetDevice(h->device);
+        if (ec == cudaSuccess)
+            ec = combconv_tc_launch(h->comb[net_id - NET_CB0], d_in, d_in + cc::C_HALF, 2 * cc::C_HALF, n_items, d_out,
+                                    static_cast<cudaStream_t>(stream), d_dbg, d_dbg ? phase : -1);
+        h->launches++;
+        if (ec != cudaSuccess) { h->err = std::string("combconv_tc: ") + cudaGetErrorString(ec); return HELLO_ERR_CUDA; }
+        return HELLO_OK;
+    }
+    if (net_id < 0 || net_id >= N_NETS || !h->head[net_id]) { h->err = "no tensor-core head for this network"; return HELLO_ERR_UNSUPPORTED; }
     HeadConvTC* t = h->head[net_id];
     cudaError_t e = cudaSetDevice(h->device);
     if (e == cudaSuccess)

@@ -339,18 +339,19 @@ class MoEEngine:
 
 
     def headconv_debug(self, net: str, x: torch.Tensor, phase: int = -1):
-        """Test hook: one fused tensor-core head network (compressor / xattn on a combined input / meta_convolver) on
-        fp32 channel-last items.  Returns (output, dump or None); the dump holds the post-activation values of layer
+        """Test hook: one fused tensor-core head network (compressor / xattn on a combined input / meta_convolver /
+        combiner on a concatenated [n,18,256] input) on fp32 channel-last items.  Returns (output, dump or None); the dump holds the post-activation values of layer
         phase `phase` as [groups, 256, 256] (include/hello_moe.h)."""
         nid = weights.NET_IDS[net]
         x = x.contiguous().float().to(self.device)
         n, lin, cin = x.shape
         co, lo = arch.net_out_shape(self.cfg.networks()[net], lin)
         out = torch.empty((n, lo, co), dtype=torch.float32, device=self.device)
-        per = 6 if cin == 64 else 12
+        per = 12 if cin == 128 else 6
         dbg = None
         if phase >= 0:
-            dbg = torch.zeros(((n + per - 1) // per, 256, 256), dtype=torch.float32, device=self.device)
+            shape = (128, 512) if cin == 256 else (256, 256)        # combiner: its 512-channel intermediate
+            dbg = torch.zeros(((n + per - 1) // per,) + shape, dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):
             rc = self.lib.hello_moe_headconv_debug(self.handle, nid, x.data_ptr(), n, phase, out.data_ptr(),

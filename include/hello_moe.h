@@ -53,8 +53,8 @@ enum { HELLO_META_NONE = 0,
        HELLO_META_REF = 2 };   /* architectures/meta_convolver_ref.py: input = one-hot reference segment      */
 
 enum { HELLO_PREC_FP32 = 0,    /* fp32 FMA everywhere (CUDA cores)                                            */
-       HELLO_PREC_BF16X3 = 1,  /* read convolver, compressor, xattn and meta_convolver on tcgen05: operands split
-                                  into hi+lo bf16, 3 MMAs per product, fp32 accumulate                        */
+       HELLO_PREC_BF16X3 = 1,  /* read convolver, compressor, combiner, xattn and meta_convolver on tcgen05:
+                                  operands split into hi+lo bf16, three products, fp32 accumulate             */
        HELLO_PREC_BF16 = 2 };  /* same kernels with single bf16 operands, fp32 accumulate ("fast" mode)       */
 
 /* Model wiring = which sub-networks MoEAttention holds (python/moe_attention_config_*.py). */
@@ -162,7 +162,8 @@ int hello_moe_readconv_debug(hello_moe* h, int tech, const uint8_t* d_reads, int
  * compressor, 4,5,6 xattn on an already combined 2a-s input, 9 meta_convolver): run the kernel on n_items fp32
  * channel-last items and, when d_dbg is not NULL, dump the post-activation values of layer phase `phase`
  * (0: 1x1 conv, 1-2: stride-2 block conv a / block output, 3-6: the two identity blocks) as fp32
- * [groups, 256, 256]: a group is 6 (compressor) or 12 items, row = packed row of the group (pitch 40 / 20 in phase 0,
+ * [groups, 256, 256] (combiner, net_id 7,8, input [n,18,256]: phase 0 only = the 512-channel intermediate as
+ * [groups of 6 items, 128, 512], pitch 20): a group is 6 (compressor) or 12 items, row = packed row of the group (pitch 40 / 20 in phase 0,
  * half of it afterwards), column = channel. d_out as for hello_moe_run_net. */
 int hello_moe_headconv_debug(hello_moe* h, int net_id, const float* d_in, int64_t n_items, int32_t phase, float* d_out,
                              float* d_dbg, void* stream);

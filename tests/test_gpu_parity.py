@@ -165,6 +165,27 @@ def test_headconv_tc_every_layer(gpu, cfg_name, net_name, shape, precision):
     assert (got - full).abs().max().item() < TC_LAYER_REL[precision] * scale
 
 
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("n_items", [1, 6, 7, 13, 901])
+def test_combconv_tc(gpu, n_items, precision):
+    """Fused tensor-core combiner (concat -> conv k3 256->512 -> conv 1x1 512->128): the 512-channel intermediate
+    and the output against the oracle's fp32 layers, for partial groups and several waves of work items."""
+    cfg = arch.CONFIGS["hybrid_full"]
+    g = torch.Generator().manual_seed(40 + n_items)
+    x = (torch.randn((n_items, 18, 256), generator=g) * 20).float()
+    eng = net_for(gpu, cfg, precision).engine
+    net = oracle_for(cfg).nets["combiner1"]
+    trace = []
+    ref = net(x.transpose(1, 2), trace)
+    out, dump = eng.headconv_debug("combiner1", x, 0)
+    dump = dump.cpu()
+    mid = torch.stack([dump[r // 6, (r % 6) * 20:(r % 6) * 20 + 18, :].t() for r in range(n_items)])
+    assert (mid - trace[0]).abs().max().item() < TC_LAYER_REL[precision] * max(1.0, trace[0].abs().max().item())
+    got = out.cpu().transpose(1, 2)
+    assert (got - ref).abs().max().item() < TC_LAYER_REL[precision] * max(1.0, ref.abs().max().item(), trace[0].abs().max().item())
+    assert torch.equal(out, eng.run_net("combiner1", x)), "run_net routes the combiner through the same kernel"
+
+
 @pytest.mark.parametrize("n_items", [1, 5, 6, 7, 12, 13, 25, 1801])
 def test_headconv_tc_ragged_counts(gpu, n_items):
     """Any item count (partial groups, an empty second group, several waves of work items): run_net routes the
