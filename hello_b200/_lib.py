@@ -21,6 +21,8 @@ EXPORTS = (
     "hello_moe_workspace_bytes", "hello_moe_forward", "hello_moe_launch_count", "hello_moe_run_net",
     "hello_moe_profile_enable", "hello_moe_profile_collect", "hello_moe_readconv_debug",
     "hello_moe_headconv_debug",
+    # include/hello_encode.h
+    "hello_encode_reads", "hello_encode_last_error",
 )
 
 

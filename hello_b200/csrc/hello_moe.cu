@@ -18,6 +18,7 @@
 #include "readconv_tc.cuh"
 #include "headconv_tc.cuh"
 #include "combconv_tc.cuh"
+#include "encode_reads.cuh"
 
 using namespace hello;
 
@@ -817,6 +818,32 @@ int hello_moe_headconv_debug(hello_moe* h, int net_id, const float* d_in, int64_
                                static_cast<cudaStream_t>(stream), d_dbg, d_dbg ? phase : -1);
     h->launches++;
     if (e != cudaSuccess) { h->err = std::string("headconv_tc: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }
+    return HELLO_OK;
+}
+
+// ------------------------------------------------------------------------------------------- hello_encode.h
+static thread_local std::string g_encode_error;
+
+const char* hello_encode_last_error(void) { return g_encode_error.c_str(); }
+
+int hello_encode_reads(const hello_encode_batch* b, uint8_t* d_out, void* stream) {
+    g_encode_error.clear();
+    if (!b || !d_out) { g_encode_error = "null argument"; return HELLO_ERR_ARG; }
+    if (b->n_rows < 0 || b->feature_length < 1 || b->feature_length > enc::MAX_L || (b->channels != 6 && b->channels != 7)) {
+        g_encode_error = "need n_rows >= 0, 1 <= feature_length <= 160, channels 6 or 7"; return HELLO_ERR_ARG;
+    }
+    if (b->n_rows == 0) return HELLO_OK;
+    if (!b->d_row_read || !b->d_row_site || !b->d_read_off || !b->d_bases || !b->d_quals || !b->d_cigar_off || !b->d_cigars ||
+        !b->d_ref_start || !b->d_mapq || !b->d_orientation || (b->channels == 7 && !b->d_hp) || !b->d_ref_off ||
+        !b->d_reference || !b->d_window_start || !b->d_assembly_start || !b->d_assembly_stop) {
+        g_encode_error = "missing buffer"; return HELLO_ERR_ARG;
+    }
+    static const enc::Luts luts = enc::make_luts();
+    const long long blocks = (b->n_rows + enc::WARPS - 1) / enc::WARPS;
+    if (blocks > 0x7fffffffLL) { g_encode_error = "too many rows for one launch"; return HELLO_ERR_ARG; }
+    enc::encode_reads_kernel<<<(unsigned)blocks, enc::WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(*b, luts, d_out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { g_encode_error = std::string("encode_reads: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }
     return HELLO_OK;
 }
 

@@ -17,9 +17,12 @@ HEADER = os.path.join(ROOT, "include", "hello_moe.h")
 
 
 def header_functions():
-    text = open(HEADER).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(hello_moe_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):           # every include/*.h
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(hello_(?:moe|encode)_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -40,6 +43,8 @@ def test_ctypes_structs_match_header_layout():
     assert ctypes.sizeof(_lib.HelloCfg) == 12 * 4
     assert ctypes.sizeof(_lib.HelloBatch) == 4 * 8 + 2 * 4 + 11 * 8
     assert ctypes.sizeof(_lib.HelloResult) == 9 * 8
+    from hello_b200 import encoder
+    assert ctypes.sizeof(encoder.HelloEncodeBatch) == 8 + 2 * 4 + 16 * 8   # include/hello_encode.h
     text = open(HEADER).read()
     for field in ("struct_size", "n_tech", "read_channels", "xattn_present", "has_combiners", "meta_kind",
                   "feature_length", "precision", "max_chunk_sites"):
@@ -119,3 +124,24 @@ def test_synthetic_pileups_follow_the_codebook():
     assert set(np.unique(r[..., 6].numpy())) <= {0, 120, 240}
     sao, aro = pl.site_allele_off.numpy(), pl.allele_read_off[0].numpy()
     assert sao[0] == 0 and aro[0] == 0 and aro[-1] == r.shape[0] and (np.diff(sao) >= 1).all() and (np.diff(aro) >= 1).all()
+
+
+def test_encoder_host_packing():
+    """pack_sites / row_plan: flat arrays, BAM CIGAR encoding, row order site -> allele -> supporting reads of the
+    technology, -1 row for an allele without support (c++/src/AlleleSearcherLiteFiltered.cpp:958-968, 1037-1043)."""
+    from hello_b200 import encoder
+    s0 = encoder.SitePileup(["ACGT", "TTGCA"], [[30] * 4, [20] * 5], [[(0, 4)], [(4, 1), (0, 2), (1, 1), (0, 1)]], [100, 101],
+                            [60, 255], [1, -1], [False, True], [0, 2], "ACGTACGTAC", 95, 101, 102, {"A": [1, 0], "C": [0]})
+    s1 = encoder.SitePileup(["GG"], [[7, 8]], [[(0, 2)]], [50], [3], [1], [False], [1], "GGGG", 49, 50, 51, {"G": [0]})
+    p = encoder.pack_sites([s0, s1])
+    assert p.read_off.tolist() == [0, 4, 9, 11] and p.cigar_off.tolist() == [0, 1, 5, 6]
+    assert p.cigars.tolist() == [4 << 4, 1 << 4 | 4, 2 << 4, 1 << 4 | 1, 1 << 4, 2 << 4]
+    assert bytes(p.bases) == b"ACGTTTGCAGG" and p.read_base.tolist() == [0, 2, 3] and p.ref_off.tolist() == [0, 10, 14]
+    rr, rs, counts = encoder.row_plan([s0, s1], [["A", "C", "T"], ["G"]], False, p.read_base)
+    assert rr.tolist() == [0, 0, -1, 2] and rs.tolist() == [0, 0, 0, 1] and counts == [1, 1, 1, 1]
+    rr, rs, counts = encoder.row_plan([s0, s1], [["A", "C", "T"], ["G"]], True, p.read_base)
+    assert rr.tolist() == [1, -1, -1, -1] and counts == [1, 1, 1, 1]
+    with pytest.raises(ValueError):
+        encoder.pack_sites([encoder.SitePileup(["AC"], [[1]], [[(0, 2)]], [0], [0], [1], [False], [0], "AC", 0, 0, 1, {})])
+    with pytest.raises(ValueError):
+        encoder.pack_sites([encoder.SitePileup(["AC"], [[1, 2]], [[(0, 3)]], [0], [0], [1], [False], [0], "AC", 0, 0, 1, {})])
