@@ -162,13 +162,16 @@ class DevicePackedReads:
         up = lambda a: torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).to(self.device, non_blocking=non_blocking)
         self.t = {f: up(getattr(packed, f)) for f in packed.__dataclass_fields__ if f != "read_base"}
 
-    def encode(self, row_read: np.ndarray, row_site: np.ndarray, channels: int = 6,
+    def encode(self, row_read, row_site, channels: int = 6,
                feature_length: int = FEATURE_LENGTH, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """uint8 [n_rows, feature_length, channels] on the device (asynchronous, on the current stream)."""
         lib = _load()
-        n = int(row_read.size)
-        rr = torch.from_numpy(row_read).to(self.device, non_blocking=True)
-        rs = torch.from_numpy(row_site).to(self.device, non_blocking=True)
+        as_dev = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a, np.int32))
+        rr = as_dev(row_read).to(self.device, non_blocking=True)      # device tensors are used as they are
+        rs = as_dev(row_site).to(self.device, non_blocking=True)
+        if rr.dtype != torch.int32 or rs.dtype != torch.int32 or rr.numel() != rs.numel():
+            raise ValueError("row_read / row_site must be int32 arrays of equal length")
+        n = int(rr.numel())
         if out is None:
             out = torch.empty((n, feature_length, channels), dtype=torch.uint8, device=self.device)
         b = HelloEncodeBatch()

@@ -185,3 +185,45 @@ def pair_offsets(site_allele_off: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(n.numel() + 1, dtype=torch.int64)
     out[1:] = torch.cumsum(n * (n + 1) // 2, 0)
     return out
+
+
+def make_packed_reads(n_sites: int, coverage: int = 30, read_len: int = 150, seed: int = 13, hp: bool = False):
+    """Aligned reads for the GPU feature encoder, generated vectorised (numpy) straight in the packed layout of
+    include/hello_encode.h: every read is `M a, I b, M c, D d, M e` (b or d may be 0 -> the operation is dropped to a
+    0-length one, which the CIGAR walk skips) starting 0..119 bases before the 150-wide window centre.
+    Returns (hello_b200.encoder.PackedReads, row_read int32, row_site int32) with one row per read in site order."""
+    import numpy as np
+    from .encoder import PackedReads
+    rng = np.random.default_rng(seed)
+    per_site = np.maximum(rng.poisson(coverage, n_sites), 1)
+    R = int(per_site.sum())
+    site_of = np.repeat(np.arange(n_sites, dtype=np.int32), per_site)
+    ref_len = 450
+    window_start = rng.integers(10_000, 200_000_000, n_sites).astype(np.int64)
+    a0 = window_start + 225 + rng.integers(-10, 10, n_sites)
+    a1 = a0 + rng.integers(1, 10, n_sites)
+    start = (a0 + a1) // 2 - 75
+    ins = np.where(rng.random(R) < 0.15, rng.integers(1, 8, R), 0)
+    dele = np.where(rng.random(R) < 0.15, rng.integers(1, 8, R), 0)
+    m1 = rng.integers(20, 60, R)
+    m2 = rng.integers(20, 60, R)
+    m3 = np.maximum(read_len - ins - m1 - m2, 1)
+    lens = (m1 + ins + m2 + m3).astype(np.int64)
+    ref_start = start[site_of] - rng.integers(0, 120, R)
+    ref_start = np.maximum(ref_start, window_start[site_of] + 1)
+    read_off = np.zeros(R + 1, np.int64)
+    np.cumsum(lens, out=read_off[1:])
+    total = int(read_off[-1])
+    bases = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, total)]
+    quals = rng.integers(2, 42, total).astype(np.uint8)
+    cig = np.stack([m1 << 4, ins << 4 | 1, m2 << 4, dele << 4 | 2, m3 << 4], axis=1).astype(np.uint32).reshape(-1)
+    cigar_off = np.arange(R + 1, dtype=np.int64) * 5
+    read_base = np.zeros(n_sites + 1, np.int64)
+    np.cumsum(per_site, out=read_base[1:])
+    packed = PackedReads(read_off, bases, quals, cigar_off, cig, ref_start.astype(np.int64),
+                         rng.integers(0, 61, R).astype(np.uint8), rng.choice(np.array([-1, 1], np.int8), R),
+                         rng.integers(0, 3, R).astype(np.uint8) if hp else np.zeros(R, np.uint8), read_base,
+                         np.arange(n_sites + 1, dtype=np.int64) * ref_len,
+                         np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n_sites * ref_len)],
+                         window_start, a0.astype(np.int64), a1.astype(np.int64))
+    return packed, np.arange(R, dtype=np.int32), site_of

@@ -88,3 +88,31 @@ def test_encoder_rejects_bad_arguments(encoder):
     assert lib.hello_encode_reads(C.byref(b), 1, None) == -1 and b"missing" in lib.hello_encode_last_error()
     b.n_rows = 0
     assert lib.hello_encode_reads(C.byref(b), 1, None) == 0
+
+
+def test_encoder_at_scale_properties(encoder):
+    """1.5 M rows (50 k sites x 30x): a random sample of rows equals the oracle; encoding a permutation of the rows
+    gives the permuted bytes (rows are independent); a second launch is bit-identical."""
+    from hello_b200 import synth
+    from oracle import encoder_oracle as E
+    packed, row_read, row_site = synth.make_packed_reads(50_000, 30, seed=5)
+    dp = encoder.DevicePackedReads(packed, DEV)
+    out = dp.encode(row_read, row_site, 6)
+    R = row_read.size
+    assert out.shape == (R, 150, 6)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(R).astype(np.int64)
+    out_p = dp.encode(row_read[perm], row_site[perm], 6)
+    assert torch.equal(out_p, out[torch.from_numpy(perm).to(DEV)])
+    assert torch.equal(dp.encode(row_read, row_site, 6), out)
+    host = out.cpu().numpy()
+    p = packed
+    for r in rng.choice(R, 300, replace=False):
+        s = int(row_site[r])
+        site = E.SitePileup([bytes(p.bases[p.read_off[r]:p.read_off[r + 1]]).decode()],
+                            [list(p.quals[p.read_off[r]:p.read_off[r + 1]])],
+                            [[(int(c) & 15, int(c) >> 4) for c in p.cigars[p.cigar_off[r]:p.cigar_off[r + 1]]]],
+                            [int(p.ref_start[r])], [int(p.mapq[r])], [int(p.orientation[r])], [False], [0],
+                            bytes(p.reference[p.ref_off[s]:p.ref_off[s + 1]]).decode(), int(p.window_start[s]),
+                            int(p.assembly_start[s]), int(p.assembly_stop[s]), {"a": [0]})
+        assert np.array_equal(host[r], E.compute_features_colored_simple(site, "a", 150, False, False)[0]), r
