@@ -2,7 +2,7 @@
 // c++/src/AlleleSearcherLiteFiltered.cpp:1031-1180) for a whole batch of rows in one launch.
 //
 // One warp per output row.  The 150 window positions are spread over the lanes (position = lane + 32 k, 5 per lane)
-// and kept in registers as one 64-bit word of up to 7 channel bytes each; the CIGAR is walked operation by operation
+// and kept in registers as two 32-bit words of channel bytes each; the CIGAR is walked operation by operation
 // by the whole warp (the operations are warp-uniform), every lane colouring the window positions it owns, so later
 // operations overwrite earlier ones exactly as the sequential C++ does.  The finished row is staged in shared memory
 // and written with coalesced 32-bit stores (a row is 900 or 1050 contiguous bytes).  HBM-bound byte work: ~0.4 KB of
@@ -25,103 +25,101 @@ struct Luts { uint8_t base_q[256]; uint8_t map_q[256]; };
 __device__ __forceinline__ uint32_t base_color(uint8_t b) {            // :971-984
     return b == 'A' ? 250u : b == 'G' ? 180u : b == 'T' ? 100u : b == 'C' ? 30u : 0u;
 }
-__device__ __forceinline__ unsigned long long set_byte(unsigned long long w, int track, uint32_t v) {
-    const int sh = track * 8;
-    return (w & ~(0xffull << sh)) | ((unsigned long long)(v & 0xffu) << sh);
-}
 
+// Per window position f the tracks split into what depends only on (site, read, f) -- reference base, mapq, strand,
+// position marker, hp: the "constant" words, computed once per row -- and what the CIGAR walk decides: read base and
+// base quality.  Low word = tracks 0-3 (read base, ref base, quality, mapq), high word = tracks 4-6.  All window
+// arithmetic is 32-bit and relative to the window start.
 __global__ void __launch_bounds__(WARPS * 32) encode_reads_kernel(const hello_encode_batch b, const Luts lut,
                                                                    uint8_t* __restrict__ out) {
     __shared__ __align__(16) uint8_t stage[WARPS][MAX_L * 8];
+    __shared__ uint8_t s_base[256], s_qual[256];
+    s_base[threadIdx.x] = (uint8_t)base_color((uint8_t)threadIdx.x);
+    s_qual[threadIdx.x] = lut.base_q[threadIdx.x];
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * WARPS + warp;
     if (row >= b.n_rows) return;
     const int L = b.feature_length, C = b.channels;
-    unsigned long long px[PER_LANE];
+    uint32_t lo[PER_LANE], hi[PER_LANE];
 #pragma unroll
-    for (int k = 0; k < PER_LANE; ++k) px[k] = 0ull;
+    for (int k = 0; k < PER_LANE; ++k) { lo[k] = 0u; hi[k] = 0u; }
     const int rid = b.d_row_read[row];
     if (rid >= 0) {
         const int site = b.d_row_site[row];
         const long long wstart = b.d_window_start[site], a0 = b.d_assembly_start[site], a1 = b.d_assembly_stop[site];
-        const uint8_t* ref = b.d_reference + b.d_ref_off[site];
-        const long long start = (a0 + a1) / 2 - (long long)(L / 2), end = start + L;
+        const long long start = (a0 + a1) / 2 - (long long)(L / 2);
+        const long long ref_len = b.d_ref_off[site + 1] - b.d_ref_off[site];
+        const uint8_t* refw = b.d_reference + b.d_ref_off[site] + (start - wstart);     // reference base of window position f
+        const long long ref_lo = wstart - start, ref_hi = ref_lo + ref_len;             // valid f range of refw
+        // PositionColor (:1007-1015) compares unsigned offsets from windowStart
+        const long long p_lo = a0 >= wstart ? a0 - start : (1ll << 40), p_hi = a1 >= wstart ? a1 - start : (1ll << 40);
         const uint8_t* bases = b.d_bases + b.d_read_off[rid];
         const uint8_t* quals = b.d_quals + b.d_read_off[rid];
         const long long c0 = b.d_cigar_off[rid], c1 = b.d_cigar_off[rid + 1];
-        long long rf = b.d_ref_start[rid], rd = 0;
         const uint32_t mq = lut.map_q[b.d_mapq[rid]];
         const uint32_t sc = b.d_orientation[rid] > 0 ? 70u : 240u;
         const uint32_t hp_raw = C == 7 ? b.d_hp[rid] : 0u;
         const uint32_t hc = hp_raw == 1 ? 120u : (hp_raw == 2 ? 240u : 0u);
-        // tracks every coloured position gets: mapq, strand, (hp)
-        unsigned long long common = ((unsigned long long)mq << (8 * T_READ_MAPQ)) | ((unsigned long long)sc << (8 * T_ORIENT));
-        if (C == 7) common |= (unsigned long long)hc << (8 * T_HP);
-        auto pos_color = [&](long long pos) -> uint32_t {               // :1007-1015 (unsigned comparison in the C++)
-            const unsigned long long p = (unsigned long long)(pos - wstart);
-            return ((unsigned long long)(a0 - wstart) <= p && p < (unsigned long long)(a1 - wstart)) ? 240u : 70u;
-        };
+        uint32_t cst_lo[PER_LANE], cst_hi[PER_LANE];
+#pragma unroll
+        for (int k = 0; k < PER_LANE; ++k) {
+            const int f = lane + 32 * k;
+            const uint32_t rc = (f >= ref_lo && f < ref_hi) ? s_base[__ldg(refw + f)] : 0u;
+            const uint32_t pc = (f >= p_lo && f < p_hi) ? 240u : 70u;
+            cst_lo[k] = (rc << 8) | (mq << 24);
+            cst_hi[k] = sc | (pc << 8) | (hc << 16);
+        }
+        // window-relative reference cursor, clamped far outside the window instead of overflowing
+        const long long rel = b.d_ref_start[rid] - start;
+        int rf = (int)max(-(1ll << 30), min(1ll << 30, rel));
+        int rd = 0;
         for (long long ci = c0; ci < c1; ++ci) {
             const uint32_t cg = __ldg(b.d_cigars + ci);
             const uint32_t op = cg & 15u;
-            const long long len = cg >> 4;
+            const int len = (int)(cg >> 4);
             if (op == 0 || op == 7 || op == 8) {                         // M, =, X
-                if (rf < end && rf + len > start) {
+                if (rf < L && rf + len > 0) {
 #pragma unroll
                     for (int k = 0; k < PER_LANE; ++k) {
                         const int f = lane + 32 * k;
-                        const long long pos = start + f;
-                        if (f < L && pos >= rf && pos < rf + len) {
-                            const long long j = pos - rf;
-                            unsigned long long w = common;
-                            w |= (unsigned long long)base_color(__ldg(bases + rd + j)) << (8 * T_READ_BASE);
-                            w |= (unsigned long long)base_color(__ldg(ref + (pos - wstart))) << (8 * T_REF_BASE);
-                            w |= (unsigned long long)lut.base_q[__ldg(quals + rd + j)] << (8 * T_READ_QUAL);
-                            w |= (unsigned long long)pos_color(pos) << (8 * T_POSITION);
-                            px[k] = w;
+                        const int j = f - rf;
+                        if (f < L && j >= 0 && j < len) {
+                            lo[k] = cst_lo[k] | s_base[__ldg(bases + rd + j)] | ((uint32_t)s_qual[__ldg(quals + rd + j)] << 16);
+                            hi[k] = cst_hi[k];
                         }
                     }
                 }
-                rf += len; rd += len;
+                rf = min(rf + len, 1 << 30); rd += len;
             } else if (op == 2 || op == 3) {                             // D (falls through into N)
-                if (op == 2 && start <= rf - 1 && rf - 1 < end) {
-                    const uint32_t q0 = rd > 0 ? lut.base_q[__ldg(quals + rd - 1)] : 0u;
+                if (op == 2 && rf - 1 >= 0 && rf - 1 < L) {
+                    const uint32_t q0 = rd > 0 ? s_qual[__ldg(quals + rd - 1)] : 0u;
 #pragma unroll
                     for (int k = 0; k < PER_LANE; ++k) {
                         const int f = lane + 32 * k;
-                        const long long pos = start + f;
-                        if (f < L && pos >= rf - 1 && pos < rf + len) {
-                            // reference base, mapq, strand, position marker, hp; read base / quality keep their value
-                            unsigned long long w = px[k];
-                            w = set_byte(w, T_REF_BASE, base_color(__ldg(ref + (pos - wstart))));
-                            w = set_byte(w, T_READ_MAPQ, mq);
-                            w = set_byte(w, T_ORIENT, sc);
-                            w = set_byte(w, T_POSITION, pos_color(pos));
-                            if (C == 7) w = set_byte(w, T_HP, hc);
-                            if (pos == rf - 1) {                          // '*' and the quality of the base before the gap
-                                w = set_byte(w, T_READ_BASE, 0u);
-                                w = set_byte(w, T_READ_QUAL, q0);
-                            }
-                            px[k] = w;
+                        if (f < L && f >= rf - 1 && f < rf + len) {
+                            // reference base, mapq, strand, position marker, hp; read base / quality keep their value,
+                            // except at the base before the gap: '*' and that base's quality
+                            lo[k] = f == rf - 1 ? (cst_lo[k] | (q0 << 16)) : ((lo[k] & 0x00ff00ffu) | cst_lo[k]);
+                            hi[k] = cst_hi[k];
                         }
                     }
                 }
-                rf += len;
+                rf = min(rf + len, 1 << 30);
             } else if (op == 1 || op == 4) {                             // I (falls through into S)
-                if (op == 1 && start <= rf - 1 && rf - 1 < end) {
-                    const long long lo = rd > 0 ? rd - 1 : rd, hi = rd + len;
+                if (op == 1 && rf - 1 >= 0 && rf - 1 < L) {
+                    const int q_lo = rd > 0 ? rd - 1 : rd, q_hi = rd + len;
                     uint32_t qmin = 255u;                                // min over the base before and the inserted bases
-                    for (long long t = lo + lane; t < hi; t += 32) qmin = min(qmin, (uint32_t)__ldg(quals + t));
+                    for (int t = q_lo + lane; t < q_hi; t += 32) qmin = min(qmin, (uint32_t)__ldg(quals + t));
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) qmin = min(qmin, __shfl_xor_sync(0xffffffffu, qmin, d));
-                    const long long pos = rf - 1;
-                    const int f = (int)(pos - start);
-                    unsigned long long w = common;
-                    w |= (unsigned long long)base_color(__ldg(ref + (pos - wstart))) << (8 * T_REF_BASE);
-                    w |= (unsigned long long)lut.base_q[qmin] << (8 * T_READ_QUAL);
-                    w |= (unsigned long long)pos_color(pos) << (8 * T_POSITION);
+                    const uint32_t qc = (uint32_t)s_qual[qmin] << 16;
 #pragma unroll
-                    for (int k = 0; k < PER_LANE; ++k) px[k] = (f == lane + 32 * k) ? w : px[k];   // selects keep px in registers
+                    for (int k = 0; k < PER_LANE; ++k) {                 // selects keep the arrays in registers
+                        const bool hit = rf - 1 == lane + 32 * k;
+                        lo[k] = hit ? (cst_lo[k] | qc) : lo[k];
+                        hi[k] = hit ? cst_hi[k] : hi[k];
+                    }
                 }
                 rd += len;
             }
@@ -134,7 +132,10 @@ __global__ void __launch_bounds__(WARPS * 32) encode_reads_kernel(const hello_en
     for (int k = 0; k < PER_LANE; ++k) {
         const int f = lane + 32 * k;
         if (f < L) {
-            for (int c = 0; c < C; ++c) st[f * C + c] = (uint8_t)(px[k] >> (8 * c));
+            uint8_t* q = st + f * C;
+            q[0] = (uint8_t)lo[k]; q[1] = (uint8_t)(lo[k] >> 8); q[2] = (uint8_t)(lo[k] >> 16); q[3] = (uint8_t)(lo[k] >> 24);
+            q[4] = (uint8_t)hi[k]; q[5] = (uint8_t)(hi[k] >> 8);
+            if (C == 7) q[6] = (uint8_t)(hi[k] >> 16);
         }
     }
     __syncwarp();
