@@ -420,3 +420,47 @@ def test_read_order_and_site_independence(gpu):
         sub = net.forward((pl.reads[0][r0:r1].transpose(1, 2), None), [a1 - a0],
                           (torch.diff(aro[a0:a1 + 1]).tolist(), None), None)
         assert torch.equal(sub, full[a0:a1])
+
+
+def test_properties_at_scale(gpu):
+    """60 k ragged-coverage sites (15x-60x, ~2.3 M reads) through a deliberately small workspace (many chunks):
+    two runs are bit-identical; 150 random sites re-run on their own give bit-identical logits, pair probabilities and
+    calls (sites are independent of batch composition and chunk boundaries); a random sample agrees with the oracle;
+    every site's mixture probabilities are a sub-distribution and the call is its argmax."""
+    from oracle import hello_oracle as O
+    cfg = arch.CONFIGS["single_tech"]
+    pl = synth.make_pileups(60_000, coverage=(15, 60), channels=cfg.read_cin, seed=2024, device=DEV)
+    net = net_for(gpu, cfg, "bf16x3", workspace_bytes=1 << 30)
+    batch = gpu.DeviceBatch.from_pileups(pl, DEV)
+    a = net.engine.run(batch)
+    logits_a, pp_a, bp_a = a.logits.clone(), a.pair_prob.clone(), a.best_pair.clone()
+    b = net.engine.run(batch)
+    assert torch.equal(logits_a, b.logits) and torch.equal(pp_a, b.pair_prob) and torch.equal(bp_a, b.best_pair)
+    sao, aro, off = pl.site_allele_off, pl.allele_read_off[0], a.pair_off
+    rng = np.random.default_rng(3)
+    picks = np.sort(rng.choice(60_000, 150, replace=False))
+    reads = torch.cat([pl.reads[0][int(aro[sao[s]]):int(aro[sao[s + 1]])] for s in picks])
+    nrpa = torch.cat([torch.diff(aro[int(sao[s]):int(sao[s + 1]) + 1]) for s in picks]).tolist()
+    naps = [int(sao[s + 1] - sao[s]) for s in picks]
+    sub_net = net_for(gpu, cfg, "bf16x3")
+    sub = sub_net.forward((reads.transpose(1, 2), None), naps, (nrpa, None), None)
+    r = sub_net.last_result
+    idx_a = torch.cat([torch.arange(int(sao[s]), int(sao[s + 1])) for s in picks])
+    idx_p = torch.cat([torch.arange(int(off[s]), int(off[s + 1])) for s in picks])
+    assert torch.equal(sub.reshape(-1).cpu(), logits_a[0].cpu()[idx_a])
+    assert torch.equal(r.pair_prob.cpu(), pp_a.cpu()[:, idx_p]) and torch.equal(r.best_pair.cpu(), bp_a.cpu()[picks])
+    # oracle on 40 of them
+    orc = oracle_for(cfg)
+    some = picks[:40]
+    reads_s = torch.cat([pl.reads[0][int(aro[sao[s]]):int(aro[sao[s + 1]])] for s in some]).cpu()
+    nrpa_s = torch.cat([torch.diff(aro[int(sao[s]):int(sao[s + 1]) + 1]) for s in some]).tolist()
+    ref = orc.forward((reads_s.transpose(1, 2), None), [int(sao[s + 1] - sao[s]) for s in some], (nrpa_s, None), None)
+    idx_s = torch.cat([torch.arange(int(sao[s]), int(sao[s + 1])) for s in some])
+    assert (logits_a[0].cpu()[idx_s] - ref.reshape(-1)).abs().max().item() < TOL_LOGIT["bf16x3"]
+    # per-site sanity over the whole batch
+    pp = pp_a[0].cpu()
+    site_of_pair = torch.repeat_interleave(torch.arange(60_000), torch.diff(off))
+    mass = torch.zeros(60_000).index_add_(0, site_of_pair, pp)
+    assert float(mass.max()) <= 1.0 + 1e-4 and float(pp.min()) >= 0.0
+    best = torch.zeros(60_000).index_reduce_(0, site_of_pair, pp, "amax", include_self=False)
+    assert torch.equal(best, a.best_prob.cpu())
