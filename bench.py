@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of per-site results")
     ap.add_argument("--workspace-gb", type=float, default=6.0)
     ap.add_argument("--chunk-sites", type=int, default=0, help="cap on sites per internal chunk (0 = auto)")
-    ap.add_argument("--e2e-chunk-sites", type=int, default=32768)
+    ap.add_argument("--e2e-chunk-sites", type=int, default=65536)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sites", type=int, default=0, help="sites per CPU step (0 = 128 per worker)")

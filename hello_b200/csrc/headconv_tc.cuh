@@ -153,7 +153,7 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
         const int i = m / PITCH, p = m - i * PITCH;
         const bool valid = (i < n) && (p < LVALID);
         const bool in_buf = m < ROWS;
-#pragma unroll
+#pragma unroll 1                                  // blocks are serial anyway (TMEM load wait); keeps the kernel ~2x smaller
         for (int b = 0; b < NB; ++b) {
             const int c0 = (chalf * NB + b) * 32;
             float v[32];
@@ -289,7 +289,7 @@ __device__ __forceinline__ uint32_t phase_bytes(int ph) {
     return ph == 0 ? k16 * per16 * C : ph == 1 ? 4 * k16 * per16 * 2 * C : 6 * k16 * per16 * 2 * C;
 }
 
-template <int MODE, int C>
+template <int MODE, int C, bool DBG>
 __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const __grid_constant__ HeadParams prm) {
     using Gm = Geo<C>;
     constexpr int NGRP = Gm::NGRP, CS = Gm::CS, G = Gm::G;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                 ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
                 ++acc_n;
                 ptx::tc_fence_after();
-                float* dbg = (prm.dbg && prm.dbg_phase == ph)
+                float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph)
                                  ? prm.dbg + ((long long)item * NGRP + g) * (DBG_ROWS * DBG_COLS) : nullptr;
                 if (ph == 0) {
                     epi_conv<MODE, C, C, 2, Gm::P1, Gm::L, false, false, false, OUT_EO>(
@@ -570,13 +570,17 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, const f
         delete t;
         return nullptr;
     }
-    cudaError_t e;
-    if (C == 64)
-        e = t->mode == 3 ? cudaFuncSetAttribute(headconv_tc_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(headconv_tc_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else
-        e = t->mode == 3 ? cudaFuncSetAttribute(headconv_tc_kernel<3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                         : cudaFuncSetAttribute(headconv_tc_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaSuccess;
+    auto opt_in = [&](const void* fn) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    };
+    if (C == 64) {
+        if (t->mode == 3) { opt_in((const void*)headconv_tc_kernel<3, 64, false>); opt_in((const void*)headconv_tc_kernel<3, 64, true>); }
+        else { opt_in((const void*)headconv_tc_kernel<1, 64, false>); opt_in((const void*)headconv_tc_kernel<1, 64, true>); }
+    } else {
+        if (t->mode == 3) { opt_in((const void*)headconv_tc_kernel<3, 128, false>); opt_in((const void*)headconv_tc_kernel<3, 128, true>); }
+        else { opt_in((const void*)headconv_tc_kernel<1, 128, false>); opt_in((const void*)headconv_tc_kernel<1, 128, true>); }
+    }
     if (e != cudaSuccess) {
         err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         cudaFree(t->d_weights); cudaFree(t->d_bias); delete t;
@@ -604,13 +608,18 @@ static cudaError_t headconv_tc_launch(HeadConvTC* t, const float* in_a, const fl
     if (work > 0x7fffffffLL) return cudaErrorInvalidValue;
     prm.n_work = (int)work;
     const int grid = (int)std::min<long long>(work, t->sm_count);
+    const bool debug = dbg != nullptr;
+#define HELLO_HEAD_LAUNCH(M, CC) \
+    do { \
+        if (debug) hc::headconv_tc_kernel<M, CC, true><<<grid, hc::Geo<CC>::THREADS, hc::Geo<CC>::SMEM_BYTES, st>>>(prm); \
+        else hc::headconv_tc_kernel<M, CC, false><<<grid, hc::Geo<CC>::THREADS, hc::Geo<CC>::SMEM_BYTES, st>>>(prm); \
+    } while (0)
     if (t->C == 64) {
-        if (t->mode == 3) hc::headconv_tc_kernel<3, 64><<<grid, hc::Geo<64>::THREADS, hc::Geo<64>::SMEM_BYTES, st>>>(prm);
-        else hc::headconv_tc_kernel<1, 64><<<grid, hc::Geo<64>::THREADS, hc::Geo<64>::SMEM_BYTES, st>>>(prm);
+        if (t->mode == 3) HELLO_HEAD_LAUNCH(3, 64); else HELLO_HEAD_LAUNCH(1, 64);
     } else {
-        if (t->mode == 3) hc::headconv_tc_kernel<3, 128><<<grid, hc::Geo<128>::THREADS, hc::Geo<128>::SMEM_BYTES, st>>>(prm);
-        else hc::headconv_tc_kernel<1, 128><<<grid, hc::Geo<128>::THREADS, hc::Geo<128>::SMEM_BYTES, st>>>(prm);
+        if (t->mode == 3) HELLO_HEAD_LAUNCH(3, 128); else HELLO_HEAD_LAUNCH(1, 128);
     }
+#undef HELLO_HEAD_LAUNCH
     return cudaGetLastError();
 }
 

@@ -400,7 +400,9 @@ __device__ __forceinline__ long long* trace_slot(const TcParams& prm, int item, 
     return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * NG + g) * N_PHASES) * 4;
 }
 
-template <int MODE>
+// DBG = false is the production kernel: the layer dump and the timeline stamps are compiled out (the kernel is ~9 k
+// instructions; every KB less helps the instruction cache, whose misses show up as stall_no_inst in the epilogues).
+template <int MODE, bool DBG>
 __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_constant__ TcParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
@@ -457,14 +459,14 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
             ptx::fence_proxy_async();
             ptx::mbar_arrive(bar(BAR_ACT + g));
             float* gout = prm.out + r0 * (long long)(LOUT * COUT);
-            long long* tr = trace_slot(prm, item, g);
+            long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
                 ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
                 ++acc_n;
                 ptx::tc_fence_after();
                 if (tr && tid == 0) tr[ph * 4 + 2] = clock64();
-                float* dbg = (prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * NG + g) * (T1 * 128 * 64) : nullptr;
+                float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * NG + g) * (T1 * 128 * 64) : nullptr;
                 if (ph == 0) {
                     epi_conv<MODE, true, 16, T1, P1, LV1, false, false, false, false, OUT_NAT, 0>(
                         act, tl, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr);
@@ -520,7 +522,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         const uint32_t d0 = tmem_base + g * GRP_COLS;
         for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
             const int n = (int)max(0LL, min((long long)G, R - ((long long)item * NG + g) * G));
-            long long* tr = trace_slot(prm, item, g);
+            long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
                 const uint32_t slot = w_n & 1u;
@@ -739,9 +741,12 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
         delete t;
         return nullptr;
     }
-    cudaError_t e = t->mode == 3
-        ? cudaFuncSetAttribute(readconv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES)
-        : cudaFuncSetAttribute(readconv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaSuccess;
+    auto opt_in = [&](const void* fn) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    };
+    if (t->mode == 3) { opt_in((const void*)readconv_tc_kernel<3, false>); opt_in((const void*)readconv_tc_kernel<3, true>); }
+    else { opt_in((const void*)readconv_tc_kernel<1, false>); opt_in((const void*)readconv_tc_kernel<1, true>); }
     if (e != cudaSuccess) {
         err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         cudaFree(t->d_weights); cudaFree(t->d_bias); delete t;
@@ -769,10 +774,14 @@ static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long 
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
     prm.n_items = (int)items;
     const int grid = (int)std::min<long long>(items, t->sm_count);
-    if (t->mode == 3)
-        tc::readconv_tc_kernel<3><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
-    else
-        tc::readconv_tc_kernel<1><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
+    const bool debug = dbg != nullptr;
+    if (t->mode == 3) {
+        if (debug) tc::readconv_tc_kernel<3, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
+        else tc::readconv_tc_kernel<3, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
+    } else {
+        if (debug) tc::readconv_tc_kernel<1, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
+        else tc::readconv_tc_kernel<1, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
+    }
     return cudaGetLastError();
 }
 
