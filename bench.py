@@ -136,7 +136,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "model": cfg_name, "sites_per_step": n_sites, "coverage": cov},
+        "config": {"workload": args.workload, "wiring": cfg_name, "sites_per_step": n_sites, "coverage": cov},
         "cpu_baseline": {"value": value, "unit": "sites/s", "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -350,8 +350,8 @@ def run_ours(args):
         "stage_share_of_step": rc_ms / ms_total if ms_total > 0 else None,
         "note": {"fp32": "fp32 mode runs the convolutions on CUDA cores (FFMA); the fraction is quoted against the bf16 "
                          "tensor-core peak the north star targets",
-                 "bf16x3": "one fused tcgen05 kernel per chunk; bf16x3 issues 3 MMAs per algorithmic MAC (hi*hi + hi*lo + "
-                           "lo*hi, fp32 accumulate), so the ceiling of `frac` is 1/3 by construction",
+                 "bf16x3": "one fused tcgen05 kernel per chunk; bf16x3 computes 3 products per algorithmic MAC (hi*hi + hi*lo "
+                           "+ lo*hi as two instructions, fp32 accumulate), so the ceiling of `frac` is 1/3 by construction",
                  "bf16": "one fused tcgen05 kernel per chunk; single bf16 MMA per MAC (fast mode, ~1e-1 logit error)"
                  }[args.precision],
     }
@@ -370,7 +370,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)"}[args.precision],
         "data": "synthetic",
-        "config": {"workload": "%s_%dk_sites_per_gpu" % (args.workload, args.sites // 1000), "model": cfg_name,
+        "config": {"workload": "%s_%dk_sites_per_gpu" % (args.workload, args.sites // 1000), "wiring": cfg_name,
                    "weights": "random-init (seed 13), shipped blobs are git-lfs pointers", "sites_per_gpu": S,
                    "alleles_per_gpu": A, "reads_per_gpu": R, "coverage": cov, "precision": args.precision,
                    "partition": "sites sharded across ranks, no collective inside the forward" +
