@@ -321,8 +321,9 @@ __device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float*
 //   A_LBO   distance between 8-channel chunk arrays;  A_LO  distance to the "lo" copy of the activations
 //   STACK   bf16x3 as two instructions: A_hi x [W_hi | W_lo] -> D[0,2N), A_lo x W_hi -> D[0,N);
 //           otherwise three instructions into D[0,N) (used where the accumulator columns are scarce)
-//   PART 0: every tap but the last;  PART 1: the last tap.  The issuer hands the tensor-pipe token to the other
-//   group between the two parts, so the hand-over latency hides behind this group's last third.
+//   PART 0: all but the last few (tap, 16-channel) steps;  PART 1: those last steps.  The issuer hands the tensor-pipe
+//   token to the next group between the two parts, so the hand-over latency hides behind this group's last MMAs
+//   (a longer tail only interleaves the two groups in the pipe's FIFO and delays this group's accumulators).
 template <int MODE, int PART, bool STACK, int N, int NTAPS, int K16, bool A_HAS_LO, uint32_t AO0, uint32_t AO1,
           uint32_t AO2, uint32_t A_LBO, uint32_t A_LO, uint32_t B_UNIT0>
 __device__ __forceinline__ void issue_tile(uint32_t act_lo, uint32_t w_lo, uint32_t d) {
@@ -331,13 +332,16 @@ __device__ __forceinline__ void issue_tile(uint32_t act_lo, uint32_t w_lo, uint3
     constexpr uint32_t UNIT = BROWS * 32;
     constexpr uint32_t idesc_n = ptx::idesc_bf16_m128(N);
     constexpr uint32_t idesc_2n = ptx::idesc_bf16_m128(2 * N);
-    constexpr int T_BEGIN = PART == 0 ? 0 : NTAPS - 1, T_END = PART == 0 ? NTAPS - 1 : NTAPS;
+    // PART 1 = the last TAIL (tap, 16-channel) steps: ~4 MMAs per group, enough to cover the token hand-over
+    constexpr int STEPS = NTAPS * K16;
+    constexpr int TAIL = NTAPS == 1 ? STEPS : (K16 >= 4 ? 2 : 1);
+    constexpr int S_BEGIN = PART == 0 ? 0 : STEPS - TAIL, S_END = PART == 0 ? STEPS - TAIL : STEPS;
     const uint32_t a0 = act_lo | (((A_LBO >> 4) & 0x3FFFu) << 16);
     const uint32_t b0 = (w_lo + ((B_UNIT0 * UNIT) >> 4)) | (((BROWS * 16u) >> 4) << 16);
 #pragma unroll
-    for (int t = T_BEGIN; t < T_END; ++t) {
-#pragma unroll
-        for (int j = 0; j < K16; ++j) {
+    for (int s = S_BEGIN; s < S_END; ++s) {
+        {
+            const int t = s / K16, j = s - t * K16;
             const uint32_t a = a0 + AO[t] + (uint32_t)j * ((2u * A_LBO) >> 4);
             const uint32_t b = b0 + (uint32_t)(t * K16 + j) * (UNIT >> 4);
             const uint32_t acc = (t == 0 && j == 0) ? 0u : 1u;
