@@ -121,8 +121,9 @@ __device__ __forceinline__ void store_chunk8(uint8_t* p, uint32_t lo_delta, cons
         uint32_t l[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float h0 = __uint_as_float(h[q] << 16), h1 = __uint_as_float(h[q] & 0xffff0000u);
-            l[q] = ptx::pack_bf16x2(v[2 * q] - h0, v[2 * q + 1] - h1);
+            float d0 = v[2 * q], d1 = v[2 * q + 1];
+            ptx::sub2(d0, d1, __uint_as_float(h[q] << 16), __uint_as_float(h[q] & 0xffff0000u));
+            l[q] = ptx::pack_bf16x2(d0, d1);
         }
         *reinterpret_cast<uint4*>(p + lo_delta) = make_uint4(l[0], l[1], l[2], l[3]);
     }
@@ -193,14 +194,18 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
         float x[16];
         ptx::tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            float y = TWO ? v[c] + w[c] : v[c];
-            y = fmaxf(y + bias[c0 + c], 0.f);
+        for (int c = 0; c < 16; c += 2) {               // packed fp32x2 adds: same roundings, half the issue slots
+            float y0 = v[c], y1 = v[c + 1];
+            if (TWO) ptx::add2(y0, y1, w[c], w[c + 1]);
+            ptx::add2(y0, y1, bias[c0 + c], bias[c0 + c + 1]);
+            y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f);
             if (RESID) {
-                const float res = blk < 2 ? rr[(blk & 1) * 16 + c] : r[c];
-                y += RES_BIAS ? (res + bias2[c0 + c]) : res;
+                float r0 = blk < 2 ? rr[(blk & 1) * 16 + c] : r[c], r1 = blk < 2 ? rr[(blk & 1) * 16 + c + 1] : r[c + 1];
+                if (RES_BIAS) ptx::add2(r0, r1, bias2[c0 + c], bias2[c0 + c + 1]);
+                ptx::add2(y0, y1, r0, r1);
             }
-            x[c] = valid ? y : 0.f;
+            x[c] = valid ? y0 : 0.f;
+            x[c + 1] = valid ? y1 : 0.f;
         }
         if (WRITE_RESID || MOVE_SC) {
             if (blk < 2) {

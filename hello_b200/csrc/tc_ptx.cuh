@@ -216,6 +216,18 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// Packed fp32x2 add / subtract (Blackwell FADD2): two independent round-to-nearest results, one issue slot.
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ta, tb;\n\tmov.b64 ta, {%0, %1};\n\tmov.b64 tb, {%2, %3};\n\t"
+        "add.rn.f32x2 ta, ta, tb;\n\tmov.b64 {%0, %1}, ta;\n\t}"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void sub2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ta, tb;\n\tmov.b64 ta, {%0, %1};\n\tmov.b64 tb, {%2, %3};\n\t"
+        "sub.rn.f32x2 ta, ta, tb;\n\tmov.b64 {%0, %1}, ta;\n\t}"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+
 // two fp32 -> packed bf16x2 (round to nearest even); `lo` lands in the low half
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
