@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/hello_moe.h"
@@ -165,42 +166,42 @@ template <int MODE, bool STACK, int N, int TILES, int PITCH, int LVALID, bool RE
           bool MOVE_SC, int OUT, int LEAD>
 __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float* bias, const float* bias2, int n_reads,
                                          uint32_t out_stride, uint32_t out_lo, float* __restrict__ gout,
-                                         float* __restrict__ dbg, int wrow, int lane, float (&rr)[32]) {
+                                         float* __restrict__ dbg, int wrow, int lane, float (&rr)[32],
+                                         long long* tr = nullptr) {
     static_assert(TILES * N == 64, "four 16-column blocks per layer");
     constexpr int ROWS = G * PITCH;
     constexpr int BPT = N / 16;                       // blocks per tile
     constexpr bool TWO = MODE == 3 && STACK;
     constexpr uint32_t TILE_COLS = TWO ? 2 * N : N;
-    // Software pipeline over the four blocks: the TMEM loads of block b+1 are in flight while block b is packed and
-    // stored.
-    float v[16];
-    float w[TWO ? 16 : 1];
-    float r[(RESID || MOVE_SC) ? 16 : 1];
-    auto issue_loads = [&](int blk) {
-        const int tile = blk / BPT, c0 = (blk - tile * BPT) * 16;
-        ptx::tmem_ld16(tl + tile * TILE_COLS + c0, v);
-        if (TWO) ptx::tmem_ld16(tl + tile * TILE_COLS + N + c0, w);
-        if (RESID && blk >= 2) ptx::tmem_ld16(tl + RES_COL + (blk - 2) * 16, r);
-        if (MOVE_SC) ptx::tmem_ld16(tl + 64 + c0, r);
-    };
-    issue_loads(0);
-#pragma unroll
-    for (int blk = 0; blk < 4; ++blk) {
+    // One block = 16 accumulator columns of one tile.  REG = the block's residual lives in registers rr[RO .. RO+16)
+    // (blocks 0 and 1), otherwise in TMEM.  The body is instantiated as rarely as the register indexing allows and the
+    // rest is a rolled loop: the kernel's code size is what the instruction cache sees (the epilogues were stalling
+    // on instruction fetch), not its instruction count.
+    auto block = [&](int blk, auto reg_tag, auto ro_tag) {
+        constexpr bool REG = decltype(reg_tag)::value;
+        constexpr int RO = decltype(ro_tag)::value;
         const int tile = blk / BPT, c0 = (blk - tile * BPT) * 16;
         const int m = tile * 128 + wrow + lane;
         const int i = m / PITCH, p = m - i * PITCH;
         const bool valid = (i < n_reads) && (p < LVALID);
         const bool in_buf = m < ROWS;
         float x[16];
+        float w[TWO ? 16 : 1];
+        float r[((RESID && !REG) || MOVE_SC) ? 16 : 1];
+        ptx::tmem_ld16(tl + tile * TILE_COLS + c0, x);
+        if (TWO) ptx::tmem_ld16(tl + tile * TILE_COLS + N + c0, w);
+        if (RESID && !REG) ptx::tmem_ld16(tl + RES_COL + (blk - 2) * 16, r);
+        if (MOVE_SC) ptx::tmem_ld16(tl + 64 + c0, r);
         ptx::tmem_wait_ld();
+        if (tr && blk == 0 && wrow + lane == 0) tr[4] = clock64();
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {               // packed fp32x2 adds: same roundings, half the issue slots
-            float y0 = v[c], y1 = v[c + 1];
+            float y0 = x[c], y1 = x[c + 1];
             if (TWO) ptx::add2(y0, y1, w[c], w[c + 1]);
             ptx::add2(y0, y1, bias[c0 + c], bias[c0 + c + 1]);
             y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f);
             if (RESID) {
-                float r0 = blk < 2 ? rr[(blk & 1) * 16 + c] : r[c], r1 = blk < 2 ? rr[(blk & 1) * 16 + c + 1] : r[c + 1];
+                float r0 = REG ? rr[RO + c] : r[c], r1 = REG ? rr[RO + c + 1] : r[c + 1];
                 if (RES_BIAS) ptx::add2(r0, r1, bias2[c0 + c], bias2[c0 + c + 1]);
                 ptx::add2(y0, y1, r0, r1);
             }
@@ -208,14 +209,13 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
             x[c + 1] = valid ? y1 : 0.f;
         }
         if (WRITE_RESID || MOVE_SC) {
-            if (blk < 2) {
+            if (REG) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) rr[(blk & 1) * 16 + c] = MOVE_SC ? r[c] : x[c];
+                for (int c = 0; c < 16; ++c) rr[RO + c] = MOVE_SC ? r[c] : x[c];
             } else {
                 ptx::tmem_st16(tl + RES_COL + (blk - 2) * 16, MOVE_SC ? r : x);
             }
         }
-        if (blk + 1 < 4) issue_loads(blk + 1);
         if (dbg) {
 #pragma unroll
             for (int c = 0; c < 16; ++c) dbg[m * 64 + c0 + c] = x[c];
@@ -242,6 +242,18 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
                 store_chunk8<MODE>(dst, out_lo, x + 8 * q);
             }
         }
+        if (tr && wrow + lane == 0 && (blk == 0 || blk == 3)) tr[blk == 0 ? 5 : 6] = clock64();
+    };
+    using T = std::true_type;
+    using F = std::false_type;
+    if (RESID || WRITE_RESID || MOVE_SC) {
+        block(0, T{}, std::integral_constant<int, 0>{});
+        block(1, T{}, std::integral_constant<int, 16>{});
+#pragma unroll 1
+        for (int blk = 2; blk < 4; ++blk) block(blk, F{}, std::integral_constant<int, 0>{});
+    } else {
+#pragma unroll 1
+        for (int blk = 0; blk < 4; ++blk) block(blk, F{}, std::integral_constant<int, 0>{});
     }
     if (LEAD && OUT != OUT_GLOBAL && wrow + lane == 0) {          // zero padding row in front of the first read
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -420,13 +432,14 @@ __device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_
 }
 
 // Timeline hook (dbg_phase == TRACE_PHASE): CTA 0 stamps clock64() for its first TRACE_ITEMS work items into the debug
-// buffer as int64 [item][group][phase][4] = {issue start, issue end, accumulators seen by the epilogue, epilogue end}.
+// buffer as int64 [item][group][phase][8] = {issue start, issue end, accumulators seen by the epilogue, epilogue end,
+// first TMEM load landed, first block stored, last block stored, after the operand fence}.
 constexpr int TRACE_PHASE = -2, TRACE_ITEMS = 16;
 __device__ __forceinline__ long long* trace_slot(const TcParams& prm, int item, int g) {
     if (!prm.dbg || prm.dbg_phase != TRACE_PHASE || blockIdx.x != 0) return nullptr;
     const int li = item / (int)gridDim.x;
     if (li >= TRACE_ITEMS) return nullptr;
-    return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * NG + g) * N_PHASES) * 4;
+    return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * NG + g) * N_PHASES) * 8;
 }
 
 // DBG = false is the production kernel: the layer dump and the timeline stamps are compiled out (the kernel is ~9 k
@@ -494,53 +507,54 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                 ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
                 ++acc_n;
                 ptx::tc_fence_after();
-                if (tr && tid == 0) tr[ph * 4 + 2] = clock64();
+                if (tr && tid == 0) tr[ph * 8 + 2] = clock64();
                 float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * NG + g) * (T1 * 128 * 64) : nullptr;
                 if (ph == 0) {
                     epi_conv<MODE, true, 16, T1, P1, LV1, false, false, false, false, OUT_NAT, 0>(
-                        act, tl, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr);
+                        act, tl, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 1) {
                     epi_conv<MODE, true, 16, T1, P1, LV2, false, false, false, false, OUT_EO, 0>(
-                        act, tl, s_bias + B_L2, nullptr, n, A2_ARR, 4 * A2_ARR, nullptr, dbg, wrow, lane, rr);
+                        act, tl, s_bias + B_L2, nullptr, n, A2_ARR, 4 * A2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 2) {
                     epi_pool<MODE>(act, tl, s_bias + B_L3, n, g, wq, lane, dbg, rr);
                 } else if (ph < 9) {
                     const float* b = s_bias + B_S2 + (ph - 3) * 32;
                     if ((ph - 3) % 2 == 0)
                         epi_conv<MODE, true, 32, T2, P2, LV3, false, false, false, false, OUT_NAT, 1>(
-                            act, tl, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr);
+                            act, tl, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else if (ph < 8)
                         epi_conv<MODE, true, 32, T2, P2, LV3, true, false, true, false, OUT_NAT, 1>(
-                            act, tl, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr);
+                            act, tl, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else
                         epi_conv<MODE, true, 32, T2, P2, LV3, true, false, false, false, OUT_EO, 1>(
-                            act, tl, b, nullptr, n, E3_ARR, 8 * E3_ARR, nullptr, dbg, wrow, lane, rr);
+                            act, tl, b, nullptr, n, E3_ARR, 8 * E3_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 9) {
                     epi_conv<MODE, false, 64, T3, P3, LV4, false, false, false, true, OUT_NAT, 1>(
-                        act, tl, s_bias + B_RCA, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr);
+                        act, tl, s_bias + B_RCA, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 10) {
                     epi_conv<MODE, true, 64, T3, P3, LV4, true, true, true, false, OUT_NAT, 1>(
-                        act, tl, s_bias + B_RCB, s_bias + B_RCS, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr);
+                        act, tl, s_bias + B_RCB, s_bias + B_RCS, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else {
                     const float* b = s_bias + B_S3 + (ph - 11) * 64;
                     if ((ph - 11) % 2 == 0)
                         epi_conv<MODE, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1>(
-                            act, tl, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr);
+                            act, tl, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else if (ph < 16)
                         epi_conv<MODE, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1>(
-                            act, tl, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr);
+                            act, tl, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else {
                         epi_conv<MODE, true, 64, T3, P3, LV4, true, false, false, false, OUT_GLOBAL, 1>(
-                            act, tl, b, nullptr, n, 0, 0, gout, dbg, wrow, lane, rr);
+                            act, tl, b, nullptr, n, 0, 0, gout, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                         copy_out(act, gout, n, g, tid);
                     }
                 }
-                if (tr && tid == 0) tr[ph * 4 + 3] = clock64();
+                if (tr && tid == 0) tr[ph * 8 + 3] = clock64();
                 if (ph + 1 < N_PHASES) {
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
                     ptx::mbar_arrive(bar(BAR_ACT + g));
                 }
+                if (tr && tid == 0) tr[ph * 8 + 7] = clock64();
             }
         }
     } else if (warp < W_EPI + NG) {
@@ -572,7 +586,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                 ++tok_n;
                 if (n > 0) {
                     ptx::tc_fence_after();
-                    if (tr && lane == 0) tr[ph * 4 + 0] = clock64();
+                    if (tr && lane == 0) tr[ph * 8 + 0] = clock64();
                     const uint32_t w_lo = w0_lo + slot * (WSLOT_BYTES >> 4);
                     issue_phase<MODE, 0>(ph, act_lo, w_lo, d0);
                     __syncwarp();
@@ -581,7 +595,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                     issue_phase<MODE, 1>(ph, act_lo, w_lo, d0);
                     ptx::tc_commit(bar(BAR_ACC + g));                    // accumulators ready -> epilogue
                     ptx::tc_commit(bar(2 + slot));                       // weight slot no longer read by this group
-                    if (tr && lane == 0) tr[ph * 4 + 1] = clock64();
+                    if (tr && lane == 0) tr[ph * 8 + 1] = clock64();
                 } else if (lane == 0) {
                     ptx::mbar_arrive(bar(2 + slot));
                     ptx::mbar_arrive(bar(BAR_TOK + (g + 1) % NG));

@@ -27,7 +27,7 @@ if __name__ == "__main__":
     g = torch.Generator().manual_seed(1)
     reads = torch.randint(0, 256, (n, 150, 6), generator=g, dtype=torch.uint8).cuda()
     out = torch.empty((n, 36, 64), dtype=torch.float32, device="cuda")
-    tr = torch.zeros((ITEMS, NG, NPH, 4), dtype=torch.int64, device="cuda")
+    tr = torch.zeros((ITEMS, NG, NPH, 8), dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
         rc = eng.lib.hello_moe_readconv_debug(eng.handle, 0, reads.data_ptr(), n, 1, -2, out.data_ptr(), tr.data_ptr(),
@@ -47,7 +47,10 @@ if __name__ == "__main__":
         total = (sel[:, :, ph, 2] - sel[:, :, ph, 0]).float().mean().item()
         epi = (sel[:, :, ph, 3] - sel[:, :, ph, 2]).float().mean().item()
         nxt = (sel[:, :, ph + 1, 0] - sel[:, :, ph, 3]).float().mean().item() if ph + 1 < NPH else float("nan")
-        print("%5d | %7.0f %7.0f (issue->acc %7.0f) %9.0f %9.0f" % (ph, issue, wait, total, epi, nxt))
+        f = lambda a, b: (sel[:, :, ph, a] - sel[:, :, ph, b]).float().mean().item()
+        inner = "" if ph == 2 else "  [epilogue: first ld %5.0f | block0 %5.0f | blocks1-3 %5.0f | tail %5.0f | fence+arrive %4.0f]" % (
+            f(4, 2), f(5, 4), f(6, 5), f(3, 6), f(7, 3))
+        print("%5d | %7.0f %7.0f (issue->acc %7.0f) %9.0f %9.0f%s" % (ph, issue, wait, total, epi, nxt, inner))
     # one item in full: when is each group in which state
     i = 3
     print("item %d timeline (cycles since first issue of the item), group: [issue_start, acc_seen, epi_end] per phase" % i)
