@@ -314,7 +314,7 @@ def run_ours(args):
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * S * args.steps / dt, "unit": "sites/s", "h2d_bytes_per_step": hb.input_nbytes(),
                "d2h_bytes_per_step": out.nbytes(), "api": "MoEEngine.forward_host (pinned host buffers, "
-               "%d-site chunks, copy/compute overlap on 2 streams)" % args.e2e_chunk_sites}
+               "read rows streamed in %d-site ranges on a copy stream while the previous range computes)" % args.e2e_chunk_sites}
 
     if rank != 0:
         if world > 1:

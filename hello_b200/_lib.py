@@ -9,7 +9,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhello_moe.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 LAYOUT_RCL, LAYOUT_RLC = 0, 1
 META_NONE, META_SITE, META_REF = 0, 1, 2
@@ -18,7 +18,8 @@ PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 EXPORTS = (
     "hello_moe_abi_version", "hello_moe_create", "hello_moe_destroy", "hello_moe_last_error",
-    "hello_moe_workspace_bytes", "hello_moe_forward", "hello_moe_launch_count", "hello_moe_run_net",
+    "hello_moe_workspace_bytes", "hello_moe_forward", "hello_moe_forward_range", "hello_moe_launch_count",
+    "hello_moe_run_net",
     "hello_moe_profile_enable", "hello_moe_profile_collect", "hello_moe_readconv_debug",
     "hello_moe_headconv_debug",
     # include/hello_encode.h
@@ -82,6 +83,9 @@ def load():
     lib.hello_moe_forward.restype = C.c_int
     lib.hello_moe_forward.argtypes = [C.c_void_p, C.POINTER(HelloBatch), C.POINTER(HelloResult), C.c_void_p,
                                       C.c_size_t, C.c_void_p]
+    lib.hello_moe_forward_range.restype = C.c_int
+    lib.hello_moe_forward_range.argtypes = [C.c_void_p, C.POINTER(HelloBatch), C.POINTER(HelloResult), C.c_int64, C.c_int64,
+                                            C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.hello_moe_launch_count.restype = C.c_int64
     lib.hello_moe_launch_count.argtypes = [C.c_void_p]
     lib.hello_moe_run_net.restype = C.c_int

@@ -650,15 +650,17 @@ int hello_moe_profile_collect(hello_moe* h, double* ms_read_conv, int64_t* n_reg
 
 int64_t hello_moe_launch_count(const hello_moe* h) { return h ? h->launches : 0; }
 
-int hello_moe_forward(hello_moe* h, const hello_batch* in, const hello_result* out, void* d_workspace,
-                      size_t workspace_bytes, void* stream) {
+// Sites [sb, se) of the batch; n_pairs < 0 = count the genotype pairs of the whole batch here.
+static int forward_impl(hello_moe* h, const hello_batch* in, const hello_result* out, long long sb, long long se,
+                        long long n_pairs, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!h) return HELLO_ERR_ARG;
     h->err.clear();
     if (!in || !out || !d_workspace) { h->err = "null argument"; return HELLO_ERR_ARG; }
     const hello_cfg& cfg = h->cfg;
     const long long S = in->n_sites, A = in->n_alleles;
     if (S < 0 || A < S) { h->err = "need n_alleles >= n_sites >= 0"; return HELLO_ERR_ARG; }
-    if (S == 0) return HELLO_OK;
+    if (sb < 0 || se > S || sb > se) { h->err = "site range outside the batch"; return HELLO_ERR_ARG; }
+    if (S == 0 || sb == se) return HELLO_OK;
     if (!in->h_site_allele_off || !in->d_site_allele_off || !in->d_pair_off || !out->d_logits || !out->d_meta ||
         !out->d_pair_prob || !out->d_best_pair || !out->d_best_prob) {
         h->err = "missing required buffer"; return HELLO_ERR_ARG;
@@ -682,18 +684,23 @@ int hello_moe_forward(hello_moe* h, const hello_batch* in, const hello_result* o
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }
     // absent experts read as zero logits (torch.zeros_like, :244)
-    e = cudaMemsetAsync(out->d_logits, 0, size_t(3) * A * sizeof(float), st);
+    {
+        const long long ab = in->h_site_allele_off[sb], ae = in->h_site_allele_off[se];
+        for (int ex = 0; ex < 3 && e == cudaSuccess; ++ex)
+            e = cudaMemsetAsync(out->d_logits + (size_t)ex * A + ab, 0, size_t(ae - ab) * sizeof(float), st);
+    }
     if (e != cudaSuccess) { h->err = std::string("cudaMemsetAsync: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }
 
     Arena ar;
     ar.base = static_cast<char*>(d_workspace);
     ar.cap = workspace_bytes;
     Runner run{h, &ar, st, false};
-    for (long long s = 0; s < S; ++s) {
+    for (long long s = (n_pairs < 0 ? 0 : sb); s < (n_pairs < 0 ? S : se); ++s) {
         const long long n = in->h_site_allele_off[s + 1] - in->h_site_allele_off[s];
         if (n < 1) { h->err = "every site needs at least one allele"; return HELLO_ERR_ARG; }
         run.pair_total += n * (n + 1) / 2;
     }
+    if (n_pairs >= 0) run.pair_total = n_pairs;
     auto chunk_of = [&](long long s0, long long s1) {
         Chunk ck{};
         ck.s0 = s0; ck.s1 = s1;
@@ -707,9 +714,9 @@ int hello_moe_forward(hello_moe* h, const hello_batch* in, const hello_result* o
     auto fits = [&](const Chunk& ck) {
         return dry_bytes(h, ck.nr(0), ck.nr(1), ck.na(), ck.ns()) <= workspace_bytes;
     };
-    long long s0 = 0;
-    while (s0 < S) {
-        long long cap = S - s0;
+    long long s0 = sb;
+    while (s0 < se) {
+        long long cap = se - s0;
         if (cfg.max_chunk_sites > 0) cap = std::min<long long>(cap, cfg.max_chunk_sites);
         // largest chunk of whole sites that fits: gallop then bisect on the dry-run byte count
         long long lo = 1, hi = 1;
@@ -726,6 +733,17 @@ int hello_moe_forward(hello_moe* h, const hello_batch* in, const hello_result* o
         s0 += lo;
     }
     return HELLO_OK;
+}
+
+int hello_moe_forward(hello_moe* h, const hello_batch* in, const hello_result* out, void* d_workspace,
+                      size_t workspace_bytes, void* stream) {
+    return forward_impl(h, in, out, 0, in ? in->n_sites : 0, -1, d_workspace, workspace_bytes, stream);
+}
+
+int hello_moe_forward_range(hello_moe* h, const hello_batch* in, const hello_result* out, int64_t site_begin,
+                            int64_t site_end, int64_t n_pairs, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (n_pairs < 0) { if (h) h->err = "n_pairs must be the batch's total pair count"; return HELLO_ERR_ARG; }
+    return forward_impl(h, in, out, site_begin, site_end, n_pairs, d_workspace, workspace_bytes, stream);
 }
 
 int hello_moe_run_net(hello_moe* h, int net_id, const void* d_in, int64_t n_items, int32_t lin,

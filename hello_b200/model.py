@@ -208,19 +208,15 @@ class MoEEngine:
             call_qual=torch.empty((S, 5), dtype=torch.float64, device=dev),
             best_expert=torch.empty((S,), dtype=torch.int32, device=dev))
 
-    def run(self, b: DeviceBatch, out: Optional[BatchResult] = None,
-            workspace: Optional[torch.Tensor] = None) -> BatchResult:
-        """Enqueue the forward of a device-resident batch on the current stream (asynchronous)."""
+    def _abi_structs(self, b: DeviceBatch, out: BatchResult):
         n_tech = len(self.cfg.read_cin)
         if len(b.reads) < n_tech:
             raise ValueError("model needs %d technologies, batch has %d" % (n_tech, len(b.reads)))
         if self.cfg.meta == "meta_convolver_ref" and b.ref_onehot is None:
             raise ValueError("this model gates on the reference segment; reference_segments is required")
-        out = out or self.alloc_result(b)
         hb = _lib.HelloBatch()
         hb.n_sites, hb.n_alleles = b.n_sites, b.n_alleles
         hb.input_layout = b.layout
-        nr = [0, 0]
         for t in range(n_tech):
             r = b.reads[t]
             ch = self.cfg.read_cin[t]
@@ -230,7 +226,6 @@ class MoEEngine:
             if tuple(r.shape[1:]) != want:
                 raise ValueError("technology %d reads have shape %s, expected [R, %d, %d]" % (
                     t, tuple(r.shape), want[0], want[1]))
-            nr[t] = r.shape[0]
             hb.n_reads[t] = r.shape[0]
             hb.d_reads[t] = r.data_ptr()
             hb.d_allele_read_off[t] = b.allele_read_off_d[t].data_ptr()
@@ -248,6 +243,15 @@ class MoEEngine:
         hr.d_best_pair, hr.d_best_prob = out.best_pair.data_ptr(), out.best_prob.data_ptr()
         hr.d_call_pair, hr.d_call_qual = out.call_pair.data_ptr(), out.call_qual.data_ptr()
         hr.d_best_expert = out.best_expert.data_ptr()
+        return hb, hr
+
+    def run(self, b: DeviceBatch, out: Optional[BatchResult] = None,
+            workspace: Optional[torch.Tensor] = None) -> BatchResult:
+        """Enqueue the forward of a device-resident batch on the current stream (asynchronous)."""
+        out = out or self.alloc_result(b)
+        hb, hr = self._abi_structs(b, out)
+        n_tech = len(self.cfg.read_cin)
+        nr = [int(b.reads[t].shape[0]) if t < n_tech else 0 for t in range(2)]
         ws = workspace if workspace is not None else \
             self._workspace(self.workspace_bytes(nr[0], nr[1], b.n_alleles, b.n_sites))
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -257,47 +261,54 @@ class MoEEngine:
         self._check(rc, "hello_moe_forward")
         return out
 
+    def run_range(self, b: DeviceBatch, out: BatchResult, s0: int, s1: int, workspace: torch.Tensor) -> None:
+        """Enqueue the forward of sites [s0, s1) of a device batch (hello_moe_forward_range): all buffers describe the
+        whole batch, only these sites are computed."""
+        hb, hr = self._abi_structs(b, out)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            rc = self.lib.hello_moe_forward_range(self.handle, C.byref(hb), C.byref(hr), s0, s1, b.n_pairs,
+                                                  workspace.data_ptr(), workspace.numel(), C.c_void_p(stream))
+        self._check(rc, "hello_moe_forward_range")
+
     def forward_host(self, hb: "HostBatch", chunk_sites: int = 65536) -> "HostResult":
-        """End-to-end call on HOST buffers: stream chunks of sites host->device, run them, bring the per-site
-        results back.  Two streams alternate so the copies of one chunk overlap the kernels of the previous one."""
-        if not hasattr(self, "_streams"):
-            self._streams = [torch.cuda.Stream(self.device) for _ in range(2)]
-            self._ws2 = [None, None]
-        out = hb.result_buffers()
-        S = hb.n_sites
+        """End-to-end call on HOST buffers.  The device-side batch (read rows, CSR, results) is allocated once per
+        HostBatch; every call streams the read rows host -> device in ranges of `chunk_sites` sites on a copy stream
+        while the previous range computes (hello_moe_forward_range), then brings the per-site results back."""
+        st = hb.device_state(self)
         main = torch.cuda.current_stream(self.device)
-        for st in self._streams:
-            st.wait_stream(main)
-        for i, s0 in enumerate(range(0, S, chunk_sites)):
+        copy_s, comp_s = st["copy"], st["compute"]
+        copy_s.wait_stream(main)
+        comp_s.wait_stream(main)
+        db, res, out = st["batch"], st["result"], hb.result_buffers()
+        S = hb.n_sites
+        with torch.cuda.stream(copy_s):                       # the CSR arrays first (a few MB), then the rows
+            for dst, src in st["small"]:
+                dst.copy_(src, non_blocking=True)
+            small_done = torch.cuda.Event()
+            small_done.record(copy_s)
+        comp_s.wait_event(small_done)
+        sao = hb.site_allele_off
+        for s0 in range(0, S, chunk_sites):
             s1 = min(S, s0 + chunk_sites)
-            st = self._streams[i % 2]
-            with torch.cuda.stream(st):
-                db, (a0, a1), (p0, p1) = hb.device_chunk(s0, s1, self.device)
-                need = self.workspace_bytes(db.reads[0].shape[0], db.reads[1].shape[0] if len(db.reads) > 1 else 0,
-                                            db.n_alleles, db.n_sites)
-                want = min(max(need, 1 << 20), self.workspace_cap)
-                if self._ws2[i % 2] is None or self._ws2[i % 2].numel() < want:
-                    self._ws2[i % 2] = None
-                    self._ws2[i % 2] = torch.empty(want, dtype=torch.uint8, device=self.device)
-                res = self.run(db, workspace=self._ws2[i % 2])
-                # row by row: every copy is contiguous on both sides, so none of them stages through a temporary
-                # (a strided device->host copy synchronises the stream and would serialise H2D with the kernels)
-                for e in range(3):
-                    out.logits[e, a0:a1].copy_(res.logits[e], non_blocking=True)
-                out.meta[s0:s1].copy_(res.meta, non_blocking=True)
-                for e in range(4):
-                    out.pair_prob[e, p0:p1].copy_(res.pair_prob[e], non_blocking=True)
-                out.pair_mix64[p0:p1].copy_(res.pair_mix64, non_blocking=True)
-                out.best_pair[s0:s1].copy_(res.best_pair, non_blocking=True)
-                out.best_prob[s0:s1].copy_(res.best_prob, non_blocking=True)
-                out.call_pair[s0:s1].copy_(res.call_pair, non_blocking=True)
-                out.call_qual[s0:s1].copy_(res.call_qual, non_blocking=True)
-                out.best_expert[s0:s1].copy_(res.best_expert, non_blocking=True)
-                for t in res.tensors() + \
-                        db.reads + db.allele_read_off_d + (db.site_allele_off_d, db.pair_off_d):
-                    t.record_stream(st)
-        for st in self._streams:
-            main.wait_stream(st)
+            a0, a1 = int(sao[s0]), int(sao[s1])
+            ev = torch.cuda.Event()
+            with torch.cuda.stream(copy_s):
+                for t, r in enumerate(hb.reads):
+                    aro = hb.allele_read_off[t]
+                    r0, r1 = int(aro[a0]), int(aro[a1])
+                    db.reads[t][r0:r1].copy_(r[r0:r1], non_blocking=True)
+                if hb.ref_onehot is not None and db.ref_onehot is not None:
+                    db.ref_onehot[s0:s1].copy_(hb.ref_onehot[s0:s1], non_blocking=True)
+                ev.record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(ev)
+                self.run_range(db, res, s0, s1, st["workspace"])
+        with torch.cuda.stream(comp_s):
+            for dst, src in zip(out.tensors(), res.tensors()):
+                dst.copy_(src, non_blocking=True)
+        main.wait_stream(comp_s)
+        main.wait_stream(copy_s)
         return out
 
     def run_net(self, net: str, x: torch.Tensor, layout: int = _lib.LAYOUT_RLC) -> torch.Tensor:
@@ -373,10 +384,12 @@ class HostResult:
     call_qual: torch.Tensor
     best_expert: torch.Tensor
 
+    def tensors(self):
+        return (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob,
+                self.call_pair, self.call_qual, self.best_expert)
+
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in
-                   (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob,
-                    self.call_pair, self.call_qual, self.best_expert))
+        return sum(t.numel() * t.element_size() for t in self.tensors())
 
 
 class HostBatch:
@@ -413,6 +426,31 @@ class HostBatch:
                                    mk((P,), torch.float64), mk((S, 2), torch.int32), mk((S,), torch.float32),
                                    mk((S, 5, 2), torch.int32), mk((S, 5), torch.float64), mk((S,), torch.int32))
         return self._out
+
+    def device_state(self, engine: "MoEEngine"):
+        """Device-side twin of this batch for engine.forward_host, allocated on first use: read-row buffers (filled
+        range by range on every call), CSR arrays, result buffers, workspace, two streams."""
+        st = getattr(self, "_dev", None)
+        if st is not None and st["engine"] is engine:
+            return st
+        dev = engine.device
+        pin = (lambda t: t if t.is_pinned() else t.pin_memory()) if self.pin else (lambda t: t)
+        aro_h = tuple(pin(o) for o in self.allele_read_off)
+        sao_h, po_h = pin(self.site_allele_off), pin(self.pair_off)
+        aro_d = tuple(torch.empty_like(o, device=dev) for o in aro_h)
+        sao_d, po_d = torch.empty_like(sao_h, device=dev), torch.empty_like(po_h, device=dev)
+        need_ref = engine.cfg.meta == "meta_convolver_ref" and self.ref_onehot is not None
+        batch = DeviceBatch(reads=tuple(torch.empty(r.shape, dtype=torch.uint8, device=dev) for r in self.reads),
+                            layout=self.layout, allele_read_off_h=self.allele_read_off, allele_read_off_d=aro_d,
+                            site_allele_off_h=self.site_allele_off, site_allele_off_d=sao_d, pair_off_h=self.pair_off,
+                            pair_off_d=po_d,
+                            ref_onehot=torch.empty(self.ref_onehot.shape, dtype=torch.float32, device=dev) if need_ref else None)
+        small = [(d, h) for d, h in zip(aro_d, aro_h)] + [(sao_d, sao_h), (po_d, po_h)]
+        ws = torch.empty(engine.workspace_cap, dtype=torch.uint8, device=dev)
+        st = {"engine": engine, "batch": batch, "result": engine.alloc_result(batch), "small": small, "workspace": ws,
+              "copy": torch.cuda.Stream(dev), "compute": torch.cuda.Stream(dev)}
+        self._dev = st
+        return st
 
     def device_chunk(self, s0: int, s1: int, device):
         """Upload sites [s0, s1) (asynchronously on the current stream) with chunk-local CSR offsets."""

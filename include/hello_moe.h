@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HELLO_MOE_ABI_VERSION 2
+#define HELLO_MOE_ABI_VERSION 3
 
 typedef enum hello_status {
     HELLO_OK = 0,
@@ -133,6 +133,13 @@ size_t hello_moe_workspace_bytes(const hello_moe* h, int64_t n_reads0, int64_t n
  * (:527-589) and caller_calling.py:702-705. */
 int hello_moe_forward(hello_moe* h, const hello_batch* in, const hello_result* out, void* d_workspace,
                       size_t workspace_bytes, void* stream);
+
+/* The same forward for sites [site_begin, site_end) of a batch whose buffers describe ALL n_sites sites: every offset
+ * array, read tensor and result buffer is the whole batch's, only the given sites are computed and only their result
+ * slots written.  n_pairs = d_pair_off[n_sites] (row stride of d_pair_prob).  This is what a streaming caller uses:
+ * upload the read rows of the next site range on a copy stream while this range computes (MoEEngine.forward_host). */
+int hello_moe_forward_range(hello_moe* h, const hello_batch* in, const hello_result* out, int64_t site_begin,
+                            int64_t site_end, int64_t n_pairs, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Stage timing (a measurement aid for bench.py): while enabled, forward() brackets the read-convolver stage of
  * every chunk (the dominant kernel) with CUDA events on the launching stream. collect() waits for those events and

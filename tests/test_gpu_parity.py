@@ -347,6 +347,23 @@ def test_chunking_does_not_change_results(gpu):
     assert torch.equal(res_a, res_c)
 
 
+@pytest.mark.parametrize("name", ["single_tech", "hybrid_ensemble2"])
+def test_forward_host_streams_ranges(gpu, name):
+    """forward_host (pinned host buffers, read rows streamed range by range through hello_moe_forward_range) gives
+    exactly the results of one resident forward, for any range size, and can be called repeatedly."""
+    cfg = arch.CONFIGS[name]
+    pl = synth.make_pileups(50, coverage=9, channels=cfg.read_cin, seed=61)
+    net = net_for(gpu, cfg, "bf16x3")
+    ref = net.engine.run(gpu.DeviceBatch.from_pileups(pl, DEV))
+    from hello_b200 import _lib
+    hb = gpu.HostBatch(pl.reads, _lib.LAYOUT_RLC, pl.allele_read_off, pl.site_allele_off, pl.ref_onehot)
+    for chunk in (7, 16, 50, 1000):
+        out = net.engine.forward_host(hb, chunk)
+        torch.cuda.synchronize()
+        for got, want in zip(out.tensors(), ref.tensors()):
+            assert torch.equal(got, want.cpu()), chunk
+
+
 def test_ragged_edges(gpu):
     """One read / one allele sites, a many-allele site, an all-zero technology row."""
     from oracle import hello_oracle as O
