@@ -391,6 +391,31 @@ def test_ragged_edges(gpu):
     np.testing.assert_allclose(net.last_result.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=TOL_PROB["fp32"])
 
 
+def test_empty_batch_and_many_allele_site(gpu):
+    """Zero sites is a valid (empty) call; a site with 40 alleles (820 genotype pairs, more than one warp pass) matches the
+    oracle and its call is the argmax."""
+    from oracle import hello_oracle as O
+    cfg = arch.CONFIGS["single_tech"]
+    net = net_for(gpu, cfg, "bf16x3")
+    empty = net.forward((torch.zeros((0, 6, 150), dtype=torch.uint8), None), [], ([], None), None)
+    assert empty.shape == (0, 1) and net.last_result.pair_prob.shape == (4, 0) and net.last_result.best_pair.shape == (0, 2)
+    g = torch.Generator().manual_seed(12)
+    n_alleles = [40, 1]
+    nrpa = [1 + int(x) for x in torch.randint(0, 3, (41,), generator=g)]
+    reads = torch.randint(0, 256, (sum(nrpa), 6, 150), generator=g, dtype=torch.uint8)
+    res = net.forward((reads, None), n_alleles, (nrpa, None), None)
+    ref = oracle_for(cfg).forward((reads, None), n_alleles, (nrpa, None), None)
+    assert (res - ref).abs().max().item() < TOL_LOGIT["bf16x3"] * max(1.0, ref.abs().max().item() / 10)
+    r = net.last_result
+    assert r.pair_prob.shape == (4, 820 + 1)
+    post = O.batched_posteriors(cfg, res.cpu(), n_alleles)          # posteriors from the kernel's own logits
+    mixed = torch.cat([p[0] for p in post])
+    assert (r.pair_prob[0].cpu() - mixed).abs().max().item() < 1e-5
+    top = int(r.pair_prob[0, :820].argmax())
+    i, j = (int(x) for x in r.best_pair[0])
+    assert top == i * 40 - i * (i - 1) // 2 + (j - i)
+
+
 def test_float_inputs_and_errors(gpu):
     cfg = arch.CONFIGS["single_tech"]
     pl = synth.make_pileups(3, coverage=6, channels=cfg.read_cin, seed=4)
