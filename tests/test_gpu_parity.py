@@ -272,6 +272,25 @@ def test_forward_matches_oracle_seeded(gpu, name, precision):
                                atol=TOL_PROB[precision])
 
 
+@pytest.mark.parametrize("name", ["single_tech", "hybrid_no_ensemble", "hybrid_full"])
+def test_fast_mode_is_close(gpu, name):
+    """bf16 (single product) is the fast mode, reported separately from the parity mode: logits within 0.15, pair
+    probabilities within 2e-2, and the genotype call equal wherever the reference's top-2 margin exceeds 5e-2."""
+    from oracle import hello_oracle as O
+    cfg = arch.CONFIGS[name]
+    pl = synth.make_pileups(60, coverage=20, channels=cfg.read_cin, seed=88)
+    net = net_for(gpu, cfg, "bf16")
+    res = net.forward(*pl.forward_args())
+    ref = oracle_for(cfg).forward(*pl.forward_args())
+    lg, _ = flat_result(cfg, res)
+    lr, _ = flat_result(cfg, ref)
+    assert (lg - lr).abs().max().item() < 0.15
+    post = O.batched_posteriors(cfg, ref, pl.num_alleles_per_site())
+    mixed = torch.cat([p[0] for p in post]).numpy()
+    np.testing.assert_allclose(net.last_result.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=2e-2)
+    check_calls(net.last_result, mixed, np.array([p[3] for p in post], np.int32), 2.5e-2)
+
+
 def test_strict_drop_in_wrapper_call(gpu):
     """network(featureDict, segment) with providePredictions, as python/caller_calling.py:651-652 calls it."""
     from oracle import hello_oracle as O
