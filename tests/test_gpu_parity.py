@@ -525,3 +525,34 @@ def test_properties_at_scale(gpu):
     assert float(mass.max()) <= 1.0 + 1e-4 and float(pp.min()) >= 0.0
     best = torch.zeros(60_000).index_reduce_(0, site_of_pair, pp, "amax", include_self=False)
     assert torch.equal(best, a.best_prob.cpu())
+
+
+@pytest.mark.parametrize("name", ["hybrid_no_ensemble", "hybrid_full"])
+def test_hybrid_site_independence_across_chunks(gpu, name):
+    """Two technologies, combiners and (hybrid_full) three experts + meta gate: 3000 sites through a small workspace
+    (many chunks) against the same sites re-run 40 at a time -- bit-identical logits, meta weights, pair probabilities
+    and calls, i.e. no kernel's result depends on which items share its tiles."""
+    cfg = arch.CONFIGS[name]
+    pl = synth.make_pileups(3000, coverage=(8, 30), channels=cfg.read_cin, seed=777, device=DEV)
+    net = net_for(gpu, cfg, "bf16x3", workspace_bytes=256 << 20)
+    full = net.engine.run(gpu.DeviceBatch.from_pileups(pl, DEV))
+    full = [t.clone() for t in (full.logits, full.meta, full.pair_prob, full.best_pair, full.call_pair)]
+    off = net.last_result.pair_off if net.last_result is not None else None
+    sub_net = net_for(gpu, cfg, "bf16x3")
+    sao = pl.site_allele_off
+    from hello_b200 import _lib
+    for s0 in (0, 1234, 2960):
+        s1 = s0 + 40
+        a0, a1 = int(sao[s0]), int(sao[s1])
+        reads, offs = [], []
+        for t in range(2):
+            aro = pl.allele_read_off[t]
+            r0, r1 = int(aro[a0]), int(aro[a1])
+            reads.append(pl.reads[t][r0:r1])
+            offs.append(aro[a0:a1 + 1] - r0)
+        b = gpu.DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, offs, sao[s0:s1 + 1] - a0, pl.ref_onehot[s0:s1], DEV)
+        r = sub_net.engine.run(b)
+        p0 = int(synth.pair_offsets(sao)[s0]); p1 = int(synth.pair_offsets(sao)[s1])
+        assert torch.equal(r.logits, full[0][:, a0:a1]) and torch.equal(r.meta, full[1][s0:s1])
+        assert torch.equal(r.pair_prob, full[2][:, p0:p1]) and torch.equal(r.best_pair, full[3][s0:s1])
+        assert torch.equal(r.call_pair, full[4][s0:s1])
