@@ -484,13 +484,15 @@ struct HeadConvTC {
 
 // Checks that `net` is "1x1 conv C->C, Res(C->2C, stride 2, 1x1 shortcut), 2 x Res(2C) [, pooled linear]" with
 // C = 64 (L = 36) or C = 128 (L = 18) and packs its weights into ring units.
-static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, const float* d_base, const float* h_base,
-                                      int precision, std::string& err) {
+static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_len, const float* d_base,
+                                      const float* h_base, int precision, std::string& err) {
     using namespace hc;
     if (precision != HELLO_PREC_BF16X3 && precision != HELLO_PREC_BF16) { err = "unknown tensor-core precision"; return nullptr; }
     if (net.size() < 4 || net[0].kind != KIND_CONV) { err = "not a head network"; return nullptr; }
     const int C = net[0].a.cin;
-    if (C != 64 && C != 128) { err = "head network needs 64 or 128 input channels"; return nullptr; }
+    if (!((C == 64 && in_len == 36) || (C == 128 && in_len == 18))) {
+        err = "head network needs [36, 64] or [18, 128] inputs"; return nullptr;
+    }
     auto is_res = [&](const LayerDesc& L, int cin, int cout, int s, bool sc) {
         return L.kind == KIND_RES && L.a.cin == cin && L.a.cout == cout && L.a.k == 3 && L.a.stride == s && L.a.pad == 1 &&
                L.a.relu && L.b.relu && L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&

@@ -18,6 +18,7 @@
 #include "readconv_tc.cuh"
 #include "headconv_tc.cuh"
 #include "combconv_tc.cuh"
+#include "convlayer_tc.cuh"
 #include "encode_reads.cuh"
 
 using namespace hello;
@@ -62,6 +63,7 @@ struct hello_moe {
     ReadConvTC* tc[2] = {nullptr, nullptr};
     HeadConvTC* head[N_NETS] = {};   // fused tcgen05 compressor / xattn / meta_convolver (tensor-core precisions)
     CombConvTC* comb[2] = {nullptr, nullptr};   // fused tcgen05 combiner0 / combiner1
+    ConvLayerTC* layer_tc = nullptr;            // generic tcgen05 layers for what the fused kernels do not cover
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;            // pairs (start, stop), created lazily
     size_t ev_used = 0;
@@ -126,6 +128,8 @@ struct Runner {
     bool conv(const ActView& x, const ConvDesc& c, long long n, float* y, const float* resid) {
         if (dry || n == 0) return true;
         h->launches++;
+        cudaError_t e;
+        if (convlayer_tc_launch(h->layer_tc, x, c, n, y, resid, st, &e)) return check(e, "convlayer_tc");
         return check(launch_conv(x, c, n, y, resid, st), "conv1d_fp32");
     }
 
@@ -564,42 +568,47 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
         return HELLO_ERR_UNSUPPORTED;
     }
     if (cfg->precision != HELLO_PREC_FP32) {
-        for (int t = 0; t < cfg->n_tech; ++t) {
-            std::string terr;
-            h->tc[t] = readconv_tc_create(h->nets[NET_RC0 + t], h->d_weights, h->h_weights.data(),
-                                          cfg->read_channels[t], cfg->feature_length, cfg->precision, terr);
-            if (!h->tc[t]) {
-                g_create_error = "hello_moe_create: tensor-core read convolver: " + terr;
-                hello_moe_destroy(h);
-                return HELLO_ERR_UNSUPPORTED;
-            }
-        }
-    }
-    if (cfg->precision != HELLO_PREC_FP32) {
-        // compressor / xattn / meta_convolver as fused tcgen05 kernels
+        // Fused tcgen05 kernels where the sub-network has the architecture they are specialised for; every other
+        // convolution (meta_convolver_ref, the 2x-wide models) goes through the generic tensor-core layer kernel.
+        std::string terr;
+        for (int t = 0; t < cfg->n_tech; ++t)
+            h->tc[t] = readconv_tc_create(h->nets[NET_RC0 + t], h->d_weights, h->h_weights.data(), cfg->read_channels[t],
+                                          cfg->feature_length, cfg->precision, terr);
         std::vector<int> want;
         for (int t = 0; t < cfg->n_tech; ++t) want.push_back(NET_CMP0 + t);
         for (int e3 = 0; e3 < 3; ++e3) if (cfg->xattn_present[e3]) want.push_back(NET_X0 + e3);
         if (cfg->meta_kind == HELLO_META_SITE) want.push_back(NET_META);
         for (int id : want) {
-            std::string terr;
-            h->head[id] = headconv_tc_create(h->nets[id], h->d_weights, h->h_weights.data(), cfg->precision, terr);
-            if (!h->head[id]) {
-                g_create_error = "hello_moe_create: tensor-core head network: " + terr;
-                hello_moe_destroy(h);
-                return HELLO_ERR_UNSUPPORTED;
+            const int in_len = (id == NET_CMP0 || id == NET_CMP1) ? h->read_len : h->comp_len;
+            h->head[id] = headconv_tc_create(h->nets[id], in_len, h->d_weights, h->h_weights.data(), cfg->precision, terr);
+        }
+        if (cfg->has_combiners && cfg->xattn_present[2] && h->comp_len == cc::L) {
+            for (int k = 0; k < 2; ++k)
+                h->comb[k] = combconv_tc_create(h->nets[NET_CB0 + k], h->d_weights, h->h_weights.data(), cfg->precision, terr);
+            if (!h->comb[0] || !h->comb[1]) {
+                for (int k = 0; k < 2; ++k) { combconv_tc_destroy(h->comb[k]); h->comb[k] = nullptr; }
             }
         }
-    }
-    if (cfg->precision != HELLO_PREC_FP32 && cfg->has_combiners && cfg->xattn_present[2]) {
-        for (int k = 0; k < 2; ++k) {
-            std::string terr;
-            h->comb[k] = combconv_tc_create(h->nets[NET_CB0 + k], h->d_weights, h->h_weights.data(), cfg->precision, terr);
-            if (!h->comb[k]) {
-                g_create_error = "hello_moe_create: tensor-core combiner: " + terr;
-                hello_moe_destroy(h);
-                return HELLO_ERR_UNSUPPORTED;
+        h->layer_tc = convlayer_tc_create(cfg->precision, terr);
+        bool ok_tc = h->layer_tc != nullptr;
+        for (int n = 0; n < N_NETS && ok_tc; ++n) {
+            const bool fused = (n <= NET_RC1 && h->tc[n - NET_RC0]) || h->head[n] ||
+                               ((n == NET_CB0 || n == NET_CB1) && h->comb[n - NET_CB0]);
+            if (fused) continue;
+            for (const LayerDesc& L : h->nets[n]) {
+                if (L.kind == KIND_CONV) ok_tc = convlayer_tc_add(h->layer_tc, L.a, h->d_weights, h->h_weights.data(), terr);
+                if (L.kind == KIND_RES) {
+                    ok_tc = convlayer_tc_add(h->layer_tc, L.a, h->d_weights, h->h_weights.data(), terr) &&
+                            convlayer_tc_add(h->layer_tc, L.b, h->d_weights, h->h_weights.data(), terr) &&
+                            (!L.has_shortcut || convlayer_tc_add(h->layer_tc, L.s, h->d_weights, h->h_weights.data(), terr));
+                }
+                if (!ok_tc) break;
             }
+        }
+        if (!ok_tc) {
+            g_create_error = "hello_moe_create: tensor-core layers: " + terr;
+            hello_moe_destroy(h);
+            return HELLO_ERR_CUDA;
         }
     }
     *out = h;
@@ -612,6 +621,7 @@ void hello_moe_destroy(hello_moe* h) {
     for (int t = 0; t < 2; ++t) readconv_tc_destroy(h->tc[t]);
     for (int n = 0; n < N_NETS; ++n) headconv_tc_destroy(h->head[n]);
     for (int k = 0; k < 2; ++k) combconv_tc_destroy(h->comb[k]);
+    convlayer_tc_destroy(h->layer_tc);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->d_weights) cudaFree(h->d_weights);
     delete h;
