@@ -99,6 +99,20 @@ def test_generic_tensor_core_layers(gpu, precision):
         assert (got - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item()), net_name
 
 
+def test_standard_models_run_on_the_fused_kernels(gpu):
+    """Kernel launches per chunk in the tensor-core mode: a silent fall-back to per-layer kernels would show here."""
+    expect = {"single_tech": 7,            # read convolver, segsum, compressor, segsum, xattn, site index + posterior
+              "hybrid_no_ensemble": 13}    # 2 x (read convolver, segsum, compressor, segsum) + 2 combiners + xattn2 + 2
+    for name, n_launch in expect.items():
+        cfg = arch.CONFIGS[name]
+        pl = synth.make_pileups(6, coverage=6, channels=cfg.read_cin, seed=2)
+        eng = net_for(gpu, cfg, "bf16x3").engine
+        batch = gpu.DeviceBatch.from_pileups(pl, DEV)
+        before = eng.launch_count()
+        eng.run(batch)
+        assert eng.launch_count() - before == n_launch + 1, name     # + fill_meta_default (no meta network)
+
+
 def test_combiner_and_meta_networks(gpu):
     cfg = arch.CONFIGS["hybrid_full"]
     g = torch.Generator().manual_seed(6)
