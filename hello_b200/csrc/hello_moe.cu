@@ -296,7 +296,8 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         const size_t m1 = ar.mark();
         float* a_feat = ar.allocf(na * read_e);
         const size_t m2 = ar.mark();
-        float* r_feat = ar.allocf(nr * read_e);
+        // the fused kernel sums the reads of every allele itself (no per-read maps in HBM); the per-layer path needs them
+        float* r_feat = h->tc[t] ? nullptr : ar.allocf(nr * read_e);
         if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
         // read convolver (architectures/read_convolver.py) on uint8 rows
         const uint8_t* reads = dry ? nullptr : in->d_reads[t] + (size_t)ck.r0[t] * L * C;
@@ -314,20 +315,23 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         }
         if (h->tc[t]) {
             if (!dry && nr > 0) {
-                cudaError_t e = readconv_tc_launch(h->tc[t], reads, nr, in->input_layout, r_feat, run.st);
+                // read convolver + reads -> alleles (reduceSlots, :163) in one kernel
+                cudaError_t e = readconv_tc_launch(h->tc[t], reads, nr, in->input_layout, nullptr, run.st, nullptr, -1, a_feat,
+                                                   in->d_allele_read_off[t] + ck.a0, na, (int)ck.r0[t]);
                 h->launches++;
                 if (!run.check(e, "readconv_tc")) return false;
             }
+            if (ev_stop && !run.check(cudaEventRecord(ev_stop, run.st), "cudaEventRecord")) return false;
         } else {
             ActView v;
             v.base = reads; v.len = L; v.ch = C; v.is_u8 = true; v.sn = (long long)L * C;
             if (!dry && in->input_layout == HELLO_LAYOUT_RCL) { v.sc = L; v.sl = 1; } else { v.sc = 1; v.sl = C; }
             if (!run.run_net(h->nets[NET_RC0 + t], v, nr, r_feat, nullptr)) return false;
+            if (ev_stop && !run.check(cudaEventRecord(ev_stop, run.st), "cudaEventRecord")) return false;
+            // reads -> alleles (reduceSlots, :163)
+            if (!run.segsum(r_feat, a_feat, dry ? nullptr : in->d_allele_read_off[t] + ck.a0, na, (int)ck.r0[t], read_e))
+                return false;
         }
-        if (ev_stop && !run.check(cudaEventRecord(ev_stop, run.st), "cudaEventRecord")) return false;
-        // reads -> alleles (reduceSlots, :163)
-        if (!run.segsum(r_feat, a_feat, dry ? nullptr : in->d_allele_read_off[t] + ck.a0, na, (int)ck.r0[t], read_e))
-            return false;
         ar.release(m2);
         // compressor (:125)
         if (h->head[NET_CMP0 + t]) {

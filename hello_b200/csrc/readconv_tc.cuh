@@ -80,8 +80,10 @@ constexpr uint32_t OFF_BIAS = OFF_W + 2 * WSLOT_BYTES;
 constexpr uint32_t OFF_BAR = OFF_BIAS + N_BIAS * 4;
 constexpr uint32_t N_BARS = 4 + 3 * NG;           // w_full[2], w_empty[2], act_ready[NG], acc_full[NG], token[NG]
 constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
-constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+constexpr uint32_t OFF_STATE = (OFF_TMEM + 16 + 15) & ~15u;   // work range of this CTA + running state of the fused allele sum
+constexpr uint32_t OFF_SUM = OFF_STATE + 64;           // fp32 [36][64] running sum of the current allele
+constexpr uint32_t SMEM_BYTES = OFF_SUM + LOUT * COUT * 4;
+static_assert(SMEM_BYTES <= 232448 && OFF_SUM % 16 == 0, "shared memory budget");
 static_assert(2 * A1_CH * 2 <= XCHG_OFF && 8 * A2_ARR <= XCHG_OFF && 8 * S2_CH <= XCHG_OFF &&
               16 * E3_ARR <= XCHG_OFF && 16 * S3_CH <= XCHG_OFF && 2 * X_STRIDE <= XCHG_OFF, "activation layouts");
 static_assert(T1 * 128 >= ROWS1 && T2 * 128 >= ROWS2 && T3 * 128 >= ROWS3, "tiles cover the packed rows");
@@ -101,7 +103,14 @@ struct TcParams {
     float* out;
     float* dbg;
     long long n_reads;
-    int n_items, channels, layout, dbg_phase;
+    int channels, layout, dbg_phase;
+    // Fused reads -> alleles sum (reduceSlots, python/MixtureOfExpertsAdvanced.py:23-34 / :163): when allele_out is set the
+    // kernel writes, instead of one [36,64] map per read, the sum over each allele's reads -- rows added in read order
+    // starting from zero, i.e. exactly what segsum_kernel computes from the per-read maps.
+    float* allele_out;            // [n_alleles, 36, 64] or nullptr
+    const int32_t* allele_off;    // [n_alleles + 1] read offsets of the alleles (global numbering, minus row_base = local)
+    long long n_alleles;
+    int row_base;
 };
 
 // Packed weights.  One B unit covers one tap and 16 input channels: [2 chunks of 8 channels][rows][8 bf16] with
@@ -281,6 +290,55 @@ __device__ __forceinline__ void copy_out(const uint8_t* act, float* __restrict__
     ptx::named_bar_sync(1 + g, EW * 32);              // the buffer is free for the next work item's input
 }
 
+// This CTA's share of the reads, state of the fused allele sum (shared memory, OFF_STATE).
+struct CtaState {
+    long long r_begin, r_end;     // reads [r_begin, r_end) (chunk-local numbering)
+    long long cur_end;            // first read after the allele being summed
+    int cur_allele;               // allele being summed (chunk-local index)
+    volatile int turn;            // next group (in read order) allowed to add its reads
+};
+
+// Fused reduceSlots: the groups of a CTA hold consecutive reads and a CTA owns whole alleles, so adding every group's
+// staged rows, in read order, into one running [36,64] sum and flushing it when the allele changes reproduces
+// segsum_kernel bit for bit (same additions in the same order) without the per-read maps ever reaching HBM.
+__device__ __forceinline__ void accumulate_out(uint8_t* smem, const uint8_t* act, const TcParams& prm, long long r0, int n_reads,
+                                               int seq, int g, int tid) {
+    CtaState* st = reinterpret_cast<CtaState*>(smem + OFF_STATE);
+    float4* sum = reinterpret_cast<float4*>(smem + OFF_SUM);
+    ptx::named_bar_sync(1 + g, EW * 32);                                   // the group's rows are staged
+    if (tid == 0) { while (st->turn != seq) __nanosleep(32); }
+    ptx::named_bar_sync(1 + g, EW * 32);                                   // our turn: earlier reads are in the sum
+    int cur = st->cur_allele;
+    long long cur_end = st->cur_end;
+    constexpr int SLOTS = LOUT * COUT / 4;                                 // float4 slots of one map
+    for (int i = 0; i < n_reads; ++i) {
+        if (r0 + i == cur_end) {                                           // allele complete: flush, start the next one
+            float4* dst = reinterpret_cast<float4*>(prm.allele_out + (long long)cur * (LOUT * COUT));
+            for (int f = tid; f < SLOTS; f += EW * 32) { dst[f] = sum[f]; sum[f] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            ++cur;
+            cur_end = (long long)__ldg(prm.allele_off + cur + 1) - prm.row_base;
+        }
+        for (int f = tid; f < SLOTS; f += EW * 32) {
+            const int p = f >> 4, q = f & 15, m = i * P3 + p;
+            const float4 v = *reinterpret_cast<const float4*>(act + (uint32_t)m * 256 + ((q ^ (m & 15)) * 16));
+            float4 a = sum[f];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            sum[f] = a;
+        }
+    }
+    if (r0 + n_reads == st->r_end) {                                       // last reads of this CTA: flush the last allele
+        float4* dst = reinterpret_cast<float4*>(prm.allele_out + (long long)cur * (LOUT * COUT));
+        for (int f = tid; f < SLOTS; f += EW * 32) dst[f] = sum[f];
+    }
+    ptx::named_bar_sync(1 + g, EW * 32);                                   // sums written; the staging buffer is free
+    if (tid == 0) {
+        st->cur_allele = cur;
+        st->cur_end = cur_end;
+        __threadfence_block();
+        st->turn = seq + 1;
+    }
+}
+
 // Epilogue of stem conv 3 fused with MaxPool1d(3,2): E[m] = conv(2p), O[m] = conv(2p+1) sit in two accumulators
 // (each the sum of its three operand products), conv(2p+2) = E[m+1] comes from the neighbouring lane (shared-memory
 // exchange across warp / tile borders).  Starts the residual stream: tile 0 -> registers, tile 1 -> TMEM.
@@ -437,7 +495,7 @@ __device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_
 constexpr int TRACE_PHASE = -2, TRACE_ITEMS = 16;
 __device__ __forceinline__ long long* trace_slot(const TcParams& prm, int item, int g) {
     if (!prm.dbg || prm.dbg_phase != TRACE_PHASE || blockIdx.x != 0) return nullptr;
-    const int li = item / (int)gridDim.x;
+    const int li = item;
     if (li >= TRACE_ITEMS) return nullptr;
     return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * NG + g) * N_PHASES) * 8;
 }
@@ -470,17 +528,52 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
     {   // every byte an MMA can read must hold a finite bf16 (zero weights multiply the padding channels)
         uint4* z = reinterpret_cast<uint4*>(smem);
         for (uint32_t i = threadIdx.x; i < OFF_BIAS / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        uint4* zs = reinterpret_cast<uint4*>(smem + OFF_SUM);
+        for (uint32_t i = threadIdx.x; i < LOUT * COUT / 4; i += blockDim.x) zs[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (warp == W_EPI + NG) {
         ptx::tmem_alloc(ptx::smem_u32(smem + OFF_TMEM), 512);
         ptx::tmem_relinquish();
+    }
+    if (threadIdx.x == 32) {
+        CtaState* st0 = reinterpret_cast<CtaState*>(smem + OFF_STATE);
+        const long long Rt = prm.n_reads;
+        auto bound = [&](long long c) -> long long {                       // first read of CTA c
+            if (c <= 0) return 0;
+            if (c >= (long long)gridDim.x) return Rt;
+            if (!prm.allele_out) return min(Rt, (Rt / (NG * G) * c / (long long)gridDim.x) * (NG * G));
+            const long long target = Rt * c / (long long)gridDim.x + prm.row_base;
+            long long lo = 0, hi = prm.n_alleles;                          // lower bound of `target` in allele_off[0..A]
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if ((long long)__ldg(prm.allele_off + mid) < target) lo = mid + 1; else hi = mid;
+            }
+            return (long long)__ldg(prm.allele_off + lo) - prm.row_base;
+        };
+        st0->r_begin = bound(blockIdx.x);
+        st0->r_end = bound((long long)blockIdx.x + 1);
+        st0->turn = 0;
+        if (prm.allele_out && st0->r_begin < st0->r_end) {
+            long long lo = 0, hi = prm.n_alleles;                          // allele that starts at r_begin
+            const long long target = st0->r_begin + prm.row_base;
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if ((long long)__ldg(prm.allele_off + mid) < target) lo = mid + 1; else hi = mid;
+            }
+            st0->cur_allele = (int)lo;
+            st0->cur_end = (long long)__ldg(prm.allele_off + lo + 1) - prm.row_base;
+        }
     }
     ptx::fence_proxy_async();
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
-    const long long R = prm.n_reads;
+    // Work partition: CTA c owns a contiguous range of reads.  In the fused-sum mode the range boundaries are snapped
+    // to allele boundaries (lower bound of c*R/grid in the allele CSR), so every allele is summed by one CTA.
+    CtaState* cst = reinterpret_cast<CtaState*>(smem + OFF_STATE);
+    const long long R = cst->r_end, R0 = cst->r_begin;
+    const int n_items_cta = (int)((R - R0 + NG * G - 1) / (NG * G));
 
     if (warp < W_EPI) {
         // ===================================================== epilogue warps (group g = warp / EW)
@@ -492,15 +585,15 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         float rr[32];                                  // first half of this row's fp32 residual stream
 #pragma unroll
         for (int c = 0; c < 32; ++c) rr[c] = 0.f;
-        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-            const long long r0 = ((long long)item * NG + g) * G;
+        for (int item = 0; item < n_items_cta; ++item) {
+            const long long r0 = R0 + ((long long)item * NG + g) * G;
             const int n = (int)max(0LL, min((long long)G, R - r0));
             if (n <= 0) continue;
             load_input(act, prm.reads, r0, n, prm.channels, prm.layout, tid);
             ptx::tc_fence_before();
             ptx::fence_proxy_async();
             ptx::mbar_arrive(bar(BAR_ACT + g));
-            float* gout = prm.out + r0 * (long long)(LOUT * COUT);
+            float* gout = prm.out ? prm.out + r0 * (long long)(LOUT * COUT) : nullptr;
             long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
@@ -508,7 +601,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                 ++acc_n;
                 ptx::tc_fence_after();
                 if (tr && tid == 0) tr[ph * 8 + 2] = clock64();
-                float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph) ? prm.dbg + ((long long)item * NG + g) * (T1 * 128 * 64) : nullptr;
+                float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph) ? prm.dbg + (r0 / G) * (T1 * 128 * 64) : nullptr;
                 if (ph == 0) {
                     epi_conv<MODE, true, 16, T1, P1, LV1, false, false, false, false, OUT_NAT, 0>(
                         act, tl, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
@@ -545,7 +638,8 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                     else {
                         epi_conv<MODE, true, 64, T3, P3, LV4, true, false, false, false, OUT_GLOBAL, 1>(
                             act, tl, b, nullptr, n, 0, 0, gout, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
-                        copy_out(act, gout, n, g, tid);
+                        if (prm.allele_out) accumulate_out(smem, act, prm, r0, n, item * NG + g, g, tid);
+                        else copy_out(act, gout, n, g, tid);
                     }
                 }
                 if (tr && tid == 0) tr[ph * 8 + 3] = clock64();
@@ -565,8 +659,8 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         const uint32_t act_lo = (ptx::smem_u32(smem + OFF_ACT) + g * ACT_BYTES) >> 4;
         const uint32_t w0_lo = ptx::smem_u32(smem + OFF_W) >> 4;
         const uint32_t d0 = tmem_base + g * GRP_COLS;
-        for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
-            const int n = (int)max(0LL, min((long long)G, R - ((long long)item * NG + g) * G));
+        for (int item = 0; item < n_items_cta; ++item) {
+            const int n = (int)max(0LL, min((long long)G, R - (R0 + ((long long)item * NG + g) * G)));
             long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
@@ -609,9 +703,9 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         if (lane == 0) {
             uint32_t w_n = 0;
             const uint32_t w0 = ptx::smem_u32(smem + OFF_W);
-            for (int item = blockIdx.x; item < prm.n_items; item += gridDim.x) {
+            for (int item = 0; item < n_items_cta; ++item) {
                 {   // pull the next work item's pileup rows into L2 while this one computes
-                    const long long nr0 = (long long)(item + gridDim.x) * (NG * G);
+                    const long long nr0 = R0 + (long long)(item + 1) * (NG * G);
                     if (nr0 < R) {
                         const long long bytes = min((long long)(NG * G), R - nr0) * (LIN * prm.channels);
                         const uint8_t* p = prm.reads + nr0 * (LIN * prm.channels);
@@ -805,8 +899,11 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
 
 // out: fp32 [n_reads, 36, 64] channel-last.  dbg (optional): fp32 [ceil(n_reads/3), 512, 64] dump of the epilogue
 // values of layer phase `dbg_phase` (test hook).
+// allele_out / allele_off / n_alleles / row_base (optional): write per-allele sums instead of per-read maps.
 static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long long n_reads, int layout, float* out,
-                                      cudaStream_t st, float* dbg = nullptr, int dbg_phase = -1) {
+                                      cudaStream_t st, float* dbg = nullptr, int dbg_phase = -1,
+                                      float* allele_out = nullptr, const int32_t* allele_off = nullptr,
+                                      long long n_alleles = 0, int row_base = 0) {
     if (n_reads <= 0) return cudaSuccess;
     tc::TcParams prm = t->prm;
     prm.reads = reads;
@@ -815,9 +912,12 @@ static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long 
     prm.out = out;
     prm.dbg = dbg;
     prm.dbg_phase = dbg_phase;
+    prm.allele_out = allele_out;
+    prm.allele_off = allele_off;
+    prm.n_alleles = n_alleles;
+    prm.row_base = row_base;
     const long long items = (n_reads + tc::NG * tc::G - 1) / (tc::NG * tc::G);
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
-    prm.n_items = (int)items;
     const int grid = (int)std::min<long long>(items, t->sm_count);
     const bool debug = dbg != nullptr;
     if (t->mode == 3) {

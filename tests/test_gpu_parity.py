@@ -101,8 +101,8 @@ def test_generic_tensor_core_layers(gpu, precision):
 
 def test_standard_models_run_on_the_fused_kernels(gpu):
     """Kernel launches per chunk in the tensor-core mode: a silent fall-back to per-layer kernels would show here."""
-    expect = {"single_tech": 7,            # read convolver, segsum, compressor, segsum, xattn, site index + posterior
-              "hybrid_no_ensemble": 13}    # 2 x (read convolver, segsum, compressor, segsum) + 2 combiners + xattn2 + 2
+    expect = {"single_tech": 6,            # read convolver (+ allele sum), compressor, segsum, xattn, site index + posterior
+              "hybrid_no_ensemble": 11}    # 2 x (read convolver, compressor, segsum) + 2 combiners + xattn2 + 2
     for name, n_launch in expect.items():
         cfg = arch.CONFIGS[name]
         pl = synth.make_pileups(6, coverage=6, channels=cfg.read_cin, seed=2)
