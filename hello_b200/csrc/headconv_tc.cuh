@@ -289,6 +289,16 @@ __device__ __forceinline__ uint32_t phase_bytes(int ph) {
     return ph == 0 ? k16 * per16 * C : ph == 1 ? 4 * k16 * per16 * 2 * C : 6 * k16 * per16 * 2 * C;
 }
 
+// Timeline hook (dbg_phase == -2, debug instantiation only): CTA 0 stamps clock64() for its first 16 work items as int64
+// [item][group][8 phases][4] = {issue start, issue end, accumulators seen, epilogue end}; phase slot 7 holds
+// {operand load start, operand load end, 0, 0}.
+__device__ __forceinline__ long long* head_trace_slot(const HeadParams& prm, int item, int g, int ngrp) {
+    if (!prm.dbg || prm.dbg_phase != -2 || blockIdx.x != 0) return nullptr;
+    const int li = item / (int)gridDim.x;
+    if (li >= 16) return nullptr;
+    return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * ngrp + g) * 8) * 4;
+}
+
 template <int MODE, int C, bool DBG>
 __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const __grid_constant__ HeadParams prm) {
     using Gm = Geo<C>;
@@ -336,7 +346,10 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
             const long long i0 = ((long long)item * NGRP + g) * G;
             const int n = (int)max(0LL, min((long long)G, n_items - i0));
             if (n <= 0) continue;
+            long long* tr = DBG ? head_trace_slot(prm, item, g, NGRP) : nullptr;
+            if (tr && tid == 0) tr[7 * 4 + 0] = clock64();
             load_input<MODE, C>(act, prm, i0, n, tid);
+            if (tr && tid == 0) tr[7 * 4 + 1] = clock64();
             ptx::tc_fence_before();
             ptx::fence_proxy_async();
             ptx::mbar_arrive(bar(BAR_ACT + g));
@@ -346,6 +359,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                 ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
                 ++acc_n;
                 ptx::tc_fence_after();
+                if (tr && tid == 0) tr[ph * 4 + 2] = clock64();
                 float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph)
                                  ? prm.dbg + ((long long)item * NGRP + g) * (DBG_ROWS * DBG_COLS) : nullptr;
                 if (ph == 0) {
@@ -367,6 +381,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                     epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, false, false, OUT_FINAL>(
                         act, tl, s_bias + Gm::B_REST + (ph - 3) * 2 * C, nullptr, n, 0, 0, prm, i0, dbg, wrow, lane, chalf, part);
                 }
+                if (tr && tid == 0) tr[ph * 4 + 3] = clock64();
                 if (ph + 1 < N_PHASES) {
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
@@ -414,6 +429,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
         for (int item = blockIdx.x; item < prm.n_work; item += gridDim.x) {
             const long long i0 = ((long long)item * NGRP + g) * G;
             const bool active = n_items > i0;
+            long long* tr = DBG ? head_trace_slot(prm, item, g, NGRP) : nullptr;
 #pragma unroll 1
             for (int ph = 0; ph < N_PHASES; ++ph) {
                 // (no turn-taking between the two compressor groups as in the read convolver: a layer's weights do not
@@ -423,6 +439,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                     ++ar_n;
                     ptx::tc_fence_after();
                 }
+                if (tr && lane == 0) tr[ph * 4 + 0] = clock64();
                 if (ph == 0)
                     issue_phase<MODE, C, 0>(active, act_lo, ring_lo, d_acc, bar(BAR_FULL), bar(BAR_EMPTY), slot, par, lane);
                 else if (ph == 1)
@@ -430,6 +447,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                 else
                     issue_phase<MODE, C, 2>(active, act_lo, ring_lo, d_acc, bar(BAR_FULL), bar(BAR_EMPTY), slot, par, lane);
                 if (active) ptx::tc_commit(bar(BAR_ACC + g));
+                if (tr && lane == 0) tr[ph * 4 + 1] = clock64();
                 __syncwarp();
             }
         }
