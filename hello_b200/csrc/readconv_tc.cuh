@@ -305,9 +305,8 @@ __device__ __forceinline__ void accumulate_out(uint8_t* smem, const uint8_t* act
                                                int seq, int g, int tid) {
     CtaState* st = reinterpret_cast<CtaState*>(smem + OFF_STATE);
     float4* sum = reinterpret_cast<float4*>(smem + OFF_SUM);
-    ptx::named_bar_sync(1 + g, EW * 32);                                   // the group's rows are staged
-    if (tid == 0) { while (st->turn != seq) __nanosleep(32); }
-    ptx::named_bar_sync(1 + g, EW * 32);                                   // our turn: earlier reads are in the sum
+    if (tid == 0) { while (st->turn != seq) __nanosleep(32); }             // our turn: earlier reads are in the sum
+    ptx::named_bar_sync(1 + g, EW * 32);                                   // ... and the group's rows are staged
     int cur = st->cur_allele;
     long long cur_end = st->cur_end;
     constexpr int SLOTS = LOUT * COUT / 4;                                 // float4 slots of one map
