@@ -99,7 +99,7 @@ struct TcParams {
     uint32_t w_bytes[N_PHASES];
     const uint8_t* reads;
     const uint8_t* weights;
-    const float* bias;
+    float bias_tab[N_BIAS];   // biases travel in the kernel parameters: constant-bank loads, no shared-memory bandwidth
     float* out;
     float* dbg;
     long long n_reads;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void load_input(uint8_t* act, const uint8_t* __restri
 //   the residual storage before the next layer reuses the accumulator columns.
 template <int MODE, bool STACK, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID,
           bool MOVE_SC, int OUT, int LEAD>
-__device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float* bias, const float* bias2, int n_reads,
+__device__ __forceinline__ void epi_conv(const TcParams& prm, uint8_t* act, uint32_t tl, int bias, int bias2, int n_reads,
                                          uint32_t out_stride, uint32_t out_lo, float* __restrict__ gout,
                                          float* __restrict__ dbg, int wrow, int lane, float (&rr)[32],
                                          long long* tr = nullptr) {
@@ -207,11 +207,11 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
         for (int c = 0; c < 16; c += 2) {               // packed fp32x2 adds: same roundings, half the issue slots
             float y0 = x[c], y1 = x[c + 1];
             if (TWO) ptx::add2(y0, y1, w[c], w[c + 1]);
-            ptx::add2(y0, y1, bias[c0 + c], bias[c0 + c + 1]);
+            ptx::add2(y0, y1, prm.bias_tab[bias + c0 + c], prm.bias_tab[bias + c0 + c + 1]);
             y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f);
             if (RESID) {
                 float r0 = REG ? rr[RO + c] : r[c], r1 = REG ? rr[RO + c + 1] : r[c + 1];
-                if (RES_BIAS) ptx::add2(r0, r1, bias2[c0 + c], bias2[c0 + c + 1]);
+                if (RES_BIAS) ptx::add2(r0, r1, prm.bias_tab[bias2 + c0 + c], prm.bias_tab[bias2 + c0 + c + 1]);
                 ptx::add2(y0, y1, r0, r1);
             }
             x[c] = valid ? y0 : 0.f;
@@ -342,7 +342,7 @@ __device__ __forceinline__ void accumulate_out(uint8_t* smem, const uint8_t* act
 // (each the sum of its three operand products), conv(2p+2) = E[m+1] comes from the neighbouring lane (shared-memory
 // exchange across warp / tile borders).  Starts the residual stream: tile 0 -> registers, tile 1 -> TMEM.
 template <int MODE>
-__device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float* bias, int n_reads, int g, int wq,
+__device__ __forceinline__ void epi_pool(const TcParams& prm, uint8_t* act, uint32_t tl, int bias, int n_reads, int g, int wq,
                                          int lane, float* __restrict__ dbg, float (&rr)[32]) {
     float* xchg = reinterpret_cast<float*>(act + XCHG_OFF);
     constexpr int N_SLICES = T2 * 4;
@@ -378,7 +378,7 @@ __device__ __forceinline__ void epi_pool(uint8_t* act, uint32_t tl, const float*
                 const float dn = __shfl_down_sync(0xffffffffu, e[c], 1);
                 const float nb = __shfl_sync(0xffffffffu, xv, hb * 16 + c);
                 const float e1 = lane == 31 ? nb : dn;
-                const float x = fmaxf(fmaxf(fmaxf(e[c], o[c]), e1) + bias[hb * 16 + c], 0.f);
+                const float x = fmaxf(fmaxf(fmaxf(e[c], o[c]), e1) + prm.bias_tab[bias + hb * 16 + c], 0.f);
                 o[c] = valid ? x : 0.f;
             }
             if (tile == 0) {
@@ -506,7 +506,6 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
     const int lane = threadIdx.x & 31;
-    float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
     const uint32_t bar0 = ptx::smem_u32(smem + OFF_BAR);
     // barriers: 0,1 w_full[slot]  2,3 w_empty[slot]  4.. act_ready[group]  4+NG.. acc_full[group]  4+2NG.. token[group]
     auto bar = [&](int k) { return bar0 + 8u * k; };
@@ -523,7 +522,6 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         ptx::fence_mbar_init();
         ptx::mbar_arrive(bar(BAR_TOK));                                // group 0 issues first
     }
-    for (int i = threadIdx.x; i < N_BIAS; i += blockDim.x) s_bias[i] = __ldg(prm.bias + i);
     {   // every byte an MMA can read must hold a finite bf16 (zero weights multiply the padding channels)
         uint4* z = reinterpret_cast<uint4*>(smem);
         for (uint32_t i = threadIdx.x; i < OFF_BIAS / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -603,40 +601,40 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                 float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph) ? prm.dbg + (r0 / G) * (T1 * 128 * 64) : nullptr;
                 if (ph == 0) {
                     epi_conv<MODE, true, 16, T1, P1, LV1, false, false, false, false, OUT_NAT, 0>(
-                        act, tl, s_bias + B_L1, nullptr, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                        prm, act, tl, B_L1, 0, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 1) {
                     epi_conv<MODE, true, 16, T1, P1, LV2, false, false, false, false, OUT_EO, 0>(
-                        act, tl, s_bias + B_L2, nullptr, n, A2_ARR, 4 * A2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                        prm, act, tl, B_L2, 0, n, A2_ARR, 4 * A2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 2) {
-                    epi_pool<MODE>(act, tl, s_bias + B_L3, n, g, wq, lane, dbg, rr);
+                    epi_pool<MODE>(prm, act, tl, B_L3, n, g, wq, lane, dbg, rr);
                 } else if (ph < 9) {
-                    const float* b = s_bias + B_S2 + (ph - 3) * 32;
+                    const int b = B_S2 + (ph - 3) * 32;
                     if ((ph - 3) % 2 == 0)
                         epi_conv<MODE, true, 32, T2, P2, LV3, false, false, false, false, OUT_NAT, 1>(
-                            act, tl, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                            prm, act, tl, b, 0, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else if (ph < 8)
                         epi_conv<MODE, true, 32, T2, P2, LV3, true, false, true, false, OUT_NAT, 1>(
-                            act, tl, b, nullptr, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                            prm, act, tl, b, 0, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else
                         epi_conv<MODE, true, 32, T2, P2, LV3, true, false, false, false, OUT_EO, 1>(
-                            act, tl, b, nullptr, n, E3_ARR, 8 * E3_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                            prm, act, tl, b, 0, n, E3_ARR, 8 * E3_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 9) {
                     epi_conv<MODE, false, 64, T3, P3, LV4, false, false, false, true, OUT_NAT, 1>(
-                        act, tl, s_bias + B_RCA, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                        prm, act, tl, B_RCA, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 10) {
                     epi_conv<MODE, true, 64, T3, P3, LV4, true, true, true, false, OUT_NAT, 1>(
-                        act, tl, s_bias + B_RCB, s_bias + B_RCS, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                        prm, act, tl, B_RCB, B_RCS, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else {
-                    const float* b = s_bias + B_S3 + (ph - 11) * 64;
+                    const int b = B_S3 + (ph - 11) * 64;
                     if ((ph - 11) % 2 == 0)
                         epi_conv<MODE, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1>(
-                            act, tl, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                            prm, act, tl, b, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else if (ph < 16)
                         epi_conv<MODE, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1>(
-                            act, tl, b, nullptr, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                            prm, act, tl, b, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else {
                         epi_conv<MODE, true, 64, T3, P3, LV4, true, false, false, false, OUT_GLOBAL, 1>(
-                            act, tl, b, nullptr, n, 0, 0, gout, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                            prm, act, tl, b, 0, n, 0, 0, gout, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                         if (prm.allele_out) accumulate_out(smem, act, prm, r0, n, item * NG + g, g, tid);
                         else copy_out(act, gout, n, g, tid);
                     }
@@ -756,7 +754,6 @@ struct HostConv {
 struct ReadConvTC {
     tc::TcParams prm;
     uint8_t* d_weights = nullptr;
-    float* d_bias = nullptr;
     int mode = 3;
     int sm_count = 148;
 };
@@ -870,12 +867,10 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { err = "cudaGetDeviceProperties failed"; delete t; return nullptr; }
     t->sm_count = prop.multiProcessorCount;
     if ((size_t)prop.sharedMemPerBlockOptin < SMEM_BYTES) { err = "device has too little shared memory per block"; delete t; return nullptr; }
-    if (cudaMalloc(&t->d_weights, blob.size()) != cudaSuccess || cudaMalloc(&t->d_bias, N_BIAS * 4) != cudaSuccess ||
-        cudaMemcpy(t->d_weights, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(t->d_bias, bias.data(), N_BIAS * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMalloc(&t->d_weights, blob.size()) != cudaSuccess ||
+        cudaMemcpy(t->d_weights, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
         err = "allocating the packed bf16 weights failed";
         if (t->d_weights) cudaFree(t->d_weights);
-        if (t->d_bias) cudaFree(t->d_bias);
         delete t;
         return nullptr;
     }
@@ -887,11 +882,11 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     else { opt_in((const void*)readconv_tc_kernel<1, false>); opt_in((const void*)readconv_tc_kernel<1, true>); }
     if (e != cudaSuccess) {
         err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
-        cudaFree(t->d_weights); cudaFree(t->d_bias); delete t;
+        cudaFree(t->d_weights); delete t;
         return nullptr;
     }
     t->prm.weights = t->d_weights;
-    t->prm.bias = t->d_bias;
+    std::memcpy(t->prm.bias_tab, bias.data(), N_BIAS * sizeof(float));
     t->prm.channels = channels;
     return t;
 }
@@ -932,7 +927,6 @@ static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long 
 static void readconv_tc_destroy(ReadConvTC* t) {
     if (!t) return;
     if (t->d_weights) cudaFree(t->d_weights);
-    if (t->d_bias) cudaFree(t->d_bias);
     delete t;
 }
 
