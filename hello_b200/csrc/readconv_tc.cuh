@@ -77,7 +77,7 @@ constexpr uint32_t WSLOT_BYTES = 49152;
 constexpr uint32_t OFF_ACT = 0;
 constexpr uint32_t OFF_W = NG * ACT_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_W + 2 * WSLOT_BYTES;
-constexpr uint32_t OFF_BAR = OFF_BIAS + N_BIAS * 4;
+constexpr uint32_t OFF_BAR = OFF_BIAS;                 // (the biases live in the kernel parameters)
 constexpr uint32_t N_BARS = 4 + 3 * NG;           // w_full[2], w_empty[2], act_ready[NG], acc_full[NG], token[NG]
 constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr uint32_t OFF_STATE = (OFF_TMEM + 16 + 15) & ~15u;   // work range of this CTA + running state of the fused allele sum
