@@ -591,3 +591,31 @@ def test_hybrid_site_independence_across_chunks(gpu, name):
         assert torch.equal(r.logits, full[0][:, a0:a1]) and torch.equal(r.meta, full[1][s0:s1])
         assert torch.equal(r.pair_prob, full[2][:, p0:p1]) and torch.equal(r.best_pair, full[3][s0:s1])
         assert torch.equal(r.call_pair, full[4][s0:s1])
+
+
+def test_huge_allele_and_partition_invariance(gpu):
+    """An allele supported by 4000 reads next to alleles with 1-2 reads: the fused reads->alleles sum must add every
+    allele's reads in read order whatever the CTA work partition is, so the site's results are bit-identical whether it
+    is scored alone or surrounded by other sites (which moves every partition boundary), and they match the oracle."""
+    cfg = arch.CONFIGS["single_tech"]
+    g = torch.Generator().manual_seed(4000)
+    n_alleles = [3]
+    nrpa = [4000, 1, 2]
+    reads = torch.randint(0, 256, (sum(nrpa), 6, 150), generator=g, dtype=torch.uint8)
+    reads[:, 2:] = reads[:, 2:] // 4                       # keep the 4000-read sum in a sane range
+    net = net_for(gpu, cfg, "bf16x3")
+    alone = net.forward((reads, None), n_alleles, (nrpa, None), None).clone()
+    pp_alone = net.last_result.pair_prob.clone()
+    pl = synth.make_pileups(300, coverage=11, channels=cfg.read_cin, seed=9)
+    t, naps, (nr0, _), _ = pl.forward_args()
+    for k in (0, 150, 300):                                # the big site first, in the middle, last
+        sao = pl.site_allele_off
+        a_k = int(sao[k])
+        r_k = int(pl.allele_read_off[0][a_k])
+        mixed_reads = torch.cat([t[0][:r_k], reads, t[0][r_k:]])
+        mixed = net.forward((mixed_reads, None), naps[:k] + n_alleles + naps[k:], (nr0[:a_k] + nrpa + nr0[a_k:], None), None)
+        assert torch.equal(mixed[a_k:a_k + 3], alone), k
+        p_k = int(net.last_result.pair_off[k])
+        assert torch.equal(net.last_result.pair_prob[:, p_k:p_k + 6], pp_alone), k
+    ref = oracle_for(cfg).forward((reads, None), n_alleles, (nrpa, None), None)
+    assert (alone - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
