@@ -103,6 +103,25 @@ def with_slots(layers: List[Layer]) -> List[Tuple[int, Layer]]:
     return out
 
 
+def keyed_layers(net: str, layers: List[Layer], split: Optional[int] = None) -> List[Tuple[str, Layer]]:
+    """[(state_dict key prefix of the layer's module, layer)].  Without an addendum the prefix is
+    ``<net>.network.<slot>``.  With one (``split`` = index of its first layer) the sub-network is the
+    ``torch.nn.Sequential(original, addendum)`` that build_on_top makes
+    (MixtureOfExpertsAdvancedXferLearning.py:131-160): ``<net>.0.network.<slot>`` for the original layers and
+    ``<net>.1.network.<slot>`` -- slots counted from zero again -- for the added ones."""
+    if split is None:
+        return [("%s.network.%d" % (net, slot), layer) for slot, layer in with_slots(layers)]
+    return ([("%s.0.network.%d" % (net, slot), layer) for slot, layer in with_slots(layers[:split])] +
+            [("%s.1.network.%d" % (net, slot), layer) for slot, layer in with_slots(layers[split:])])
+
+
+def linear_key(prefix: str) -> str:
+    """Key prefix of the Linear inside a GapLinear whose first module sits at `prefix` (AdaptiveAvgPool1d, Flatten,
+    an empty slot, then the linear: NNTools.terminus, NNTools.py:517-566)."""
+    head, slot = prefix.rsplit(".", 1)
+    return "%s.%d.linear" % (head, int(slot) + 3)
+
+
 def read_convolver(cin: int = 6, width: int = 1) -> List[Layer]:
     """architectures/read_convolver.py:9-144 (cin=7: read_convolver_with_hp_channel.py; width=2: _wide)."""
     a, b, c = 16 * width, 32 * width, 64 * width
@@ -162,6 +181,8 @@ class ModelConfig:
     combiners: bool
     meta: Optional[str]                  # None | "meta_convolver" | "meta_convolver_ref"
     width: int = 1
+    addendum: bool = False               # transfer-learning model: two more residual blocks on top of the read convolvers,
+                                         # the compressors and the (single) expert head (architectures/*_addendum.py)
 
     @property
     def hybrid(self) -> bool:
@@ -175,13 +196,17 @@ class ModelConfig:
     def networks(self):
         """name -> layer table, in the reference's registration order (MoEAttention.__init__, :104-115)."""
         nets = {}
+        extra = lambda c: [Res(c, c, 1, False), Res(c, c, 1, False)] if self.addendum else []
         for t, cin in enumerate(self.read_cin):
-            nets["read_convolver%d" % t] = read_convolver(cin, self.width)
+            nets["read_convolver%d" % t] = read_convolver(cin, self.width) + extra(64 * self.width)
         for t in range(len(self.read_cin)):
-            nets["compressor%d" % t] = compressor(self.width)
+            nets["compressor%d" % t] = compressor(self.width) + extra(128 * self.width)
         for e in range(3):
             if self.xattn_present[e]:
-                nets["xattn%d" % e] = xattn(self.width)
+                x = xattn(self.width)
+                # build_on_top strips the pooled linear head of the original expert before stacking
+                # (undo_terminating_layers, XferLearning.py:69-91); the addendum ends in a head of its own
+                nets["xattn%d" % e] = x[:-1] + extra(256 * self.width) + x[-1:] if self.addendum else x
         if self.meta == "meta_convolver":
             nets["meta"] = meta_convolver()
         elif self.meta == "meta_convolver_ref":
@@ -190,6 +215,20 @@ class ModelConfig:
             nets["combiner0"] = combiner(self.width)
             nets["combiner1"] = combiner(self.width)
         return nets
+
+    def addendum_split(self, net: str) -> Optional[int]:
+        """Index of the first added layer in networks()[net], None when the sub-network has no addendum
+        (moe_attention_config_*_addendum.py: read convolvers, compressors and the expert head; never combiners / meta)."""
+        if not self.addendum or net.startswith(("combiner", "meta")):
+            return None
+        base = {"read_convolver": read_convolver, "compressor": compressor}
+        for stem, fn in base.items():
+            if net.startswith(stem):
+                return len(fn())
+        return len(xattn()) - 1
+
+    def keyed(self, net: str) -> List[Tuple[str, Layer]]:
+        return keyed_layers(net, self.networks()[net], self.addendum_split(net))
 
 
 CONFIGS = {
@@ -205,6 +244,19 @@ CONFIGS = {
     "hybrid_full": ModelConfig("hybrid_full", (6, 6), (True, True, True), True, "meta_convolver"),
     # ..._no_ensemble_wide.py (2x channels everywhere)
     "hybrid_no_ensemble_wide": ModelConfig("hybrid_no_ensemble_wide", (6, 6), (False, False, True), True, None, 2),
+    # moe_attention_config_single_tech_old_equivalent_weight_norm_addendum.py stacked on the single-tech model by
+    # MixtureOfExpertsAdvancedXferLearning.build_on_top (:94-183)
+    "single_tech_addendum": ModelConfig("single_tech_addendum", (6,), (True, False, False), False, None, 1, True),
+    # ..._full_hybrid_old_equivalent_weight_norm_no_ensemble_addendum.py stacked on the shipped hybrid model
+    "hybrid_no_ensemble_addendum": ModelConfig("hybrid_no_ensemble_addendum", (6, 6), (False, False, True), True, None, 1,
+                                               True),
+}
+
+# configs whose model is <base model> + build_on_top(<addendum config module>)
+REFERENCE_ADDENDUM_MODULE = {
+    "single_tech_addendum": ("single_tech", "moe_attention_config_single_tech_old_equivalent_weight_norm_addendum"),
+    "hybrid_no_ensemble_addendum": ("hybrid_no_ensemble",
+                                    "moe_attention_config_full_hybrid_old_equivalent_weight_norm_no_ensemble_addendum"),
 }
 
 REFERENCE_CONFIG_MODULE = {

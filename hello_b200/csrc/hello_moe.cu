@@ -64,6 +64,9 @@ struct hello_moe {
     HeadConvTC* head[N_NETS] = {};   // fused tcgen05 compressor / xattn / meta_convolver (tensor-core precisions)
     CombConvTC* comb[2] = {nullptr, nullptr};   // fused tcgen05 combiner0 / combiner1
     ConvLayerTC* layer_tc = nullptr;            // generic tcgen05 layers for what the fused kernels do not cover
+    // Sub-networks with an addendum (two more residual blocks stacked by the reference's build_on_top,
+    // MixtureOfExpertsAdvancedXferLearning.py:94-183): the fused kernel runs the original layers, `tail` the added ones.
+    std::vector<LayerDesc> tail[N_NETS];
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;            // pairs (start, stop), created lazily
     size_t ev_used = 0;
@@ -225,6 +228,34 @@ struct Runner {
         return check(headconv_tc_launch(t, in_a, in_s, site_idx, n, out, out_stride, softmax, st), "headconv_tc");
     }
 
+    // One head sub-network (compressor / xattn / meta_convolver) on n items [n, in_len, in_ch]; with in_s the operand is
+    // 2*in_a - in_s[site_idx] (xattn_subtract.py:226-231).  Feature nets write `out`, pooled ones through `gap`.
+    // Fused kernel when the layer table matches it, fused kernel + the added layers for an addendum model, else layer-wise.
+    bool head_net(int id, const float* in_a, const float* in_s, const int32_t* site_idx, long long n, int in_len, int in_ch,
+                  float* out, const GapOut* gap) {
+        HeadConvTC* t = h->head[id];
+        if (t && h->tail[id].empty())
+            return gap ? head(t, in_a, in_s, site_idx, n, gap->out, gap->stride, gap->softmax)
+                       : head(t, in_a, in_s, site_idx, n, out, 0, 0);
+        const size_t m = arena->mark();
+        bool ok;
+        if (t) {
+            float* mid = arena->allocf(n * (long long)t->out_len * t->out_ch);
+            if (arena->overflow) return fail(HELLO_ERR_WORKSPACE, "workspace overflow");
+            ok = head(t, in_a, in_s, site_idx, n, mid, 0, 0) &&
+                 run_net(h->tail[id], view_cl(mid, t->out_len, t->out_ch), n, out, gap);
+        } else if (in_s) {
+            const long long elems = (long long)in_len * in_ch;
+            float* x = arena->allocf(n * elems);
+            if (arena->overflow) return fail(HELLO_ERR_WORKSPACE, "workspace overflow");
+            ok = two_a_minus_s(in_a, in_s, site_idx, x, n, elems) && run_net(h->nets[id], view_cl(x, in_len, in_ch), n, out, gap);
+        } else {
+            ok = run_net(h->nets[id], view_cl(in_a, in_len, in_ch), n, out, gap);
+        }
+        arena->release(m);
+        return ok;
+    }
+
     bool comb(CombConvTC* t, const float* in_a, const float* in_b, int stride, long long n, float* out) {
         if (dry || n == 0) return true;
         h->launches++;
@@ -297,7 +328,9 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         float* a_feat = ar.allocf(na * read_e);
         const size_t m2 = ar.mark();
         // the fused kernel sums the reads of every allele itself (no per-read maps in HBM); the per-layer path needs them
-        float* r_feat = h->tc[t] ? nullptr : ar.allocf(nr * read_e);
+        const bool rc_tail = h->tc[t] && !h->tail[NET_RC0 + t].empty();
+        float* r_feat = (h->tc[t] && !rc_tail) ? nullptr : ar.allocf(nr * read_e);
+        float* r_pre = rc_tail ? ar.allocf(nr * read_e) : nullptr;      // fused original layers -> added layers
         if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
         // read convolver (architectures/read_convolver.py) on uint8 rows
         const uint8_t* reads = dry ? nullptr : in->d_reads[t] + (size_t)ck.r0[t] * L * C;
@@ -313,7 +346,18 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
             ev_stop = h->ev_pool[h->ev_used + 1];
             h->ev_used += 2;
         }
-        if (h->tc[t]) {
+        if (rc_tail) {
+            if (!dry && nr > 0) {
+                cudaError_t e = readconv_tc_launch(h->tc[t], reads, nr, in->input_layout, r_pre, run.st, nullptr, -1, nullptr,
+                                                   nullptr, 0, 0);
+                h->launches++;
+                if (!run.check(e, "readconv_tc")) return false;
+            }
+            if (!run.run_net(h->tail[NET_RC0 + t], view_cl(r_pre, h->read_len, h->read_ch), nr, r_feat, nullptr)) return false;
+            if (ev_stop && !run.check(cudaEventRecord(ev_stop, run.st), "cudaEventRecord")) return false;
+            if (!run.segsum(r_feat, a_feat, dry ? nullptr : in->d_allele_read_off[t] + ck.a0, na, (int)ck.r0[t], read_e))
+                return false;
+        } else if (h->tc[t]) {
             if (!dry && nr > 0) {
                 // read convolver + reads -> alleles (reduceSlots, :163) in one kernel
                 cudaError_t e = readconv_tc_launch(h->tc[t], reads, nr, in->input_layout, nullptr, run.st, nullptr, -1, a_feat,
@@ -334,28 +378,14 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         }
         ar.release(m2);
         // compressor (:125)
-        if (h->head[NET_CMP0 + t]) {
-            if (!run.head(h->head[NET_CMP0 + t], a_feat, nullptr, nullptr, na, c_t[t], 0, 0)) return false;
-        } else if (!run.run_net(h->nets[NET_CMP0 + t], view_cl(a_feat, h->read_len, h->read_ch), na, c_t[t], nullptr)) {
-            return false;
-        }
+        if (!run.head_net(NET_CMP0 + t, a_feat, nullptr, nullptr, na, h->read_len, h->read_ch, c_t[t], nullptr)) return false;
         ar.release(m1);
         // alleles -> sites on the compressed features (:142-147)
         if (!run.segsum(c_t[t], s_t[t], dry ? nullptr : in->d_site_allele_off + ck.s0, ns, (int)ck.a0, comp_e))
             return false;
-        if (cfg.xattn_present[t] && h->head[NET_X0 + t]) {
-            // 2a - s is formed by the kernel's operand loader
-            if (!run.head(h->head[NET_X0 + t], c_t[t], s_t[t], site_idx, na,
-                          dry ? nullptr : out->d_logits + (long long)t * A_total + ck.a0, 1, 0))
-                return false;
-        } else if (cfg.xattn_present[t]) {
-            const size_t m3 = ar.mark();
-            float* x = ar.allocf(na * comp_e);
-            if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
-            if (!run.two_a_minus_s(c_t[t], s_t[t], site_idx, x, na, comp_e)) return false;
+        if (cfg.xattn_present[t]) {
             Runner::GapOut g{dry ? nullptr : out->d_logits + (long long)t * A_total + ck.a0, 1, 0};
-            if (!run.run_net(h->nets[NET_X0 + t], view_cl(x, h->comp_len, h->comp_ch), na, nullptr, &g)) return false;
-            ar.release(m3);
+            if (!run.head_net(NET_X0 + t, c_t[t], s_t[t], site_idx, na, h->comp_len, h->comp_ch, nullptr, &g)) return false;
         }
     }
 
@@ -382,25 +412,13 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
             if (!run.run_net(h->nets[NET_CB1], view_cl(cat, h->comp_len, 2 * cc), ns, s2, nullptr)) return false;
             ar.release(m);
         }
-        if (h->head[NET_X2]) {
-            if (!run.head(h->head[NET_X2], c2, s2, site_idx, na, dry ? nullptr : out->d_logits + 2LL * A_total + ck.a0, 1, 0))
-                return false;
-        } else {
-            float* x = ar.allocf(na * comp_e);
-            if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
-            if (!run.two_a_minus_s(c2, s2, site_idx, x, na, comp_e)) return false;
+        {
             Runner::GapOut g{dry ? nullptr : out->d_logits + 2LL * A_total + ck.a0, 1, 0};
-            if (!run.run_net(h->nets[NET_X2], view_cl(x, h->comp_len, cc), na, nullptr, &g)) return false;
-            ar.release(m);
+            if (!run.head_net(NET_X2, c2, s2, site_idx, na, h->comp_len, cc, nullptr, &g)) return false;
         }
         if (cfg.meta_kind == HELLO_META_SITE) {
-            if (h->head[NET_META]) {
-                if (!run.head(h->head[NET_META], s2, nullptr, nullptr, ns, dry ? nullptr : out->d_meta + 3 * ck.s0, 3, 1))
-                    return false;
-            } else {
-                Runner::GapOut gm{dry ? nullptr : out->d_meta + 3 * ck.s0, 3, 1};
-                if (!run.run_net(h->nets[NET_META], view_cl(s2, h->comp_len, cc), ns, nullptr, &gm)) return false;
-            }
+            Runner::GapOut gm{dry ? nullptr : out->d_meta + 3 * ck.s0, 3, 1};
+            if (!run.head_net(NET_META, s2, nullptr, nullptr, ns, h->comp_len, cc, nullptr, &gm)) return false;
             meta_done = true;
         }
     }
@@ -575,16 +593,25 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
         // Fused tcgen05 kernels where the sub-network has the architecture they are specialised for; every other
         // convolution (meta_convolver_ref, the 2x-wide models) goes through the generic tensor-core layer kernel.
         std::string terr;
-        for (int t = 0; t < cfg->n_tech; ++t)
-            h->tc[t] = readconv_tc_create(h->nets[NET_RC0 + t], h->d_weights, h->h_weights.data(), cfg->read_channels[t],
-                                          cfg->feature_length, cfg->precision, terr);
+        for (int t = 0; t < cfg->n_tech; ++t) {
+            const std::vector<LayerDesc>& net = h->nets[NET_RC0 + t];
+            const size_t fl = std::min<size_t>(net.size(), tc::N_RECORDS);
+            h->tc[t] = readconv_tc_create(std::vector<LayerDesc>(net.begin(), net.begin() + fl), h->d_weights,
+                                          h->h_weights.data(), cfg->read_channels[t], cfg->feature_length, cfg->precision, terr);
+            if (h->tc[t]) h->tail[NET_RC0 + t].assign(net.begin() + fl, net.end());
+        }
         std::vector<int> want;
         for (int t = 0; t < cfg->n_tech; ++t) want.push_back(NET_CMP0 + t);
         for (int e3 = 0; e3 < 3; ++e3) if (cfg->xattn_present[e3]) want.push_back(NET_X0 + e3);
         if (cfg->meta_kind == HELLO_META_SITE) want.push_back(NET_META);
         for (int id : want) {
             const int in_len = (id == NET_CMP0 || id == NET_CMP1) ? h->read_len : h->comp_len;
-            h->head[id] = headconv_tc_create(h->nets[id], in_len, h->d_weights, h->h_weights.data(), cfg->precision, terr);
+            const std::vector<LayerDesc>& net = h->nets[id];
+            const bool whole = net.size() <= 4 || (net.size() == 5 && net[4].kind == KIND_GAP_LINEAR);
+            const size_t fl = whole ? net.size() : 4;
+            h->head[id] = headconv_tc_create(std::vector<LayerDesc>(net.begin(), net.begin() + fl), in_len, h->d_weights,
+                                             h->h_weights.data(), cfg->precision, terr);
+            if (h->head[id]) h->tail[id].assign(net.begin() + fl, net.end());
         }
         if (cfg->has_combiners && cfg->xattn_present[2] && h->comp_len == cc::L) {
             for (int k = 0; k < 2; ++k)
@@ -598,8 +625,7 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
         for (int n = 0; n < N_NETS && ok_tc; ++n) {
             const bool fused = (n <= NET_RC1 && h->tc[n - NET_RC0]) || h->head[n] ||
                                ((n == NET_CB0 || n == NET_CB1) && h->comb[n - NET_CB0]);
-            if (fused) continue;
-            for (const LayerDesc& L : h->nets[n]) {
+            for (const LayerDesc& L : fused ? h->tail[n] : h->nets[n]) {
                 if (L.kind == KIND_CONV) ok_tc = convlayer_tc_add(h->layer_tc, L.a, h->d_weights, h->h_weights.data(), terr);
                 if (L.kind == KIND_RES) {
                     ok_tc = convlayer_tc_add(h->layer_tc, L.a, h->d_weights, h->h_weights.data(), terr) &&
@@ -789,17 +815,24 @@ int hello_moe_run_net(hello_moe* h, int net_id, const void* d_in, int64_t n_item
     ar.base = static_cast<char*>(d_workspace);
     ar.cap = workspace_bytes;
     Runner run{h, &ar, static_cast<cudaStream_t>(stream), false};
+    const bool gap = net.back().kind == KIND_GAP_LINEAR;
+    Runner::GapOut g{d_out, co, 0};
     if (is_read && h->tc[net_id - NET_RC0]) {
+        const std::vector<LayerDesc>& tail = h->tail[net_id];
+        float* pre = tail.empty() ? d_out : ar.allocf(n_items * (long long)lo * co);
+        if (ar.overflow) { h->err = "workspace overflow"; return HELLO_ERR_WORKSPACE; }
         if (n_items > 0) {
             e = readconv_tc_launch(h->tc[net_id - NET_RC0], static_cast<const uint8_t*>(d_in), n_items,
-                                   input_layout, d_out, run.st);
+                                   input_layout, pre, run.st);
             h->launches++;
             if (!run.check(e, "readconv_tc")) return run.status;
         }
-        return HELLO_OK;
+        if (!tail.empty()) run.run_net(tail, view_cl(pre, lo, co), n_items, d_out, nullptr);
+        return run.status;
     }
     if (h->head[net_id]) {
-        run.head(h->head[net_id], static_cast<const float*>(d_in), nullptr, nullptr, n_items, d_out, co, 0);
+        run.head_net(net_id, static_cast<const float*>(d_in), nullptr, nullptr, n_items, lin, cin, gap ? nullptr : d_out,
+                     gap ? &g : nullptr);
         return run.status;
     }
     if ((net_id == NET_CB0 || net_id == NET_CB1) && h->comb[net_id - NET_CB0]) {
@@ -807,8 +840,6 @@ int hello_moe_run_net(hello_moe* h, int net_id, const void* d_in, int64_t n_item
         run.comb(h->comb[net_id - NET_CB0], x, x + cc::C_HALF, 2 * cc::C_HALF, n_items, d_out);
         return run.status;
     }
-    const bool gap = net.back().kind == KIND_GAP_LINEAR;
-    Runner::GapOut g{d_out, co, 0};
     run.run_net(net, v, n_items, gap ? nullptr : d_out, gap ? &g : nullptr);
     return run.status;
 }

@@ -60,6 +60,7 @@ constexpr uint32_t GRP_COLS = 160;
 constexpr int LIN = 150, LV1 = 148, LV2 = 146, LV3 = 71, LV4 = 36;   // valid lengths
 constexpr int LOUT = 36, COUT = 64;
 constexpr int N_PHASES = 17;
+constexpr int N_RECORDS = 11;                  // layer records the kernel covers: 3 convs, max-pool, 7 residual blocks
 constexpr int N_BIAS = 832;
 constexpr int THREADS = (NG * EW + NG + 1) * 32;
 

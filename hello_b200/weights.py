@@ -28,11 +28,10 @@ _HEADER_BYTES = 128
 _REC_INTS = 32
 
 
-def conv_keys(net: str, layers) -> List[Tuple[str, Tuple[int, ...], str]]:
+def conv_keys(cfg: arch.ModelConfig, net: str) -> List[Tuple[str, Tuple[int, ...], str]]:
     """[(key prefix, v-shape, kind)] for every parametrised layer, in reference registration order."""
     out = []
-    for slot, layer in arch.with_slots(layers):
-        base = "%s.network.%d" % (net, slot)
+    for base, layer in cfg.keyed(net):
         if isinstance(layer, arch.Conv):
             out.append((base + ".conv1d", (layer.cout, layer.cin, layer.k), "conv"))
         elif isinstance(layer, arch.Res):
@@ -42,15 +41,15 @@ def conv_keys(net: str, layers) -> List[Tuple[str, Tuple[int, ...], str]]:
             if s is not None:
                 out.append((base + ".shNetwork.network.0.conv1d", (s.cout, s.cin, s.k), "conv"))
         elif isinstance(layer, arch.GapLinear):
-            out.append(("%s.network.%d.linear" % (net, slot + 3), (layer.cout, layer.cin), "linear"))
+            out.append((arch.linear_key(base), (layer.cout, layer.cin), "linear"))
     return out
 
 
 def param_shapes(cfg: arch.ModelConfig) -> Dict[str, Tuple[int, ...]]:
     """name -> shape for the whole model, mirroring MoEAttention.state_dict()."""
     shapes = {}
-    for net, layers in cfg.networks().items():
-        for prefix, vshape, _ in conv_keys(net, layers):
+    for net in cfg.networks():
+        for prefix, vshape, _ in conv_keys(cfg, net):
             shapes[prefix + ".bias"] = (vshape[0],)
             shapes[prefix + ".weight_g"] = (vshape[0],) + (1,) * (len(vshape) - 1)
             shapes[prefix + ".weight_v"] = vshape
@@ -67,8 +66,8 @@ def init_params(cfg: arch.ModelConfig, seed: int = 13) -> Dict[str, torch.Tensor
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     params = {}
-    for net, layers in cfg.networks().items():
-        for prefix, vshape, _ in conv_keys(net, layers):
+    for net in cfg.networks():
+        for prefix, vshape, _ in conv_keys(cfg, net):
             fan_in = int(np.prod(vshape[1:]))
             bound = 1.0 / np.sqrt(fan_in)
             v = ((rng.random(vshape) * 2.0 - 1.0) * bound).astype(np.float32)
@@ -163,11 +162,10 @@ def pack_blob(cfg: arch.ModelConfig, params: Dict[str, torch.Tensor]) -> bytes:
     first = [0] * N_NET_SLOTS
     count = [0] * N_NET_SLOTS
     zero8 = [0] * 8
-    for net, layers in cfg.networks().items():
+    for net in cfg.networks():
         nid = NET_IDS[net]
         first[nid] = len(recs)
-        for slot, layer in arch.with_slots(layers):
-            base = "%s.network.%d" % (net, slot)
+        for base, layer in cfg.keyed(net):
             if isinstance(layer, arch.Front):
                 continue
             if isinstance(layer, arch.Conv):
@@ -181,7 +179,7 @@ def pack_blob(cfg: arch.ModelConfig, params: Dict[str, torch.Tensor]) -> bytes:
                     if layer.conv_shortcut else zero8
                 recs.append([KIND_RES, int(layer.conv_shortcut)] + a + b + s)
             elif isinstance(layer, arch.GapLinear):
-                w, b = folded(params, "%s.network.%d.linear" % (net, slot + 3))
+                w, b = folded(params, arch.linear_key(base))
                 recs.append([KIND_GAP_LINEAR, 0] + [layer.cin, layer.cout, 1, 1, 0, 0, bw.add(w), bw.add(b)]
                             + zero8 + zero8)
         count[nid] = len(recs) - first[nid]

@@ -36,6 +36,8 @@ CASES = {
     "hybrid_full": (6, 8, 105, False),
     "hybrid_no_ensemble_wide": (3, 6, 106, False),
     "single_tech_uniform": (4, 8, 107, True),
+    "single_tech_addendum": (5, 8, 108, False),
+    "hybrid_no_ensemble_addendum": (4, 6, 109, False),
 }
 
 
@@ -51,8 +53,20 @@ def run_case(case: str) -> None:
     name = case.replace("_uniform", "")
     n_sites, cov, seed, uniform = CASES[case]
     cfg = arch.CONFIGS[name]
-    mod = importlib.import_module(arch.REFERENCE_CONFIG_MODULE[name])
-    moe = M.create_moe_attention_model(mod.configDict).eval()
+    if name in arch.REFERENCE_ADDENDUM_MODULE:
+        # transfer-learning model: the reference's build_on_top stacks the addendum networks on a trained base model
+        # (MixtureOfExpertsDNNFastXferLearning.py:494-502 does this on a DataParallel(WrapperForDataParallel(moe)))
+        import types
+        import MixtureOfExpertsAdvancedXferLearning as X
+        base_name, add_module = arch.REFERENCE_ADDENDUM_MODULE[name]
+        base = M.create_moe_attention_model(importlib.import_module(arch.REFERENCE_CONFIG_MODULE[base_name]).configDict)
+        add = importlib.import_module(add_module).configDict
+        holder = types.SimpleNamespace(module=types.SimpleNamespace(dnn=base))
+        moe, _ = X.build_on_top(holder, **{k: X.make_network(add, k) for k in add})
+        moe = moe.eval()
+    else:
+        mod = importlib.import_module(arch.REFERENCE_CONFIG_MODULE[name])
+        moe = M.create_moe_attention_model(mod.configDict).eval()
     shapes = weights.param_shapes(cfg)
     sd = moe.state_dict()
     assert list(sd.keys()) == list(shapes.keys()), "arch.py does not describe the reference model"

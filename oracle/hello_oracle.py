@@ -50,10 +50,9 @@ def reduce_slots(d: torch.Tensor, slots) -> torch.Tensor:
 class FoldedNet:
     """One sub-network with weight-norm folded once (the reference refolds on every forward)."""
 
-    def __init__(self, net: str, layers, params):
+    def __init__(self, cfg: arch.ModelConfig, net: str, params):
         self.layers = []
-        for slot, layer in arch.with_slots(layers):
-            base = "%s.network.%d" % (net, slot)
+        for base, layer in cfg.keyed(net):          # addendum layers (XferLearning.py:131-160) simply follow
             if isinstance(layer, arch.Conv):
                 self.layers.append(("conv", layer, folded(params, base + ".conv1d")))
             elif isinstance(layer, arch.MaxPool):
@@ -64,7 +63,7 @@ class FoldedNet:
                 ws = folded(params, base + ".shNetwork.network.0.conv1d") if layer.conv_shortcut else None
                 self.layers.append(("res", layer, (wa, wb, ws)))
             elif isinstance(layer, arch.GapLinear):
-                self.layers.append(("gap", layer, folded(params, "%s.network.%d.linear" % (net, slot + 3))))
+                self.layers.append(("gap", layer, folded(params, arch.linear_key(base))))
 
     @staticmethod
     def _conv(x, c: arch.Conv, wb):
@@ -96,7 +95,7 @@ class OracleModel:
 
     def __init__(self, cfg: arch.ModelConfig, params: Dict[str, torch.Tensor]):
         self.cfg = cfg
-        self.nets = {name: FoldedNet(name, layers, params) for name, layers in cfg.networks().items()}
+        self.nets = {name: FoldedNet(cfg, name, params) for name in cfg.networks()}
 
     def _compress_and_predict(self, reduced, alleles_per_site: torch.Tensor, idx: int):
         c_allele = self.nets["compressor%d" % idx](reduced)

@@ -8,7 +8,7 @@ from hello_b200 import arch, synth, weights
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["single_tech", "single_tech_hp", "hybrid_no_ensemble", "hybrid_ensemble2", "hybrid_full",
-                "hybrid_no_ensemble_wide", "single_tech_uniform"]
+                "hybrid_no_ensemble_wide", "single_tech_uniform", "single_tech_addendum", "hybrid_no_ensemble_addendum"]
 
 
 def load_golden(case):

@@ -104,8 +104,9 @@ def test_blob_roundtrip(name):
     cin, cout, k = rec[2], rec[3], rec[4]
     data = np.frombuffer(blob, np.float32, n_floats, data_off)
     w = data[rec[8]:rec[8] + k * cin * cout].reshape(k * cin, cout)
-    v = params["read_convolver0.network.0.conv1d.weight_v"].numpy().astype(np.float64)
-    g = params["read_convolver0.network.0.conv1d.weight_g"].numpy().astype(np.float64)
+    key = cfg.keyed("read_convolver0")[0][0] + ".conv1d"          # "read_convolver0.0.network.0..." with an addendum
+    v = params[key + ".weight_v"].numpy().astype(np.float64)
+    g = params[key + ".weight_g"].numpy().astype(np.float64)
     ref = g * v / np.sqrt((v ** 2).sum(axis=(1, 2), keepdims=True))
     np.testing.assert_allclose(w, ref.transpose(2, 1, 0).reshape(k * cin, cout), rtol=2e-6, atol=1e-7)
 

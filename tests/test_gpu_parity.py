@@ -102,7 +102,10 @@ def test_generic_tensor_core_layers(gpu, precision):
 def test_standard_models_run_on_the_fused_kernels(gpu):
     """Kernel launches per chunk in the tensor-core mode: a silent fall-back to per-layer kernels would show here."""
     expect = {"single_tech": 6,            # read convolver (+ allele sum), compressor, segsum, xattn, site index + posterior
-              "hybrid_no_ensemble": 11}    # 2 x (read convolver, compressor, segsum) + 2 combiners + xattn2 + 2
+              "hybrid_no_ensemble": 11,    # 2 x (read convolver, compressor, segsum) + 2 combiners + xattn2 + 2
+              # addendum models: the fused kernels run the original layers, 4 layer-wise convs per addendum follow
+              "single_tech_addendum": 2 + (1 + 4 + 1) + (1 + 4 + 1) + (1 + 4 + 1),
+              "hybrid_no_ensemble_addendum": 2 + 2 * ((1 + 4 + 1) + (1 + 4 + 1)) + 2 + (1 + 4 + 1)}
     for name, n_launch in expect.items():
         cfg = arch.CONFIGS[name]
         pl = synth.make_pileups(6, coverage=6, channels=cfg.read_cin, seed=2)
@@ -125,6 +128,34 @@ def test_combiner_and_meta_networks(gpu):
     got = net.engine.run_net("meta", s).cpu().reshape(4, 3)
     ref = orc.nets["meta"](s.transpose(1, 2))
     assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("name", ["single_tech_addendum", "hybrid_no_ensemble_addendum"])
+def test_addendum_models_against_the_oracle(gpu, name, precision):
+    """Transfer-learning models (build_on_top, MixtureOfExpertsAdvancedXferLearning.py:94-183): every sub-network with
+    an addendum against the oracle's, and the whole forward on more sites than the golden case holds."""
+    cfg = arch.CONFIGS[name]
+    eng, orc = net_for(gpu, cfg, precision).engine, oracle_for(cfg)
+    tol = TC_LAYER_REL["bf16x3"] if precision == "bf16x3" else 2e-5
+    g = torch.Generator().manual_seed(5)
+    pl = synth.make_pileups(60, coverage=9, channels=cfg.read_cin, seed=77)
+    reads = pl.reads[0][:50]
+    got = eng.run_net("read_convolver0", reads).cpu()
+    ref = orc.nets["read_convolver0"](reads.transpose(1, 2).float()).transpose(1, 2)
+    assert (got - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+    xname = "xattn0" if not cfg.hybrid else "xattn2"
+    for net_name, shape in (("compressor0", (13, 36, 64)), (xname, (13, 18, 128))):
+        x = (torch.randn(shape, generator=g) * 10).float()
+        got = eng.run_net(net_name, x).cpu()
+        ref = orc.nets[net_name](x.transpose(1, 2))
+        ref = ref.transpose(1, 2) if ref.dim() == 3 else ref.reshape(got.shape)
+        assert (got - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item()), net_name
+    tensors, naps, nrpa, ref_seg = pl.forward_args()
+    res = net_for(gpu, cfg, precision).forward(tensors, naps, nrpa, ref_seg)
+    want = orc.forward(tensors, naps, nrpa, ref_seg)
+    np.testing.assert_allclose(flat_result(cfg, res)[0].numpy(), flat_result(cfg, want)[0].numpy(), rtol=0,
+                               atol=TOL_LOGIT[precision])
 
 
 # ------------------------------------------------------------------------------------- fused tcgen05 read convolver
