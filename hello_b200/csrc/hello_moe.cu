@@ -595,9 +595,9 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
         std::string terr;
         for (int t = 0; t < cfg->n_tech; ++t) {
             const std::vector<LayerDesc>& net = h->nets[NET_RC0 + t];
-            const size_t fl = std::min<size_t>(net.size(), tc::N_RECORDS);
-            h->tc[t] = readconv_tc_create(std::vector<LayerDesc>(net.begin(), net.begin() + fl), h->d_weights,
-                                          h->h_weights.data(), cfg->read_channels[t], cfg->feature_length, cfg->precision, terr);
+            size_t fl = 0;
+            h->tc[t] = readconv_tc_create(net, h->d_weights, h->h_weights.data(), cfg->read_channels[t], cfg->feature_length,
+                                          cfg->precision, terr, &fl);
             if (h->tc[t]) h->tail[NET_RC0 + t].assign(net.begin() + fl, net.end());
         }
         std::vector<int> want;

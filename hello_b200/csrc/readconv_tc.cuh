@@ -59,9 +59,13 @@ constexpr uint32_t RES_COL = 128;
 constexpr uint32_t GRP_COLS = 160;
 constexpr int LIN = 150, LV1 = 148, LV2 = 146, LV3 = 71, LV4 = 36;   // valid lengths
 constexpr int LOUT = 36, COUT = 64;
-constexpr int N_PHASES = 17;
-constexpr int N_RECORDS = 11;                  // layer records the kernel covers: 3 convs, max-pool, 7 residual blocks
-constexpr int N_BIAS = 832;
+constexpr int N_PHASES = 17;                   // layer phases of the standard read convolver
+constexpr int N_RECORDS = 11;                  // its layer records: 3 convs, max-pool, 7 residual blocks
+// Addendum models (architectures/read_convolver_addendum.py) append residual blocks at 64 channels: two more phases each,
+// same instructions as phases 11..16, so the phase count is a kernel parameter.
+constexpr int MAX_EXTRA_BLOCKS = 2;
+constexpr int MAX_PHASES = N_PHASES + 2 * MAX_EXTRA_BLOCKS;
+constexpr int N_BIAS = 832 + 2 * MAX_EXTRA_BLOCKS * 64;
 constexpr int THREADS = (NG * EW + NG + 1) * 32;
 
 // byte layout of one group's activation buffer (offsets relative to its base)
@@ -96,8 +100,9 @@ constexpr int B_L1 = 0, B_L2 = 16, B_L3 = 32, B_S2 = 64, B_RCA = 256, B_RCS = 32
 
 // Per layer phase: where its packed weights live and how many bytes the producer streams into a slot.
 struct TcParams {
-    uint32_t w_src[N_PHASES];
-    uint32_t w_bytes[N_PHASES];
+    uint32_t w_src[MAX_PHASES];
+    uint32_t w_bytes[MAX_PHASES];
+    int n_phases;             // 17 + 2 per appended residual block
     const uint8_t* reads;
     const uint8_t* weights;
     float bias_tab[N_BIAS];   // biases travel in the kernel parameters: constant-bank loads, no shared-memory bandwidth
@@ -497,7 +502,7 @@ __device__ __forceinline__ long long* trace_slot(const TcParams& prm, int item, 
     if (!prm.dbg || prm.dbg_phase != TRACE_PHASE || blockIdx.x != 0) return nullptr;
     const int li = item;
     if (li >= TRACE_ITEMS) return nullptr;
-    return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * NG + g) * N_PHASES) * 8;
+    return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * NG + g) * MAX_PHASES) * 8;
 }
 
 // DBG = false is the production kernel: the layer dump and the timeline stamps are compiled out (the kernel is ~9 k
@@ -572,6 +577,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
     CtaState* cst = reinterpret_cast<CtaState*>(smem + OFF_STATE);
     const long long R = cst->r_end, R0 = cst->r_begin;
     const int n_items_cta = (int)((R - R0 + NG * G - 1) / (NG * G));
+    const int n_ph = prm.n_phases;
 
     if (warp < W_EPI) {
         // ===================================================== epilogue warps (group g = warp / EW)
@@ -594,7 +600,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
             float* gout = prm.out ? prm.out + r0 * (long long)(LOUT * COUT) : nullptr;
             long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
 #pragma unroll 1
-            for (int ph = 0; ph < N_PHASES; ++ph) {
+            for (int ph = 0; ph < n_ph; ++ph) {
                 ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
                 ++acc_n;
                 ptx::tc_fence_after();
@@ -630,7 +636,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                     if ((ph - 11) % 2 == 0)
                         epi_conv<MODE, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1>(
                             prm, act, tl, b, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
-                    else if (ph < 16)
+                    else if (ph + 1 < n_ph)
                         epi_conv<MODE, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1>(
                             prm, act, tl, b, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else {
@@ -641,7 +647,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                     }
                 }
                 if (tr && tid == 0) tr[ph * 8 + 3] = clock64();
-                if (ph + 1 < N_PHASES) {
+                if (ph + 1 < n_ph) {
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
                     ptx::mbar_arrive(bar(BAR_ACT + g));
@@ -661,7 +667,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
             const int n = (int)max(0LL, min((long long)G, R - (R0 + ((long long)item * NG + g) * G)));
             long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
 #pragma unroll 1
-            for (int ph = 0; ph < N_PHASES; ++ph) {
+            for (int ph = 0; ph < n_ph; ++ph) {
                 const uint32_t slot = w_n & 1u;
                 // Every issuer waits for the slot (even one whose group is empty in this item): the slot is released
                 // only when all have passed it, which keeps them in lockstep with the producer.
@@ -712,7 +718,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                     }
                 }
 #pragma unroll 1
-                for (int ph = 0; ph < N_PHASES; ++ph) {
+                for (int ph = 0; ph < n_ph; ++ph) {
                     const uint32_t slot = w_n & 1u;
                     ptx::mbar_wait(bar(2 + slot), ((w_n >> 1) & 1u) ^ 1u);
                     const uint32_t bytes = prm.w_bytes[ph];
@@ -761,8 +767,11 @@ struct ReadConvTC {
 
 // Checks that `net` is the read_convolver architecture this kernel is specialised for and packs its weights.
 // `d_base` / `h_base`: device and host copies of the same float array the ConvDesc pointers index into.
+// `covered` receives the number of leading layer records of `net` the kernel runs (the standard 11, plus up to
+// MAX_EXTRA_BLOCKS appended 64-channel residual blocks); the caller runs whatever follows layer by layer.
 static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const float* d_base, const float* h_base,
-                                      int channels, int feature_length, int precision, std::string& err) {
+                                      int channels, int feature_length, int precision, std::string& err,
+                                      size_t* covered = nullptr) {
     using namespace tc;
     if (precision != HELLO_PREC_BF16X3 && precision != HELLO_PREC_BF16) { err = "unknown tensor-core precision"; return nullptr; }
     if (feature_length != LIN || channels < 1 || channels > 8) { err = "tensor-core read convolver needs L=150, C<=8"; return nullptr; }
@@ -774,12 +783,17 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
                L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&
                (L.has_shortcut != 0) == sc && (!sc || (L.s.cin == cin && L.s.cout == cout && L.s.k == 1 && L.s.stride == s && L.s.pad == 0));
     };
-    bool ok = net.size() == 11 && is_conv(net[0], channels, 16, 3, 1, 0) && is_conv(net[1], 16, 16, 3, 1, 0) &&
+    bool ok = net.size() >= (size_t)N_RECORDS && is_conv(net[0], channels, 16, 3, 1, 0) && is_conv(net[1], 16, 16, 3, 1, 0) &&
               is_conv(net[2], 16, 32, 3, 1, 0) && net[3].kind == KIND_MAXPOOL && net[3].a.k == 3 && net[3].a.stride == 2;
     for (int i = 4; ok && i < 7; ++i) ok = is_res(net[i], 32, 32, 1, false);
     ok = ok && is_res(net[7], 32, 64, 2, true);
     for (int i = 8; ok && i < 11; ++i) ok = is_res(net[i], 64, 64, 1, false);
     if (!ok) { err = "layer table is not the 16-16-32 / 3xRes32 / Res32->64(s2) / 3xRes64 read convolver"; return nullptr; }
+    int extra = 0;
+    while (extra < MAX_EXTRA_BLOCKS && (size_t)(N_RECORDS + extra) < net.size() && is_res(net[N_RECORDS + extra], 64, 64, 1, false))
+        ++extra;
+    if (covered) *covered = N_RECORDS + extra;
+    else if (net.size() != (size_t)(N_RECORDS + extra)) { err = "layers after the read convolver"; return nullptr; }
 
     const int parts = precision == HELLO_PREC_BF16X3 ? 2 : 1;
     auto hc = [&](const ConvDesc& c) { return HostConv{h_base + (c.w - d_base), h_base + (c.b - d_base), c.cin, c.cout, c.k}; };
@@ -851,7 +865,8 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     copy_bias(hc(net[7].s), B_RCS);
     fit &= pack_phase(10, {{hc(net[7].b), false}}, UNITS_S3);
     copy_bias(hc(net[7].b), B_RCB);
-    for (int r = 0; r < 3; ++r) {
+    t->prm.n_phases = N_PHASES + 2 * extra;
+    for (int r = 0; r < 3 + extra; ++r) {
         const LayerDesc& L = net[8 + r];
         for (int h2 = 0; h2 < 2; ++h2) {
             const int ph = 11 + 2 * r + h2;

@@ -17,6 +17,7 @@ sys.path.insert(0, ROOT)
 from hello_b200 import arch, model, weights          # noqa: E402
 
 NG, NPH, ITEMS = 3, 17, 16
+STRIDE = 21                     # tc::MAX_PHASES: phase slots per (item, group) in the trace record
 
 if __name__ == "__main__":
     prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
@@ -27,7 +28,7 @@ if __name__ == "__main__":
     g = torch.Generator().manual_seed(1)
     reads = torch.randint(0, 256, (n, 150, 6), generator=g, dtype=torch.uint8).cuda()
     out = torch.empty((n, 36, 64), dtype=torch.float32, device="cuda")
-    tr = torch.zeros((ITEMS, NG, NPH, 8), dtype=torch.int64, device="cuda")
+    tr = torch.zeros((ITEMS, NG, STRIDE, 8), dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
         rc = eng.lib.hello_moe_readconv_debug(eng.handle, 0, reads.data_ptr(), n, 1, -2, out.data_ptr(), tr.data_ptr(),
