@@ -36,7 +36,13 @@ namespace hc {
 
 constexpr int NSLOT = 6;
 constexpr uint32_t SLOT_BYTES = 16384;
-constexpr int N_PHASES = 7;
+constexpr int N_PHASES = 7;                    // layer phases of the standard head
+// Addendum models (architectures/compressor_conv_small_addendum.py, xattn_subtract_addendum.py) append residual blocks at
+// 2C channels in front of the output / pooled linear head: two more phases each, the instructions of phases 3..6.
+constexpr int MAX_EXTRA_BLOCKS = 2;
+constexpr int MAX_PHASES = N_PHASES + 2 * MAX_EXTRA_BLOCKS;
+constexpr int TRACE_SLOTS = MAX_PHASES + 1;    // timeline record: one slot per phase + one for the operand loader
+constexpr int N_BIAS_MAX = (15 + 4 * MAX_EXTRA_BLOCKS) * 128;
 constexpr int EPI_WARPS = 8;
 constexpr int DBG_ROWS = 256, DBG_COLS = 256;
 
@@ -57,13 +63,11 @@ struct Geo {
     static constexpr uint32_t E_LO = (C / 8) * 2 * E_ARR;
     static constexpr uint32_t S_LO = (N2 / 8) * S_ARR;
     static constexpr uint32_t ACT_BYTES = 2 * (E_LO > S_LO ? (E_LO > X_LO ? E_LO : X_LO) : (S_LO > X_LO ? S_LO : X_LO));
-    static constexpr int N_BIAS = 15 * C;
-    // bias table (floats): 1x1 conv, block-1 conv a / shortcut / conv b, then the four convs of blocks 2 and 3
+    // bias table (floats): 1x1 conv, block-1 conv a / shortcut / conv b, then two convs per following block
     static constexpr int B_0 = 0, B_1A = C, B_1S = 3 * C, B_1B = 5 * C, B_REST = 7 * C;
     static constexpr uint32_t OFF_ACT = 0;
     static constexpr uint32_t OFF_W = NGRP * ACT_BYTES;
-    static constexpr uint32_t OFF_BIAS = OFF_W + NSLOT * SLOT_BYTES;
-    static constexpr uint32_t OFF_BAR = OFF_BIAS + 15 * 128 * 4;
+    static constexpr uint32_t OFF_BAR = OFF_W + NSLOT * SLOT_BYTES;
     static constexpr uint32_t N_BARS = 2 * NSLOT + 2 * NGRP;  // full[NSLOT], empty[NSLOT], act_ready[NGRP], acc_full[NGRP]
     static constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
     static constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16;
@@ -78,14 +82,15 @@ struct HeadParams {
     const float* in_s;        // optional [n_sites, L, C]: operand = 2*in_a[i] - in_s[site_idx[i]]
     const int32_t* site_idx;  // [n] (with in_s)
     const uint8_t* weights;   // packed units, phase after phase
-    const float* bias;        // [15*C]
+    float bias_tab[N_BIAS_MAX];   // biases travel in the kernel parameters (constant bank), like the read convolver's
     const float* lin_w;       // [n_out][2C] pooled linear head (n_out > 0)
     const float* lin_b;       // [n_out]
     float* out;               // n_out == 0: [n, L/2, 2C];  else out[i*out_stride + o]
     float* dbg;               // optional [groups][256][256] dump of phase dbg_phase
     long long n_items;
     long long out_stride;
-    uint32_t w_src[N_PHASES]; // byte offset of each phase's first unit
+    uint32_t w_src[MAX_PHASES];   // byte offset of each phase's first unit
+    int n_phases;             // 7 + 2 per appended residual block
     int n_work;               // work items (NGRP groups each)
     int n_out, softmax, dbg_phase;
 };
@@ -141,7 +146,7 @@ __device__ __forceinline__ void load_input(uint8_t* act, const HeadParams& prm, 
 // Epilogue of one convolution for one group.  Thread = TMEM lane = packed row; this warp owns columns
 // [chalf*N/CS, (chalf+1)*N/CS).   y = relu(acc + bias) [+ resid (+ bias2)], invalid rows forced to zero.
 template <int MODE, int C, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID, int OUT>
-__device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float* bias, const float* bias2, int n,
+__device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, int bias, int bias2, int n,
                                          uint32_t out_stride, uint32_t out_lo, const HeadParams& prm, long long i0,
                                          float* __restrict__ dbg, int wrow, int lane, int chalf, float* part) {
     using Gm = Geo<C>;
@@ -163,8 +168,8 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, const float*
             ptx::tmem_wait_ld();
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                float x = fmaxf(v[c] + bias[c0 + c], 0.f);
-                if (RESID) x += RES_BIAS ? (r[c] + bias2[c0 + c]) : r[c];
+                float x = fmaxf(v[c] + prm.bias_tab[bias + c0 + c], 0.f);
+                if (RESID) x += RES_BIAS ? (r[c] + prm.bias_tab[bias2 + c0 + c]) : r[c];
                 v[c] = valid ? x : 0.f;
             }
             if (WRITE_RESID) ptx::tmem_st32(tl + RES_COL + c0, v);
@@ -290,13 +295,13 @@ __device__ __forceinline__ uint32_t phase_bytes(int ph) {
 }
 
 // Timeline hook (dbg_phase == -2, debug instantiation only): CTA 0 stamps clock64() for its first 16 work items as int64
-// [item][group][8 phases][4] = {issue start, issue end, accumulators seen, epilogue end}; phase slot 7 holds
+// [item][group][TRACE_SLOTS][4] = {issue start, issue end, accumulators seen, epilogue end}; slot MAX_PHASES holds
 // {operand load start, operand load end, 0, 0}.
 __device__ __forceinline__ long long* head_trace_slot(const HeadParams& prm, int item, int g, int ngrp) {
     if (!prm.dbg || prm.dbg_phase != -2 || blockIdx.x != 0) return nullptr;
     const int li = item / (int)gridDim.x;
     if (li >= 16) return nullptr;
-    return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * ngrp + g) * 8) * 4;
+    return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * ngrp + g) * TRACE_SLOTS) * 4;
 }
 
 template <int MODE, int C, bool DBG>
@@ -306,7 +311,6 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    float* s_bias = reinterpret_cast<float*>(smem + Gm::OFF_BIAS);
     const uint32_t bar0 = ptx::smem_u32(smem + Gm::OFF_BAR);
     auto bar = [&](int k) { return bar0 + 8u * k; };
     constexpr int BAR_FULL = 0, BAR_EMPTY = NSLOT, BAR_ACT = 2 * NSLOT, BAR_ACC = 2 * NSLOT + NGRP;
@@ -317,10 +321,9 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
         for (int g = 0; g < NGRP; ++g) { ptx::mbar_init(bar(BAR_ACT + g), 128 * CS); ptx::mbar_init(bar(BAR_ACC + g), 1); }
         ptx::fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < Gm::N_BIAS; i += blockDim.x) s_bias[i] = __ldg(prm.bias + i);
     {   // rows the MMAs read past the written part of an array must at least be initialised memory
         uint4* z = reinterpret_cast<uint4*>(smem);
-        for (uint32_t i = threadIdx.x; i < Gm::OFF_BIAS / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (uint32_t i = threadIdx.x; i < Gm::OFF_BAR / 16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (warp == EPI_WARPS + NGRP) {
         ptx::tmem_alloc(ptx::smem_u32(smem + Gm::OFF_TMEM), 512);
@@ -332,6 +335,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
     ptx::tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
     const long long n_items = prm.n_items;
+    const int n_ph = prm.n_phases;
 
     if (warp < EPI_WARPS) {
         // ===================================================== epilogue warps
@@ -347,15 +351,15 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
             const int n = (int)max(0LL, min((long long)G, n_items - i0));
             if (n <= 0) continue;
             long long* tr = DBG ? head_trace_slot(prm, item, g, NGRP) : nullptr;
-            if (tr && tid == 0) tr[7 * 4 + 0] = clock64();
+            if (tr && tid == 0) tr[MAX_PHASES * 4 + 0] = clock64();
             load_input<MODE, C>(act, prm, i0, n, tid);
-            if (tr && tid == 0) tr[7 * 4 + 1] = clock64();
+            if (tr && tid == 0) tr[MAX_PHASES * 4 + 1] = clock64();
             ptx::tc_fence_before();
             ptx::fence_proxy_async();
             ptx::mbar_arrive(bar(BAR_ACT + g));
             float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-            for (int ph = 0; ph < N_PHASES; ++ph) {
+            for (int ph = 0; ph < n_ph; ++ph) {
                 ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
                 ++acc_n;
                 ptx::tc_fence_after();
@@ -364,25 +368,27 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                                  ? prm.dbg + ((long long)item * NGRP + g) * (DBG_ROWS * DBG_COLS) : nullptr;
                 if (ph == 0) {
                     epi_conv<MODE, C, C, 2, Gm::P1, Gm::L, false, false, false, OUT_EO>(
-                        act, tl, s_bias + Gm::B_0, nullptr, n, Gm::E_ARR, Gm::E_LO, prm, i0, dbg, wrow, lane, chalf, part);
+                        act, tl, Gm::B_0, 0, n, Gm::E_ARR, Gm::E_LO, prm, i0, dbg, wrow, lane, chalf, part);
                 } else if (ph == 1) {
                     epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, false, false, false, OUT_NAT>(
-                        act, tl, s_bias + Gm::B_1A, nullptr, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
+                        act, tl, Gm::B_1A, 0, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
                 } else if (ph == 2) {
                     epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, true, true, OUT_NAT>(
-                        act, tl, s_bias + Gm::B_1B, s_bias + Gm::B_1S, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
-                } else if (ph == 3 || ph == 5) {
-                    epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, false, false, false, OUT_NAT>(
-                        act, tl, s_bias + Gm::B_REST + (ph - 3) * 2 * C, nullptr, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
-                } else if (ph == 4) {
-                    epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, false, true, OUT_NAT>(
-                        act, tl, s_bias + Gm::B_REST + (ph - 3) * 2 * C, nullptr, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
+                        act, tl, Gm::B_1B, Gm::B_1S, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
                 } else {
-                    epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, false, false, OUT_FINAL>(
-                        act, tl, s_bias + Gm::B_REST + (ph - 3) * 2 * C, nullptr, n, 0, 0, prm, i0, dbg, wrow, lane, chalf, part);
+                    const int b = Gm::B_REST + (ph - 3) * 2 * C;
+                    if ((ph - 3) % 2 == 0)                  // conv a of a residual block
+                        epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, false, false, false, OUT_NAT>(
+                            act, tl, b, 0, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
+                    else if (ph + 1 < n_ph)                 // conv b + residual, feeds the next block
+                        epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, false, true, OUT_NAT>(
+                            act, tl, b, 0, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
+                    else                                    // last block: output / pooled linear head
+                        epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, false, false, OUT_FINAL>(
+                            act, tl, b, 0, n, 0, 0, prm, i0, dbg, wrow, lane, chalf, part);
                 }
                 if (tr && tid == 0) tr[ph * 4 + 3] = clock64();
-                if (ph + 1 < N_PHASES) {
+                if (ph + 1 < n_ph) {
                     ptx::tc_fence_before();
                     ptx::fence_proxy_async();
                     ptx::mbar_arrive(bar(BAR_ACT + g));
@@ -431,7 +437,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
             const bool active = n_items > i0;
             long long* tr = DBG ? head_trace_slot(prm, item, g, NGRP) : nullptr;
 #pragma unroll 1
-            for (int ph = 0; ph < N_PHASES; ++ph) {
+            for (int ph = 0; ph < n_ph; ++ph) {
                 // (no turn-taking between the two compressor groups as in the read convolver: a layer's weights do not
                 // fit the ring, and both groups must drain every ring slot before it can be refilled)
                 if (active) {
@@ -470,7 +476,7 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                     }
                 }
 #pragma unroll 1
-                for (int ph = 0; ph < N_PHASES; ++ph) {
+                for (int ph = 0; ph < n_ph; ++ph) {
                     const uint32_t total = phase_bytes<MODE, C>(ph);
                     const uint8_t* src = prm.weights + prm.w_src[ph];
                     for (uint32_t o = 0; o < total; o += SLOT_BYTES) {
@@ -495,15 +501,17 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
 struct HeadConvTC {
     hc::HeadParams prm;
     uint8_t* d_weights = nullptr;
-    float* d_bias = nullptr;       // bias table followed by the pooled linear head (weights, bias)
+    float* d_bias = nullptr;       // the pooled linear head (weights, bias)
     int mode = 3, C = 0, sm_count = 148;
     int in_len = 0, out_len = 0, out_ch = 0;
 };
 
 // Checks that `net` is "1x1 conv C->C, Res(C->2C, stride 2, 1x1 shortcut), 2 x Res(2C) [, pooled linear]" with
 // C = 64 (L = 36) or C = 128 (L = 18) and packs its weights into ring units.
+// `covered` receives the number of leading layer records the kernel runs (with up to MAX_EXTRA_BLOCKS appended 2C-channel
+// residual blocks, and the pooled linear head when it directly follows them); the caller runs the rest layer by layer.
 static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_len, const float* d_base,
-                                      const float* h_base, int precision, std::string& err) {
+                                      const float* h_base, int precision, std::string& err, size_t* covered = nullptr) {
     using namespace hc;
     if (precision != HELLO_PREC_BF16X3 && precision != HELLO_PREC_BF16) { err = "unknown tensor-core precision"; return nullptr; }
     if (net.size() < 4 || net[0].kind != KIND_CONV) { err = "not a head network"; return nullptr; }
@@ -518,9 +526,14 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_
     };
     bool ok = net[0].a.cout == C && net[0].a.k == 1 && net[0].a.stride == 1 && net[0].a.pad == 0 && net[0].a.relu &&
               is_res(net[1], C, 2 * C, 2, true) && is_res(net[2], 2 * C, 2 * C, 1, false) && is_res(net[3], 2 * C, 2 * C, 1, false);
-    const bool pooled = net.size() == 5 && net[4].kind == KIND_GAP_LINEAR;
-    ok = ok && (net.size() == 4 || pooled);
-    if (pooled) ok = ok && net[4].a.cin == 2 * C && net[4].a.cout >= 1 && net[4].a.cout <= 4;
+    int extra = 0;
+    while (ok && extra < MAX_EXTRA_BLOCKS && (size_t)(4 + extra) < net.size() && is_res(net[4 + extra], 2 * C, 2 * C, 1, false)) ++extra;
+    const size_t n_blocks_end = 4 + extra;
+    const bool pooled = ok && net.size() > n_blocks_end && net[n_blocks_end].kind == KIND_GAP_LINEAR &&
+                        net[n_blocks_end].a.cin == 2 * C && net[n_blocks_end].a.cout >= 1 && net[n_blocks_end].a.cout <= 4;
+    const size_t n_cov = n_blocks_end + (pooled ? 1 : 0);
+    if (covered) *covered = n_cov;
+    else ok = ok && net.size() == n_cov;
     if (!ok) { err = "layer table is not conv1x1 / Res(s2) / 2 x Res (/ pooled linear)"; return nullptr; }
 
     const int parts = precision == HELLO_PREC_BF16X3 ? 2 : 1;
@@ -555,23 +568,24 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_
                 }
             }
     };
-    std::vector<float> bias(15 * C + 4 * 2 * C + 4, 0.f);
-    auto copy_bias = [&](const tc::HostConv& c, int off) { for (int i = 0; i < c.cout; ++i) bias[off + i] = c.b[i]; };
+    std::vector<float> lin(4 * 2 * C + 4, 0.f);               // pooled linear head: weights [n_out][2C], then bias
+    auto copy_bias = [&](const tc::HostConv& c, int off) { for (int i = 0; i < c.cout; ++i) t->prm.bias_tab[off + i] = c.b[i]; };
+    t->prm.n_phases = N_PHASES + 2 * extra;
     t->prm.w_src[0] = (uint32_t)blob.size(); pack_conv(hcv(net[0].a)); copy_bias(hcv(net[0].a), 0);
     t->prm.w_src[1] = (uint32_t)blob.size(); pack_conv(hcv(net[1].a)); pack_conv(hcv(net[1].s));
     copy_bias(hcv(net[1].a), C); copy_bias(hcv(net[1].s), 3 * C);
     t->prm.w_src[2] = (uint32_t)blob.size(); pack_conv(hcv(net[1].b)); copy_bias(hcv(net[1].b), 5 * C);
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < 2 + extra; ++r) {
         t->prm.w_src[3 + 2 * r] = (uint32_t)blob.size(); pack_conv(hcv(net[2 + r].a)); copy_bias(hcv(net[2 + r].a), 7 * C + (2 * r) * 2 * C);
         t->prm.w_src[4 + 2 * r] = (uint32_t)blob.size(); pack_conv(hcv(net[2 + r].b)); copy_bias(hcv(net[2 + r].b), 7 * C + (2 * r + 1) * 2 * C);
     }
     if (pooled) {
-        const ConvDesc& lin = net[4].a;                       // linear: w [cout][cin]
-        const float* w = h_base + (lin.w - d_base);
-        const float* b = h_base + (lin.b - d_base);
-        for (int i = 0; i < lin.cout * lin.cin; ++i) bias[15 * C + i] = w[i];
-        for (int i = 0; i < lin.cout; ++i) bias[15 * C + 4 * 2 * C + i] = b[i];
-        t->prm.n_out = lin.cout;
+        const ConvDesc& ld = net[n_blocks_end].a;             // linear: w [cout][cin]
+        const float* w = h_base + (ld.w - d_base);
+        const float* b = h_base + (ld.b - d_base);
+        for (int i = 0; i < ld.cout * ld.cin; ++i) lin[i] = w[i];
+        for (int i = 0; i < ld.cout; ++i) lin[4 * 2 * C + i] = b[i];
+        t->prm.n_out = ld.cout;
     }
 
     cudaDeviceProp prop;
@@ -581,9 +595,9 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_
     t->sm_count = prop.multiProcessorCount;
     const size_t smem = C == 64 ? Geo<64>::SMEM_BYTES : Geo<128>::SMEM_BYTES;
     if ((size_t)prop.sharedMemPerBlockOptin < smem) { err = "device has too little shared memory per block"; delete t; return nullptr; }
-    if (cudaMalloc(&t->d_weights, blob.size()) != cudaSuccess || cudaMalloc(&t->d_bias, bias.size() * 4) != cudaSuccess ||
+    if (cudaMalloc(&t->d_weights, blob.size()) != cudaSuccess || cudaMalloc(&t->d_bias, lin.size() * 4) != cudaSuccess ||
         cudaMemcpy(t->d_weights, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(t->d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpy(t->d_bias, lin.data(), lin.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
         err = "allocating the packed bf16 head weights failed";
         if (t->d_weights) cudaFree(t->d_weights);
         if (t->d_bias) cudaFree(t->d_bias);
@@ -607,9 +621,8 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_
         return nullptr;
     }
     t->prm.weights = t->d_weights;
-    t->prm.bias = t->d_bias;
-    t->prm.lin_w = t->d_bias + 15 * C;
-    t->prm.lin_b = t->d_bias + 15 * C + 4 * 2 * C;
+    t->prm.lin_w = t->d_bias;
+    t->prm.lin_b = t->d_bias + 4 * 2 * C;
     return t;
 }
 

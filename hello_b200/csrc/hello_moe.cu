@@ -607,10 +607,8 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
         for (int id : want) {
             const int in_len = (id == NET_CMP0 || id == NET_CMP1) ? h->read_len : h->comp_len;
             const std::vector<LayerDesc>& net = h->nets[id];
-            const bool whole = net.size() <= 4 || (net.size() == 5 && net[4].kind == KIND_GAP_LINEAR);
-            const size_t fl = whole ? net.size() : 4;
-            h->head[id] = headconv_tc_create(std::vector<LayerDesc>(net.begin(), net.begin() + fl), in_len, h->d_weights,
-                                             h->h_weights.data(), cfg->precision, terr);
+            size_t fl = 0;
+            h->head[id] = headconv_tc_create(net, in_len, h->d_weights, h->h_weights.data(), cfg->precision, terr, &fl);
             if (h->head[id]) h->tail[id].assign(net.begin() + fl, net.end());
         }
         if (cfg->has_combiners && cfg->xattn_present[2] && h->comp_len == cc::L) {

@@ -19,7 +19,7 @@ if __name__ == "__main__":
     x = (torch.randn((n,) + shape, generator=torch.Generator().manual_seed(1)) * 20).cuda()
     co, lo = arch.net_out_shape(cfg.networks()[net], shape[0])
     out = torch.empty((n, lo, co), dtype=torch.float32, device="cuda")
-    tr = torch.zeros((16, ngrp, 8, 4), dtype=torch.int64, device="cuda")
+    tr = torch.zeros((16, ngrp, 12, 4), dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
         rc = eng.lib.hello_moe_headconv_debug(eng.handle, weights.NET_IDS[net], x.data_ptr(), n, -2, out.data_ptr(), tr.data_ptr(),
@@ -29,7 +29,7 @@ if __name__ == "__main__":
     t = tr.cpu()
     print("cycles per item (steady):", float(t[11, 0, 6, 3] - t[1, 0, 6, 3]) / 10)
     sel = t[2:12]
-    print("operand load: %.0f" % (sel[:, :, 7, 1] - sel[:, :, 7, 0]).float().mean().item())
+    print("operand load: %.0f" % (sel[:, :, 11, 1] - sel[:, :, 11, 0]).float().mean().item())
     print("phase | issue (start->end)  end->acc seen  epilogue  epi end->next issue start")
     for ph in range(7):
         f = lambda a, b, p=ph: (sel[:, :, p, a] - sel[:, :, p, b]).float().mean().item()
