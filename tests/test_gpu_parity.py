@@ -650,3 +650,63 @@ def test_huge_allele_and_partition_invariance(gpu):
         assert torch.equal(net.last_result.pair_prob[:, p_k:p_k + 6], pp_alone), k
     ref = oracle_for(cfg).forward((reads, None), n_alleles, (nrpa, None), None)
     assert (alone - ref).abs().max().item() < 1e-3 * max(1.0, ref.abs().max().item())
+
+
+def test_c_abi_status_codes(gpu):
+    """include/hello_moe.h: every entry point answers with a negative hello_status and a message, never an exception or
+    a crash, and a failed call leaves the handle usable."""
+    import ctypes as C
+    from hello_b200 import _lib
+    lib = _lib.load()
+    cfg = arch.CONFIGS["single_tech"]
+    blob = weights.pack_blob(cfg, params_for(cfg))
+
+    def make_cfg(**over):
+        c = _lib.HelloCfg()
+        c.struct_size = C.sizeof(_lib.HelloCfg)
+        c.n_tech = 1
+        c.read_channels[0] = 6
+        c.xattn_present[0] = 1
+        c.meta_kind = _lib.META_NONE
+        c.feature_length = arch.FEATURE_LENGTH
+        c.precision = _lib.PRECISIONS["bf16x3"]
+        for k, v in over.items():
+            setattr(c, k, v)
+        return c
+
+    def create(blob_bytes, c):
+        h = C.c_void_p()
+        buf = (C.c_char * len(blob_bytes)).from_buffer_copy(blob_bytes)
+        rc = lib.hello_moe_create(buf, len(blob_bytes), C.byref(c), 0, C.byref(h))
+        return rc, h, lib.hello_moe_last_error(None).decode()
+
+    rc, h, msg = create(blob, make_cfg(struct_size=8))
+    assert rc == -1 and not h.value and "struct_size" in msg                      # HELLO_ERR_ARG
+    rc, h, msg = create(b"NOTABLOB" + blob[8:], make_cfg())
+    assert rc == -2 and not h.value and "magic" in msg                            # HELLO_ERR_BLOB
+    rc, h, msg = create(blob[:len(blob) // 2], make_cfg())
+    assert rc == -2 and not h.value and "truncated" in msg
+    rc, h, msg = create(blob, make_cfg(n_tech=2))
+    assert rc == -5 and not h.value and "wiring" in msg                           # HELLO_ERR_UNSUPPORTED
+    c7 = make_cfg()
+    c7.read_channels[0] = 7
+    rc, h, msg = create(blob, c7)
+    assert rc == -5 and not h.value
+
+    rc, h, msg = create(blob, make_cfg())
+    assert rc == 0 and h.value
+    try:
+        assert lib.hello_moe_forward(h, None, None, None, 0, None) == -1          # null batch / result
+        eng = net_for(gpu, cfg, "bf16x3").engine
+        pl = synth.make_pileups(50, coverage=8, channels=cfg.read_cin, seed=3)
+        batch = gpu.DeviceBatch.from_pileups(pl, DEV)
+        good = eng.run(batch)
+        tiny = torch.empty(4096, dtype=torch.uint8, device=DEV)                   # not even one site fits
+        with pytest.raises(_lib.HelloMoEError) as ei:
+            eng.run(batch, workspace=tiny)
+        assert "(-4)" in str(ei.value) or "workspace" in str(ei.value).lower()    # HELLO_ERR_WORKSPACE
+        again = eng.run(batch)                                                    # the handle is still good
+        assert torch.equal(good.logits, again.logits) and torch.equal(good.best_pair, again.best_pair)
+    finally:
+        lib.hello_moe_destroy(h)
+    lib.hello_moe_destroy(None)                                                   # documented as a no-op
