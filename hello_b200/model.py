@@ -567,6 +567,37 @@ def final_calls(res: BatchResult, site: int, alleles: Sequence[str]) -> Dict[str
     return out
 
 
+def feature_records(expert_prob, meta, pair_off, alleles_per_site: Sequence[Sequence[str]],
+                    loci: Sequence[Tuple[str, int, int]]) -> List[Dict[str, object]]:
+    """The ``.features`` list the caller pickles next to its VCF (caller_calling.py:746-754, 897-899) and that
+    ``prepareVcf.vcfRecords`` (prepareVcf.py:110-175) reads back: one dict per site with ``chromosome``, ``position``,
+    ``length`` (of the reference allele), ``meta`` (numpy float32 [3]) and ``expertPredictions`` (three dicts keyed by
+    the (allele_i, allele_j) tuples, i <= j in site order, holding 0-d float32 tensors).
+
+    expert_prob: [3, P] per-expert pair probabilities (rows 1..3 of BatchResult.pair_prob); meta: [S, 3];
+    pair_off: [S+1]; loci: (chromosome, start, reference-allele length) per site."""
+    ep = torch.as_tensor(expert_prob).detach().cpu().float()
+    mt = torch.as_tensor(meta).detach().cpu().float().numpy()
+    po = [int(x) for x in pair_off]
+    if ep.dim() != 2 or ep.shape[0] != 3 or len(po) != len(alleles_per_site) + 1 or len(loci) != len(alleles_per_site):
+        raise ValueError("feature_records: expert_prob must be [3, P] and pair_off / alleles / loci must describe the same sites")
+    out = []
+    for s, names in enumerate(alleles_per_site):
+        n = len(names)
+        if po[s + 1] - po[s] != n * (n + 1) // 2:
+            raise ValueError("site %d: %d alleles do not match %d genotype pairs" % (s, n, po[s + 1] - po[s]))
+        keys = [(names[i], names[j]) for i in range(n) for j in range(i, n)]
+        chrom, start, length = loci[s]
+        out.append({"chromosome": chrom, "position": int(start), "length": int(length), "meta": mt[s].copy(),
+                    "expertPredictions": tuple({k: ep[e, po[s] + q] for q, k in enumerate(keys)} for e in range(3))})
+    return out
+
+
+def result_feature_records(res: "BatchResult", alleles_per_site, loci):
+    """feature_records of a whole batch result (device or host)."""
+    return feature_records(res.pair_prob[1:], res.meta, res.pair_off, alleles_per_site, loci)
+
+
 class MoEMergedWrapperB200:
     """Drop-in for ``MoEMergedWrapperAdvanced``: ``network(featureDict, segment)`` for one site."""
 

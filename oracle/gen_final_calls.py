@@ -75,15 +75,20 @@ def tie_sites():
 def main():
     import torch
     sites = sites_from_golden("hybrid_full") + sites_from_golden("hybrid_ensemble2") + sites_from_golden("single_tech") + tie_sites()
-    ref_alleles, items = {}, []
+    ref_alleles, names_per_site, loci = {}, [], []
     for k, (n, experts, meta) in enumerate(sites):
         names = NAMES[:n] if k % 2 == 0 else NAMES[:n][::-1]       # reference allele first; vary the name order
         pos = 1000 + 10 * k
         ref_alleles[pos] = names[0]
-        pairs = [(names[i], names[j]) for i in range(n) for j in range(i, n)]
-        # values are 0-d torch tensors, as in the .features pickles (caller_calling.py:746-754)
-        preds = tuple({pairs[q]: torch.tensor(experts[e, q]) for q in range(len(pairs))} for e in range(3))
-        items.append({"chromosome": "chr1", "position": pos, "length": len(names[0]), "meta": meta, "expertPredictions": preds})
+        names_per_site.append(names)
+        loci.append(("chr1", pos, len(names[0])))
+    # The .features records (caller_calling.py:746-754; values are 0-d torch tensors) are made by the product's own host
+    # function, so the reference's vcfRecords below consumes exactly what a hello_b200 caller would pickle.
+    sys.path.insert(0, ROOT)
+    from hello_b200.model import feature_records
+    pair_off = np.concatenate([[0], np.cumsum([s[1].shape[1] for s in sites])])
+    items = feature_records(np.concatenate([s[1] for s in sites], axis=1), np.stack([s[2] for s in sites]), pair_off,
+                            names_per_site, loci)
     install_stubs(ref_alleles)
     sys.path.insert(0, REF)
     import prepareVcf                                                # the reference

@@ -146,3 +146,40 @@ def test_encoder_host_packing():
         encoder.pack_sites([encoder.SitePileup(["AC"], [[1]], [[(0, 2)]], [0], [0], [1], [False], [0], "AC", 0, 0, 1, {})])
     with pytest.raises(ValueError):
         encoder.pack_sites([encoder.SitePileup(["AC"], [[1, 2]], [[(0, 3)]], [0], [0], [1], [False], [0], "AC", 0, 0, 1, {})])
+
+
+def test_feature_records_match_the_callers_pickle_format():
+    """model.feature_records builds the `.features` list of caller_calling.py:746-754 (what prepareVcf.vcfRecords reads;
+    tests/golden/final_calls.npz was produced by feeding exactly these records to the reference)."""
+    import pickle
+    from hello_b200 import model
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "final_calls.npz"))
+    names_all = [str(x) for x in g["names"]]
+    n_alleles = g["n_alleles"]
+    alleles = [[names_all[i] for i in g["allele_name_idx"][s, :n]] for s, n in enumerate(n_alleles)]
+    pair_off = np.concatenate([[0], np.cumsum(n_alleles * (n_alleles + 1) // 2)])
+    loci = [("chr1", 1000 + 10 * s, len(a[0])) for s, a in enumerate(alleles)]
+    recs = pickle.loads(pickle.dumps(model.feature_records(g["experts"], g["meta"], pair_off, alleles, loci)))
+    assert len(recs) == len(alleles)
+    for s, r in enumerate(recs):
+        assert set(r) == {"chromosome", "position", "length", "meta", "expertPredictions"}
+        assert (r["chromosome"], r["position"], r["length"]) == loci[s]
+        assert isinstance(r["meta"], np.ndarray) and r["meta"].dtype == np.float32 and r["meta"].shape == (3,)
+        np.testing.assert_array_equal(r["meta"], g["meta"][s])
+        assert int(np.argmax(r["meta"])) == int(g["best_expert"][s])
+        n = len(alleles[s])
+        keys = [(alleles[s][i], alleles[s][j]) for i in range(n) for j in range(i, n)]
+        assert len(r["expertPredictions"]) == 3
+        for e, d in enumerate(r["expertPredictions"]):
+            assert list(d.keys()) == keys                                    # itertools.product order, i <= j
+            for q, k in enumerate(keys):
+                assert torch.is_tensor(d[k]) and d[k].dim() == 0 and d[k].dtype == torch.float32
+                assert float(d[k]) == float(g["experts"][e, pair_off[s] + q])
+        # the caller's rule on these records gives the golden calls (sorted((v, k)) picks max value, then greatest key)
+        for e in range(3):
+            top = sorted([(float(v), k) for k, v in r["expertPredictions"][e].items()], reverse=True)[0][1]
+            assert [alleles[s].index(top[0]), alleles[s].index(top[1])] == list(g["call_pair"][s, e])
+    with pytest.raises(ValueError):
+        model.feature_records(g["experts"], g["meta"], pair_off, alleles[:-1], loci)
+    with pytest.raises(ValueError):
+        model.feature_records(g["experts"], g["meta"], pair_off, [a[:1] for a in alleles], loci)

@@ -401,10 +401,14 @@ def test_final_call_records(gpu):
                                           allele_rank=gpu.allele_ranks(names))
         r = net.engine.run(batch)
         pp, meta, off = r.pair_prob.cpu(), r.meta.cpu(), r.pair_off.numpy()
+        # the `.features` records a hello_b200 caller pickles for prepareVcf (caller_calling.py:746-754)
+        recs = gpu.result_feature_records(r, names, [("chr1", 100 + s, len(names[s][0])) for s in range(len(naps))])
         for s, n in enumerate(naps):
             pairs = [(names[s][i], names[s][j]) for i in range(n) for j in range(i, n)]
             preds = [{pairs[q]: pp[1 + e, off[s] + q] for q in range(len(pairs))} for e in range(3)]
-            ref = O.final_calls(preds, meta[s])
+            assert [list(d.items()) for d in recs[s]["expertPredictions"]] == [list(d.items()) for d in preds]
+            assert np.array_equal(recs[s]["meta"], meta[s].numpy())
+            ref = O.final_calls(recs[s]["expertPredictions"], recs[s]["meta"])
             got = gpu.final_calls(r, s, names[s])
             assert got["choice"] == ref["choice"]
             for key in ("expert0", "expert1", "expert2", "best", "mean"):
