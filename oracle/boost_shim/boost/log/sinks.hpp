@@ -1,0 +1,1 @@
+#include <boost/log/common.hpp>

@@ -7,14 +7,19 @@ C++ does (including its switch fall-throughs: a deletion is only drawn when the 
 an insertion colours the base before it with the minimum quality of that base and the inserted bases).
 Only tests/ and tools/bench_encoder.py's cpu_baseline leg may import this file.
 
-Parity pin: the C++ cannot be built here (Boost.Python / numpy C++ bindings, CMake with hard-coded paths), so the
-restatement is pinned against the reference's own Python specification of the encoding,
-``python/test_aligner.py:create_read_encoding`` (:108-183) -- the function the reference's test asserts the C++
-against -- on the reference's two fixture pileups (:300-380) and on seeded random reads
-(tests/golden/encoder.npz, made by oracle/gen_encoder_golden.py).  The specification and the C++ differ at the
-window borders, for insertions into reads of varying quality (the specification takes one quality, the C++ the
-minimum) and for soft clips (the specification has no branch for them, the C++ advances the read pointer); the golden
-cases stay inside the domain where the two agree, so those corners are restated from the C++ only ("unpinned" there).
+Parity pin (two independent ones):
+  * the reference's COMPILED C++: oracle/Makefile builds /root/reference/c++/src/*.cpp where they lie (against
+    oracle/boost_shim, a stand-in for the Boost.Python container types -- Boost is not in this image and the reference's
+    CMake build, with its hard-coded /opt/boost and python3.7m, is not run) into oracle/_ref/libref_encoder.so;
+    tests/golden/encoder_cpp.npz (oracle/gen_encoder_cpp_golden.py) holds its outputs for 26 sites / 432 queries covering
+    clips, indels at the window borders and at the start of a read, insertions into reads of varying quality, N bases,
+    the technology filter and the no-support row, and tests/test_encoder_oracle.py compares fresh random sites live when
+    the library is present.  This restatement is bit-identical on all of them.
+  * the reference's own Python specification of the encoding, ``python/test_aligner.py:create_read_encoding`` (:108-183)
+    -- the function the reference's test asserts the C++ against -- on the reference's two fixture pileups (:300-380)
+    and on seeded random reads (tests/golden/encoder.npz, oracle/gen_encoder_golden.py).  The specification and the C++
+    differ at the window borders, for insertions into reads of varying quality and for soft clips (the specification has
+    no branch for them); those golden cases stay inside the domain where the two agree.
 """
 from __future__ import annotations
 

@@ -43,3 +43,61 @@ def test_oracle_edge_semantics():
     assert not ill[0, 0:3].any() and ill[0, 3, E.READ_BASE] != 0
     # read 1: insertion of 3 bases after position 131 -> feature 6 carries '*' and min(qual[1:5]) = 5
     assert pac[0, 6, E.READ_BASE] == 0 and pac[0, 6, E.READ_QUAL] == E.base_quality_color(5) and pac[0, 6, E.HP] == 240
+
+
+def cpp_golden_cases():
+    """tests/golden/encoder_cpp.npz: whole sites + the outputs of the reference's COMPILED C++ encoder
+    (oracle/gen_encoder_cpp_golden.py, AlleleSearcherLiteFiltered.cpp:1031-1180 built by oracle/Makefile)."""
+    g = np.load(os.path.join(GOLDEN, "encoder_cpp.npz"))
+    sites = []
+    for s in range(int(g["n_sites"])):
+        p = "s%d_" % s
+        reads = [str(r) for r in g[p + "reads"]]
+        qoff = np.concatenate([[0], np.cumsum([len(r) for r in reads])])
+        quals = [[int(x) for x in g[p + "quals"][qoff[i]:qoff[i + 1]]] for i in range(len(reads))]
+        coff = np.concatenate([[0], np.cumsum(g[p + "cig_n"])])
+        cig = [[(int(a), int(b)) for a, b in g[p + "cig"][coff[i]:coff[i + 1]]] for i in range(len(reads))]
+        pr = g[p + "per_read"]
+        soff = np.concatenate([[0], np.cumsum(g[p + "sup_n"])])
+        supports = {str(a): [int(x) for x in g[p + "sup"][soff[i]:soff[i + 1]]] for i, a in enumerate(g[p + "alleles"])}
+        w, a0, a1 = (int(x) for x in g[p + "loc"])
+        sites.append(E.SitePileup(reads, quals, cig, [int(x) for x in pr[0]], [int(x) for x in pr[1]], [int(x) for x in pr[2]],
+                                  [bool(x) for x in pr[3]], [int(x) for x in pr[4]], str(g[p + "ref"]), w, a0, a1, supports))
+    pos = 0
+    for (s, ai, pac, hp, L), rows in zip(g["queries"], g["out_rows"]):
+        n = int(rows) * int(L) * (7 if hp else 6)
+        want = g["out"][pos:pos + n].reshape(int(rows), int(L), 7 if hp else 6)
+        pos += n
+        yield sites[int(s)], list(sites[int(s)].supports)[int(ai)], int(L), bool(pac), bool(hp), want
+    assert pos == g["out"].size
+
+
+def test_oracle_matches_compiled_reference_encoder():
+    """Every corner the Python specification cannot pin (soft / hard clips, indels at the window borders and at the start
+    of a read, insertions into reads of varying quality, N bases, technology filter, no-support row): bit-exact against
+    the reference's own C++."""
+    n = rows = 0
+    for site, allele, L, pac, hp, want in cpp_golden_cases():
+        got = E.compute_features_colored_simple(site, allele, L, pac, hp)
+        assert got.shape == want.shape and np.array_equal(got, want), (allele, L, pac, hp)
+        n += 1
+        rows += want.shape[0]
+    assert n >= 400 and rows >= 800
+
+
+def test_oracle_matches_compiled_reference_encoder_live():
+    """With oracle/_ref/libref_encoder.so present (built by __graft_entry__.build() where /root/reference exists): fresh
+    random sites through both."""
+    import pytest
+    from oracle import ref_encoder as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libref_encoder.so not built (needs /root/reference)")
+    rng = np.random.default_rng(424242)
+    for k in range(60):
+        long_reads = k % 3 == 2
+        site = E.random_site(rng, n_reads=9, long_reads=long_reads, border_cases=True, window_start=500 if k % 2 else 0)
+        for allele in site.supports:
+            for hp in (False, True):
+                a = E.compute_features_colored_simple(site, allele, 150, long_reads, hp)
+                b = R.compute_features_colored_simple(site, allele, 150, long_reads, hp)
+                assert a.shape == b.shape and np.array_equal(a, b), (k, allele, hp)

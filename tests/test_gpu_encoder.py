@@ -33,6 +33,21 @@ def test_encoder_matches_reference_specification(encoder):
     assert n >= 60
 
 
+def test_encoder_matches_compiled_reference_encoder(encoder):
+    """tests/golden/encoder_cpp.npz: outputs of the reference's own compiled C++ computeFeaturesColoredSimple on the
+    corner cases its Python specification cannot express (clips, border indels, varying qualities, N bases)."""
+    from test_encoder_oracle import cpp_golden_cases
+    n, encs = 0, {}
+    for site, allele, L, pac, hp, want in cpp_golden_cases():
+        enc = encs.get(id(site))
+        if enc is None:
+            enc = encs[id(site)] = encoder.SiteEncoderB200(site, DEV)
+        got = enc.computeFeaturesColoredSimple(allele, L, pac, hp)
+        assert got.shape == want.shape and np.array_equal(got, want), (allele, L, pac, hp)
+        n += 1
+    assert n >= 400
+
+
 @pytest.mark.parametrize("long_reads", [False, True])
 def test_encoder_matches_oracle_everywhere(encoder, long_reads):
     """Window borders, clips, skips, 'N' bases, long insertions, varying qualities, both technologies, 6 and 7
