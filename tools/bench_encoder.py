@@ -6,7 +6,8 @@
 One JSON line, same conventions as bench.py: `value` = read rows encoded per second with the packed reads resident in
 HBM; `e2e` = the same with the packed reads coming from pinned host memory every step (H2D inside the timed region,
 an 8-byte checksum read back); `roofline` = achieved algorithmic bytes/s of encode_reads_kernel against the measured
-HBM copy bandwidth; `cpu_baseline` = the oracle port (oracle/encoder_oracle.py, Python loops restating the C++) on a
+HBM copy bandwidth; `cpu_baseline` = the reference's own compiled C++ encoder (oracle/_ref/libref_encoder.so, kind
+"reference") when it was built, else the oracle port (oracle/encoder_oracle.py, Python loops restating the C++), on a
 bounded sample.
 """
 import argparse
@@ -21,16 +22,19 @@ sys.path.insert(0, ROOT)
 
 
 def _cpu_rows(args):
-    seed, n = args
+    seed, n, use_ref = args
     import numpy as np
-    from oracle import encoder_oracle as E
+    from oracle import encoder_oracle as E, ref_encoder as R
+    fn = R.compute_features_colored_simple if use_ref else E.compute_features_colored_simple
     rng = np.random.default_rng(seed)
-    done = 0
+    sites = [E.random_site(rng, n_reads=30, border_cases=False) for _ in range(20)]      # made outside the timed region
+    done, k = 0, 0
     t0 = time.perf_counter()
     while done < n:
-        site = E.random_site(rng, n_reads=30, border_cases=False)
+        site = sites[k % len(sites)]
+        k += 1
         for allele in site.supports:
-            done += E.compute_features_colored_simple(site, allele, 150, False, False).shape[0]
+            done += fn(site, allele, 150, False, False).shape[0]
     return done, time.perf_counter() - t0
 
 
@@ -87,12 +91,16 @@ def main():
     achieved = (in_bytes + out_bytes) / (ms / 1e3) / 1e9
     cpu = None
     if not args.no_cpu_baseline:
+        from oracle import ref_encoder
+        use_ref = ref_encoder.available()
         workers = len(os.sched_getaffinity(0))
         with mp.get_context("fork").Pool(workers) as pool:
-            res = pool.map(_cpu_rows, [(100 + w, 600) for w in range(workers)])
+            res = pool.map(_cpu_rows, [(100 + w, 20000 if use_ref else 600, use_ref) for w in range(workers)])
         rows = sum(r[0] for r in res)
-        cpu = {"value": rows / max(r[1] for r in res), "unit": "rows/s", "cores": workers, "kind": "port",
-               "sample": "%d rows of random 30-read sites, %d worker processes (pure-Python restatement of the C++ loop)" % (rows, workers)}
+        what = ("the reference's compiled computeFeaturesColoredSimple, one AlleleSearcherLiteFiltered built per call as "
+                "the caller does per site" if use_ref else "pure-Python restatement of the C++ loop")
+        cpu = {"value": rows / max(r[1] for r in res), "unit": "rows/s", "cores": workers, "kind": "reference" if use_ref else "port",
+               "sample": "%d rows of random 30-read sites, %d worker processes (%s)" % (rows, workers, what)}
     print(json.dumps({
         "metric": "encoded_read_rows_per_sec", "value": R / (ms / 1e3), "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "dtype": "u8", "data": "synthetic",
