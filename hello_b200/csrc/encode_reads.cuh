@@ -30,7 +30,7 @@ __device__ __forceinline__ uint32_t base_color(uint8_t b) {            // :971-9
 // position marker, hp: the "constant" words, computed once per row -- and what the CIGAR walk decides: read base and
 // base quality.  Low word = tracks 0-3 (read base, ref base, quality, mapq), high word = tracks 4-6.  All window
 // arithmetic is 32-bit and relative to the window start.
-__global__ void __launch_bounds__(WARPS * 32) encode_reads_kernel(const hello_encode_batch b, const Luts lut,
+__global__ void __launch_bounds__(WARPS * 32, 8) encode_reads_kernel(const hello_encode_batch b, const Luts lut,
                                                                    uint8_t* __restrict__ out) {
     __shared__ __align__(16) uint8_t stage[WARPS][MAX_L * 8];
     __shared__ uint8_t s_base[256], s_qual[256];
@@ -49,33 +49,38 @@ __global__ void __launch_bounds__(WARPS * 32) encode_reads_kernel(const hello_en
         const int site = b.d_row_site[row];
         const long long wstart = b.d_window_start[site], a0 = b.d_assembly_start[site], a1 = b.d_assembly_stop[site];
         const long long start = (a0 + a1) / 2 - (long long)(L / 2);
-        const long long ref_len = b.d_ref_off[site + 1] - b.d_ref_off[site];
-        const uint8_t* refw = b.d_reference + b.d_ref_off[site] + (start - wstart);     // reference base of window position f
-        const long long ref_lo = wstart - start, ref_hi = ref_lo + ref_len;             // valid f range of refw
+        const long long ref_off = b.d_ref_off[site], ref_len = b.d_ref_off[site + 1] - ref_off;
+        const uint8_t* refw = b.d_reference + ref_off + (start - wstart);               // reference base of window position f
+        // everything below is window-relative and clamped to +-2^30, so the per-position tests are 32-bit
+        auto clamp30 = [](long long v) { return (int)max(-(1ll << 30), min(1ll << 30, v)); };
+        const int ref_lo = clamp30(wstart - start), ref_hi = clamp30(wstart - start + ref_len);   // valid f range of refw
         // PositionColor (:1007-1015) compares unsigned offsets from windowStart
-        const long long p_lo = a0 >= wstart ? a0 - start : (1ll << 40), p_hi = a1 >= wstart ? a1 - start : (1ll << 40);
-        const uint8_t* bases = b.d_bases + b.d_read_off[rid];
-        const uint8_t* quals = b.d_quals + b.d_read_off[rid];
-        const long long c0 = b.d_cigar_off[rid], c1 = b.d_cigar_off[rid + 1];
+        const int p_lo = a0 >= wstart ? clamp30(a0 - start) : (1 << 30), p_hi = a1 >= wstart ? clamp30(a1 - start) : (1 << 30);
+        const long long r_off = b.d_read_off[rid];
+        const uint8_t* bases = b.d_bases + r_off;
+        const uint8_t* quals = b.d_quals + r_off;
+        const long long c0 = b.d_cigar_off[rid];
+        const int n_ops = (int)(b.d_cigar_off[rid + 1] - c0);
+        const uint32_t* cigar = b.d_cigars + c0;
         const uint32_t mq = lut.map_q[b.d_mapq[rid]];
         const uint32_t sc = b.d_orientation[rid] > 0 ? 70u : 240u;
         const uint32_t hp_raw = C == 7 ? b.d_hp[rid] : 0u;
         const uint32_t hc = hp_raw == 1 ? 120u : (hp_raw == 2 ? 240u : 0u);
+        const uint32_t cst_hi0 = sc | (hc << 16), cst_lo0 = mq << 24;
         uint32_t cst_lo[PER_LANE], cst_hi[PER_LANE];
 #pragma unroll
         for (int k = 0; k < PER_LANE; ++k) {
             const int f = lane + 32 * k;
             const uint32_t rc = (f >= ref_lo && f < ref_hi) ? s_base[__ldg(refw + f)] : 0u;
             const uint32_t pc = (f >= p_lo && f < p_hi) ? 240u : 70u;
-            cst_lo[k] = (rc << 8) | (mq << 24);
-            cst_hi[k] = sc | (pc << 8) | (hc << 16);
+            cst_lo[k] = (rc << 8) | cst_lo0;
+            cst_hi[k] = cst_hi0 | (pc << 8);
         }
         // window-relative reference cursor, clamped far outside the window instead of overflowing
-        const long long rel = b.d_ref_start[rid] - start;
-        int rf = (int)max(-(1ll << 30), min(1ll << 30, rel));
+        int rf = clamp30(b.d_ref_start[rid] - start);
         int rd = 0;
-        for (long long ci = c0; ci < c1; ++ci) {
-            const uint32_t cg = __ldg(b.d_cigars + ci);
+        for (int ci = 0; ci < n_ops; ++ci) {
+            const uint32_t cg = __ldg(cigar + ci);
             const uint32_t op = cg & 15u;
             const int len = (int)(cg >> 4);
             if (op == 0 || op == 7 || op == 8) {                         // M, =, X
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(WARPS * 32) encode_reads_kernel(const hello_en
                     for (int k = 0; k < PER_LANE; ++k) {
                         const int f = lane + 32 * k;
                         const int j = f - rf;
-                        if (f < L && j >= 0 && j < len) {
+                        if (f < L && (unsigned)j < (unsigned)len) {
                             lo[k] = cst_lo[k] | s_base[__ldg(bases + rd + j)] | ((uint32_t)s_qual[__ldg(quals + rd + j)] << 16);
                             hi[k] = cst_hi[k];
                         }
@@ -126,7 +131,23 @@ __global__ void __launch_bounds__(WARPS * 32) encode_reads_kernel(const hello_en
             // H, P, B: no case in the reference's switch
         }
     }
-    // stage the row [L][C] and write it out with coalesced 32-bit words
+    const int row_bytes = L * C;
+    uint8_t* dst = out + row * row_bytes;
+    if (C == 6 && (((uintptr_t)dst) & 1) == 0) {
+        // 6-byte records of consecutive lanes are contiguous: three 16-bit stores per position, each warp instruction
+        // covering a third of a 192-byte span; L2 merges them, nothing is staged.
+        uint16_t* d2 = reinterpret_cast<uint16_t*>(dst) + lane * 3;
+#pragma unroll
+        for (int k = 0; k < PER_LANE; ++k) {
+            if (lane + 32 * k < L) {
+                d2[96 * k] = (uint16_t)lo[k];
+                d2[96 * k + 1] = (uint16_t)(lo[k] >> 16);
+                d2[96 * k + 2] = (uint16_t)hi[k];
+            }
+        }
+        return;
+    }
+    // otherwise stage the row [L][C] in shared memory and write it out with coalesced 32-bit words
     uint8_t* st = stage[warp];
 #pragma unroll
     for (int k = 0; k < PER_LANE; ++k) {
@@ -139,8 +160,6 @@ __global__ void __launch_bounds__(WARPS * 32) encode_reads_kernel(const hello_en
         }
     }
     __syncwarp();
-    const int row_bytes = L * C;
-    uint8_t* dst = out + row * row_bytes;
     if (((row_bytes | (int)((uintptr_t)dst & 3)) & 3) == 0) {
         const uint32_t* s4 = reinterpret_cast<const uint32_t*>(st);
         uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
