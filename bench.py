@@ -234,7 +234,10 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this repo has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = None
     if world > 1:
+        # one process per GPU: stay on the GPU's socket so the pinned buffers of the e2e leg are allocated next to it
+        numa_cpus = shard.bind_rank_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=dev)
 
     cfg_name, cov, desc = WORKLOADS[args.workload]
@@ -337,6 +340,8 @@ def run_ours(args):
                "d2h_bytes_per_step": out.nbytes(), "sites_per_gpu": S_e,
                "api": "MoEEngine.forward_host (pinned host buffers, read rows streamed in %d-site ranges on a copy "
                       "stream while the previous range computes)" % args.e2e_chunk_sites}
+        if numa_cpus is not None:
+            e2e["host_binding"] = "rank 0 runs on %d cores local to its GPU (pinned buffers first-touched there)" % len(numa_cpus)
 
     if rank != 0:
         if world > 1:

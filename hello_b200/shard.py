@@ -117,3 +117,39 @@ def gather_site_results(best_pair: torch.Tensor, best_prob: torch.Tensor, meta: 
         pair_prob=_all_gather_ragged(pair_prob.t().contiguous(), group),
         pair_mix64=_all_gather_ragged(pair_mix64.contiguous(), group),
         logits=_all_gather_ragged(logits.t().contiguous(), group))
+
+
+def parse_cpulist(text: str) -> List[int]:
+    """'0-3,8,10-11' (the kernel's cpulist format) -> [0, 1, 2, 3, 8, 10, 11]."""
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_local_cpus(device_index: int, sysfs: str = "/sys/bus/pci/devices") -> List[int]:
+    """CPU cores on the NUMA node the GPU hangs off (its PCI function's ``local_cpulist``); [] when unknown."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(os.path.join(sysfs, bdf, "local_cpulist")) as f:
+            return parse_cpulist(f.read())
+    except Exception:
+        return []
+
+
+def bind_rank_to_gpu_numa(device_index: int) -> List[int]:
+    """One process per GPU: run this rank -- and, by first touch, place the pinned host buffers it allocates afterwards --
+    on the socket its GPU is attached to, so host<->device copies do not cross the inter-socket link.  Keeps the current
+    affinity when the topology is unknown or the intersection is empty.  Returns the cores now allowed."""
+    import os
+    allowed = set(os.sched_getaffinity(0))
+    local = [c for c in gpu_local_cpus(device_index) if c in allowed]
+    if local and len(local) < len(allowed):
+        os.sched_setaffinity(0, local)
+    return sorted(os.sched_getaffinity(0))
+

@@ -183,3 +183,28 @@ def test_feature_records_match_the_callers_pickle_format():
         model.feature_records(g["experts"], g["meta"], pair_off, alleles[:-1], loci)
     with pytest.raises(ValueError):
         model.feature_records(g["experts"], g["meta"], pair_off, [a[:1] for a in alleles], loci)
+
+
+def test_gpu_numa_binding_helpers(tmp_path, monkeypatch):
+    """shard.bind_rank_to_gpu_numa: cpulist parsing, sysfs lookup by PCI address, and the no-op fallbacks."""
+    import types
+    from hello_b200 import shard
+    assert shard.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert shard.parse_cpulist("") == [] and shard.parse_cpulist("5") == [5]
+    dev = tmp_path / "0000:1b:00.0"
+    dev.mkdir()
+    mine = sorted(os.sched_getaffinity(0))
+    (dev / "local_cpulist").write_text("%d\n" % mine[0])
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda i: props)
+    assert shard.gpu_local_cpus(0, sysfs=str(tmp_path)) == [mine[0]]
+    assert shard.gpu_local_cpus(0, sysfs=str(tmp_path / "missing")) == []
+    real = shard.gpu_local_cpus
+    try:
+        monkeypatch.setattr(shard, "gpu_local_cpus", lambda i: real(i, sysfs=str(tmp_path)))
+        assert shard.bind_rank_to_gpu_numa(0) == ([mine[0]] if len(mine) > 1 else mine)
+        monkeypatch.setattr(shard, "gpu_local_cpus", lambda i: [10 ** 6])          # no overlap with the allowed set
+        before = sorted(os.sched_getaffinity(0))
+        assert shard.bind_rank_to_gpu_numa(0) == before
+    finally:
+        os.sched_setaffinity(0, mine)
