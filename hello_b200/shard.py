@@ -150,6 +150,9 @@ def bind_rank_to_gpu_numa(device_index: int) -> List[int]:
     allowed = set(os.sched_getaffinity(0))
     local = [c for c in gpu_local_cpus(device_index) if c in allowed]
     if local and len(local) < len(allowed):
-        os.sched_setaffinity(0, local)
+        try:
+            os.sched_setaffinity(0, local)
+        except OSError:                   # a cpuset the kernel refuses: keep what we have
+            pass
     return sorted(os.sched_getaffinity(0))
 
