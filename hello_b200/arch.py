@@ -183,6 +183,7 @@ class ModelConfig:
     width: int = 1
     addendum: bool = False               # transfer-learning model: two more residual blocks on top of the read convolvers,
                                          # the compressors and the (single) expert head (architectures/*_addendum.py)
+    addendum_blocks: int = 2             # the shipped addenda have two; other depths run too (fused kernels cover <= 2)
 
     @property
     def hybrid(self) -> bool:
@@ -196,7 +197,7 @@ class ModelConfig:
     def networks(self):
         """name -> layer table, in the reference's registration order (MoEAttention.__init__, :104-115)."""
         nets = {}
-        extra = lambda c: [Res(c, c, 1, False), Res(c, c, 1, False)] if self.addendum else []
+        extra = lambda c: [Res(c, c, 1, False)] * self.addendum_blocks if self.addendum else []
         for t, cin in enumerate(self.read_cin):
             nets["read_convolver%d" % t] = read_convolver(cin, self.width) + extra(64 * self.width)
         for t in range(len(self.read_cin)):

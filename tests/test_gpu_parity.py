@@ -158,6 +158,29 @@ def test_addendum_models_against_the_oracle(gpu, name, precision):
                                atol=TOL_LOGIT[precision])
 
 
+def test_deeper_addendum_runs_fused_prefix_plus_layerwise_tail(gpu):
+    """Three added blocks per sub-network (the fused kernels take two): the third runs layer by layer behind the fused
+    kernel, for feature networks and for the pooled expert head."""
+    import dataclasses
+    cfg = dataclasses.replace(arch.CONFIGS["single_tech_addendum"], name="single_tech_addendum3", addendum_blocks=3)
+    params = weights.init_params(cfg, seed=13)
+    from oracle import hello_oracle as O
+    orc = O.OracleModel(cfg, params)
+    net = gpu.MoEAttentionB200(cfg, params, device=DEV, precision="bf16x3")
+    pl = synth.make_pileups(30, coverage=8, channels=cfg.read_cin, seed=31)
+    tensors, naps, nrpa, ref_seg = pl.forward_args()
+    before = net.engine.launch_count()
+    res = net.forward(tensors, naps, nrpa, ref_seg)
+    # site index, posterior, fill_meta + read convolver (1 + 2 convs + segsum) + compressor (1 + 2) + segsum + xattn (1 + 2 + pooled head)
+    assert net.engine.launch_count() - before == 3 + 4 + 3 + 1 + 4
+    want = orc.forward(tensors, naps, nrpa, ref_seg)
+    np.testing.assert_allclose(res.reshape(-1).numpy(), want.reshape(-1).numpy(), rtol=0, atol=TOL_LOGIT["bf16x3"])
+    reads = pl.reads[0][:40]
+    got = net.engine.run_net("read_convolver0", reads).cpu()
+    ref = orc.nets["read_convolver0"](reads.transpose(1, 2).float()).transpose(1, 2)
+    assert (got - ref).abs().max().item() < TC_LAYER_REL["bf16x3"] * max(1.0, ref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------- fused tcgen05 read convolver
 @pytest.mark.parametrize("precision,name", [("bf16x3", "single_tech"), ("bf16x3", "single_tech_hp"),
                                             ("bf16", "single_tech")])
