@@ -33,6 +33,8 @@ WORKLOADS = {
     "hybrid_no_ensemble_30x": ("hybrid_no_ensemble", 30, "hybrid Illumina+PacBio no_ensemble model"),
     "hybrid_ensemble2_30x": ("hybrid_ensemble2", 30, "hybrid 2-expert gated model"),
     "wgs_ragged_15_60x": ("single_tech", (15, 60), "ragged coverage 15x-60x sweep"),
+    "hybrid_no_ensemble_wide_30x": ("hybrid_no_ensemble_wide", 30, "hybrid no_ensemble model with 2x channels (layer-wise tensor-core kernels)"),
+    "hybrid_no_ensemble_addendum_30x": ("hybrid_no_ensemble_addendum", 30, "hybrid transfer-learning model"),
     "illumina_30x_addendum": ("single_tech_addendum", 30, "Illumina 30x transfer-learning model (two more residual blocks per sub-network)"),
 }
 
