@@ -346,6 +346,7 @@ def run_ours(args):
             e2e["host_binding"] = "rank 0 runs on %d cores local to its GPU (pinned buffers first-touched there)" % len(numa_cpus)
 
     if rank != 0:
+        print("bench.py: rank %d of %d done" % (rank, world), file=sys.stderr, flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -408,17 +409,26 @@ def run_ours(args):
                    "flops_per_step_per_gpu": flops_step},
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    text = json.dumps(line)
+    print(text, flush=True)
+    print("bench.py: rank 0 wrote the result line (%d bytes)" % len(text), file=sys.stderr, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE line, the JSON result: libraries that write to file descriptor 1 behind Python's back
+    # (NCCL prints "NCCL version ..." there when the process group comes up) are sent to stderr instead.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(result_fd, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
