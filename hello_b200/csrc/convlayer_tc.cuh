@@ -84,28 +84,43 @@ __global__ void __launch_bounds__(THREADS, 2) convlayer_tc_kernel(const ConvTcAr
         if (row_ok) { item = m / a.lout; pos0 = (int)(m - item * a.lout) * a.stride - a.pad; }
         const float* xitem = a.x + item * a.sn;
         uint32_t stage = 0, par = 1;
-        for (int s = 0; s < steps; ++s) {
+        // The gather of step s + PF is issued as soon as step s has been stored: PF - 1 steps of MMA time cover the
+        // latency of the global loads (one step is only ~200 tensor-pipe cycles).
+        constexpr int PF = 3;
+        float v[PF][16];
+        auto gather = [&](int s, float (&dst)[16]) {
             const int tap = s / k16, j = s - tap * k16;
             const int pos = pos0 + tap;
-            float v[16];
             if (row_ok && pos >= 0 && pos < a.lin) {
                 const float4* p = reinterpret_cast<const float4*>(xitem + (long long)pos * a.sl + 16 * j);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 t = __ldg(p + q);
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                    dst[4 * q] = t.x; dst[4 * q + 1] = t.y; dst[4 * q + 2] = t.z; dst[4 * q + 3] = t.w;
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = 0.f;
+                for (int q = 0; q < 16; ++q) dst[q] = 0.f;
             }
-            ptx::mbar_wait(bar(BAR_EMPTY + stage), par);
-            uint8_t* dst = s_a + stage * a_stage + (uint32_t)r * 16;
-            tc::store_chunk8<MODE>(dst, A_STAGE / 2, v);                 // channels 0-7: chunk 0 (hi; lo plane 4 KB further)
-            tc::store_chunk8<MODE>(dst + 2048, A_STAGE / 2, v + 8);      // channels 8-15: chunk 1
-            ptx::fence_proxy_async();
-            ptx::mbar_arrive(bar(BAR_AFULL + stage));
-            if (++stage == STAGES) { stage = 0; par ^= 1u; }
+        };
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+            if (u < steps) gather(u, v[u]);
+        for (int s0 = 0; s0 < steps; s0 += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int s = s0 + u;
+                if (s < steps) {
+                    ptx::mbar_wait(bar(BAR_EMPTY + stage), par);
+                    uint8_t* dst = s_a + stage * a_stage + (uint32_t)r * 16;
+                    tc::store_chunk8<MODE>(dst, A_STAGE / 2, v[u]);              // channels 0-7: chunk 0 (hi; lo plane 4 KB further)
+                    tc::store_chunk8<MODE>(dst + 2048, A_STAGE / 2, v[u] + 8);   // channels 8-15: chunk 1
+                    ptx::fence_proxy_async();
+                    ptx::mbar_arrive(bar(BAR_AFULL + stage));
+                    if (s + PF < steps) gather(s + PF, v[u]);
+                    if (++stage == STAGES) { stage = 0; par ^= 1u; }
+                }
+            }
         }
         ptx::mbar_wait(bar(BAR_ACC), 0);
         ptx::tc_fence_after();
