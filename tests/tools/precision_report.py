@@ -2,7 +2,7 @@
 """Error of the three precision modes against the CPU oracle (run on a GPU box): max / mean |dlogit|, max |dP| and the
 number of genotype calls that differ at sites whose reference top-2 margin exceeds 2e-3.
 
-    python tools/precision_report.py [n_sites]
+    python tests/tools/precision_report.py [n_sites]
 """
 import json
 import os
@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from hello_b200 import arch, model, synth, weights          # noqa: E402
 from oracle import hello_oracle as O                         # noqa: E402

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Layer-by-layer check of the fused tcgen05 read convolver against the CPU oracle (run on a GPU box).
 
-    python tools/tc_debug.py [bf16x3|bf16] [n_reads]
+    python tests/tools/tc_debug.py [bf16x3|bf16] [n_reads]
 
 Prints, for each of the 17 layer phases, the max abs error of the kernel's post-activation values against the
 oracle's fp32 values of the same layer, plus the error of the final [R,36,64] features.
@@ -11,7 +11,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from hello_b200 import arch, model, synth, weights          # noqa: E402
