@@ -718,6 +718,14 @@ static int forward_impl(hello_moe* h, const hello_batch* in, const hello_result*
         h->err = "bad input_layout"; return HELLO_ERR_ARG;
     }
     if (cfg.meta_kind == HELLO_META_REF && !in->d_ref_onehot) { h->err = "reference segment required"; return HELLO_ERR_ARG; }
+    // reduceSlots (python/MixtureOfExpertsAdvanced.py:23-34) indexes cumsum(slots) - 1: an empty slot silently reads the
+    // previous allele's row in the reference; here it is an error (the caller supplies one all-zero row instead,
+    // AlleleSearcherLiteFiltered.cpp:1037-1043)
+    for (int t = 0; t < cfg.n_tech; ++t) {
+        const int32_t* off = in->h_allele_read_off[t];
+        for (long long al = in->h_site_allele_off[sb]; al < in->h_site_allele_off[se]; ++al)
+            if (off[al + 1] <= off[al]) { h->err = "every allele needs at least one read row per technology"; return HELLO_ERR_ARG; }
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }

@@ -732,6 +732,12 @@ def test_c_abi_status_codes(gpu):
         with pytest.raises(_lib.HelloMoEError) as ei:
             eng.run(batch, workspace=tiny)
         assert "(-4)" in str(ei.value) or "workspace" in str(ei.value).lower()    # HELLO_ERR_WORKSPACE
+        aro = pl.allele_read_off[0].clone()
+        aro[3] = aro[2]                                                           # an allele without rows
+        empty = gpu.DeviceBatch.from_host(pl.reads, _lib.LAYOUT_RLC, (aro,), pl.site_allele_off, None, DEV)
+        with pytest.raises(_lib.HelloMoEError) as ei:
+            eng.run(empty)
+        assert "(-1)" in str(ei.value) and "at least one read row" in str(ei.value)   # HELLO_ERR_ARG
         again = eng.run(batch)                                                    # the handle is still good
         assert torch.equal(good.logits, again.logits) and torch.equal(good.best_pair, again.best_pair)
     finally:
