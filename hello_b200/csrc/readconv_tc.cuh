@@ -83,12 +83,17 @@ constexpr uint32_t OFF_ACT = 0;
 constexpr uint32_t OFF_W = NG * ACT_BYTES;
 constexpr uint32_t OFF_BIAS = OFF_W + 2 * WSLOT_BYTES;
 constexpr uint32_t OFF_BAR = OFF_BIAS;                 // (the biases live in the kernel parameters)
-constexpr uint32_t N_BARS = 4 + 3 * NG;           // w_full[2], w_empty[2], act_ready[NG], acc_full[NG], token[NG]
+constexpr uint32_t N_BARS = 4 + 5 * NG;           // w_full[2], w_empty[2], act_ready / acc_full / token / stage_full / stage_free [NG]
 constexpr uint32_t OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr uint32_t OFF_STATE = (OFF_TMEM + 16 + 15) & ~15u;   // work range of this CTA + running state of the fused allele sum
 constexpr uint32_t OFF_SUM = OFF_STATE + 64;           // fp32 [36][64] running sum of the current allele
-constexpr uint32_t SMEM_BYTES = OFF_SUM + LOUT * COUT * 4;
-static_assert(SMEM_BYTES <= 232448 && OFF_SUM % 16 == 0, "shared memory budget");
+// Raw pileup bytes of each group's NEXT work item, copied by the producer thread (cp.async.bulk) while the current item
+// computes: the item's first operand is then built from shared memory.  (Built from global memory it took ~6k cycles per
+// item -- byte loads queueing behind the epilogues' shared-memory traffic -- with the tensor pipe idle: 8 % of the kernel.)
+constexpr uint32_t STG_BYTES = 3712;                   // >= 15 + G * LIN * 8 rounded up to 16, multiple of 128
+constexpr uint32_t OFF_STG = (OFF_SUM + LOUT * COUT * 4 + 127) & ~127u;
+constexpr uint32_t SMEM_BYTES = OFF_STG + NG * STG_BYTES;
+static_assert(SMEM_BYTES <= 232448 && OFF_SUM % 16 == 0 && STG_BYTES >= 16 + G * LIN * 8, "shared memory budget");
 static_assert(2 * A1_CH * 2 <= XCHG_OFF && 8 * A2_ARR <= XCHG_OFF && 8 * S2_CH <= XCHG_OFF &&
               16 * E3_ARR <= XCHG_OFF && 16 * S3_CH <= XCHG_OFF && 2 * X_STRIDE <= XCHG_OFF, "activation layouts");
 static_assert(T1 * 128 >= ROWS1 && T2 * 128 >= ROWS2 && T3 * 128 >= ROWS3, "tiles cover the packed rows");
@@ -145,27 +150,67 @@ __device__ __forceinline__ void store_chunk8(uint8_t* p, uint32_t lo_delta, cons
     }
 }
 
-// uint8 pileup rows of one group -> layer-1 operand (two row-shifted copies, bf16, channels padded to 8)
+// Which bytes the producer stages for the group whose reads start at r0: the 16-byte aligned superset of its rows.
+// `ok` is false when that superset would reach outside this launch's read buffer (first / last rows of an unaligned
+// buffer); the group then builds its operand from global memory as before.  Producer and consumers call this with the
+// same arguments, so they agree.
+struct StageDesc { const uint8_t* src; uint32_t off, bytes; bool ok; };
+__device__ __forceinline__ StageDesc stage_desc(const uint8_t* reads, long long n_reads_total, int C, long long r0, int n) {
+    const long long rb = (long long)LIN * C;
+    const uint8_t* p = reads + r0 * rb;
+    StageDesc d;
+    d.src = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p) & ~uintptr_t(15));
+    d.off = (uint32_t)(p - d.src);
+    d.bytes = (d.off + (uint32_t)(n * rb) + 15u) & ~15u;
+    d.ok = n > 0 && d.src >= reads && d.src + d.bytes <= reads + n_reads_total * rb;
+    return d;
+}
+
+// uint8 pileup rows of one group -> layer-1 operand (two row-shifted copies, bf16, channels padded to 8).
+// STAGED: `reads` + r0 rows is the group's staging buffer in shared memory instead of global memory.
+template <bool STAGED>
 __device__ __forceinline__ void load_input(uint8_t* act, const uint8_t* __restrict__ reads, long long r0, int n_reads,
-                                           int C, int layout, int tid) {
-    for (int m = tid; m < ROWS1 + 8; m += EW * 32) {
+                                           int C, int layout, int tid, long long* tr = nullptr) {
+    // All global loads of the thread's rows are issued before the first one is used: one trip to L2 per work item
+    // instead of one per 128 rows (the item cannot start before its operand is written, so this latency is exposed).
+    constexpr int IT = (ROWS1 + 8 + EW * 32 - 1) / (EW * 32);
+    uint32_t raw[IT][8];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int m = tid + it * (EW * 32);
         const int i = m / P1, p = m - i * P1;
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (i < n_reads && p < LIN) {
-            const uint8_t* src = reads + (r0 + i) * (long long)(LIN * C);
-            uint32_t b[8];
+        const bool ok = m < ROWS1 + 8 && i < n_reads && p < LIN;
+        const uint8_t* src = reads + (r0 + (ok ? i : 0)) * (long long)(LIN * C);
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-                uint32_t x = 0u;
-                if (ch < C) x = layout == HELLO_LAYOUT_RLC ? __ldg(src + p * C + ch) : __ldg(src + ch * LIN + p);
-                b[ch] = __float_as_uint((float)x) >> 16;          // 0..255 are exact in bf16
+        for (int ch = 0; ch < 8; ++ch) {
+            uint32_t x = 0u;
+            if (ok && ch < C) {
+                const uint8_t* q = layout == HELLO_LAYOUT_RLC ? src + p * C + ch : src + ch * LIN + p;
+                x = STAGED ? *q : __ldg(q);
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) w[q] = b[2 * q] | (b[2 * q + 1] << 16);
+            raw[it][ch] = x;
         }
-        const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(act + (uint32_t)m * 16) = v;
-        if (m >= 1) *reinterpret_cast<uint4*>(act + X_STRIDE + (uint32_t)(m - 1) * 16) = v;
+    }
+    if (tr && tid == 0) {                       // debug timeline: when the loads have landed
+        uint32_t sum = 0u;
+#pragma unroll
+        for (int it = 0; it < IT; ++it)
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) sum += raw[it][ch];
+        tr[N_PHASES * 8 + 6] = clock64() + (sum == 0xffffffffu ? 1 : 0);
+    }
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const int m = tid + it * (EW * 32);
+        if (m < ROWS1 + 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)                               // 0..255 are exact in bf16
+                w[q] = (__float_as_uint((float)raw[it][2 * q]) >> 16) | (__float_as_uint((float)raw[it][2 * q + 1]) & 0xffff0000u);
+            const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(act + (uint32_t)m * 16) = v;
+            if (m >= 1) *reinterpret_cast<uint4*>(act + X_STRIDE + (uint32_t)(m - 1) * 16) = v;
+        }
     }
     if (tid == 0) *reinterpret_cast<uint4*>(act + X_STRIDE + (uint32_t)(ROWS1 + 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
 }
@@ -515,7 +560,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
     const uint32_t bar0 = ptx::smem_u32(smem + OFF_BAR);
     // barriers: 0,1 w_full[slot]  2,3 w_empty[slot]  4.. act_ready[group]  4+NG.. acc_full[group]  4+2NG.. token[group]
     auto bar = [&](int k) { return bar0 + 8u * k; };
-    constexpr int BAR_ACT = 4, BAR_ACC = 4 + NG, BAR_TOK = 4 + 2 * NG;
+    constexpr int BAR_ACT = 4, BAR_ACC = 4 + NG, BAR_TOK = 4 + 2 * NG, BAR_SFULL = 4 + 3 * NG, BAR_SFREE = 4 + 4 * NG;
     constexpr int W_EPI = NG * EW;                                             // epilogue warps
     volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
@@ -524,6 +569,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         ptx::mbar_init(bar(2), NG); ptx::mbar_init(bar(3), NG);        // released by every group's issuer
         for (int g = 0; g < NG; ++g) {
             ptx::mbar_init(bar(BAR_ACT + g), EW * 32); ptx::mbar_init(bar(BAR_ACC + g), 1); ptx::mbar_init(bar(BAR_TOK + g), 1);
+            ptx::mbar_init(bar(BAR_SFULL + g), 1); ptx::mbar_init(bar(BAR_SFREE + g), EW * 32);
         }
         ptx::fence_mbar_init();
         ptx::mbar_arrive(bar(BAR_TOK));                                // group 0 issues first
@@ -585,7 +631,7 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         const int tid = threadIdx.x - g * (EW * 32);
         uint8_t* act = smem + OFF_ACT + g * ACT_BYTES;
         const uint32_t tl = tmem_base + ((uint32_t)wrow << 16) + g * GRP_COLS;
-        uint32_t acc_n = 0;
+        uint32_t acc_n = 0, stg_n = 0;
         float rr[32];                                  // first half of this row's fp32 residual stream
 #pragma unroll
         for (int c = 0; c < 32; ++c) rr[c] = 0.f;
@@ -593,12 +639,25 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
             const long long r0 = R0 + ((long long)item * NG + g) * G;
             const int n = (int)max(0LL, min((long long)G, R - r0));
             if (n <= 0) continue;
-            load_input(act, prm.reads, r0, n, prm.channels, prm.layout, tid);
+            long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
+            // item-level stamps live in the first spare phase slot: {operand load start, end, after the arrive;
+            // issuer: weights landed, operand seen, token received} for phase 0
+            if (tr && tid == 0) tr[N_PHASES * 8 + 0] = clock64();
+            const StageDesc sd = stage_desc(prm.reads, prm.n_reads, prm.channels, r0, n);
+            if (sd.ok) {
+                ptx::mbar_wait(bar(BAR_SFULL + g), stg_n & 1u);            // the producer staged this item's rows
+                ++stg_n;
+                load_input<true>(act, smem + OFF_STG + g * STG_BYTES + sd.off, 0, n, prm.channels, prm.layout, tid, tr);
+                ptx::mbar_arrive(bar(BAR_SFREE + g));                       // staging may take the next item
+            } else {
+                load_input<false>(act, prm.reads, r0, n, prm.channels, prm.layout, tid, tr);
+            }
+            if (tr && tid == 0) tr[N_PHASES * 8 + 1] = clock64();
             ptx::tc_fence_before();
             ptx::fence_proxy_async();
             ptx::mbar_arrive(bar(BAR_ACT + g));
+            if (tr && tid == 0) tr[N_PHASES * 8 + 2] = clock64();
             float* gout = prm.out ? prm.out + r0 * (long long)(LOUT * COUT) : nullptr;
-            long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
 #pragma unroll 1
             for (int ph = 0; ph < n_ph; ++ph) {
                 ptx::mbar_wait(bar(BAR_ACC + g), acc_n & 1);
@@ -672,16 +731,19 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                 // Every issuer waits for the slot (even one whose group is empty in this item): the slot is released
                 // only when all have passed it, which keeps them in lockstep with the producer.
                 ptx::mbar_wait(bar(slot), (w_n >> 1) & 1u);              // this layer's weights have landed
+                if (tr && ph == 0 && lane == 0) tr[N_PHASES * 8 + 3] = clock64();
                 if (n > 0) {
                     ptx::mbar_wait(bar(BAR_ACT + g), ar_n & 1u);         // this group's operand is written
                     ++ar_n;
                 }
+                if (tr && ph == 0 && lane == 0) tr[N_PHASES * 8 + 4] = clock64();
                 // The groups take turns on the tensor pipe (token passed round-robin): one group's layer executes
                 // as a block and its epilogue then overlaps the other group's MMAs.  Without the turn order the
                 // issue streams interleave in the pipe's FIFO, all accumulators complete together and all
                 // epilogues run together with the tensor pipe idle.
                 ptx::mbar_wait(bar(BAR_TOK + g), tok_n & 1u);
                 ++tok_n;
+                if (tr && ph == 0 && lane == 0) tr[N_PHASES * 8 + 5] = clock64();
                 if (n > 0) {
                     ptx::tc_fence_after();
                     if (tr && lane == 0) tr[ph * 8 + 0] = clock64();
@@ -707,6 +769,23 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         if (lane == 0) {
             uint32_t w_n = 0;
             const uint32_t w0 = ptx::smem_u32(smem + OFF_W);
+            uint32_t stg_n[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) stg_n[g] = 0;
+            auto stage_item = [&](int item) {                      // raw rows of work item `item` -> the groups' staging buffers
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const long long r0 = R0 + ((long long)item * NG + g) * G;
+                    const int n = (int)max(0LL, min((long long)G, R - r0));
+                    const StageDesc sd = stage_desc(prm.reads, prm.n_reads, prm.channels, r0, n);
+                    if (!sd.ok) continue;
+                    if (stg_n[g] > 0) ptx::mbar_wait(bar(BAR_SFREE + g), (stg_n[g] - 1) & 1u);   // previous rows consumed
+                    ++stg_n[g];
+                    ptx::mbar_expect_tx(bar(BAR_SFULL + g), sd.bytes);
+                    ptx::bulk_g2s(ptx::smem_u32(smem + OFF_STG + g * STG_BYTES), sd.src, sd.bytes, bar(BAR_SFULL + g));
+                }
+            };
+            if (n_items_cta > 0) stage_item(0);
             for (int item = 0; item < n_items_cta; ++item) {
                 {   // pull the next work item's pileup rows into L2 while this one computes
                     const long long nr0 = R0 + (long long)(item + 1) * (NG * G);
@@ -727,6 +806,8 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                     for (uint32_t o = 0; o < bytes; o += 8192u)
                         ptx::bulk_g2s(w0 + slot * WSLOT_BYTES + o, src + o, min(8192u, bytes - o), bar(slot));
                     ++w_n;
+                    // by now every group has built this item's first operand: its staging buffer takes the next item
+                    if (ph == 2 && item + 1 < n_items_cta) stage_item(item + 1);
                 }
             }
         }

@@ -59,3 +59,17 @@ if __name__ == "__main__":
     for gi in range(NG):
         print(" g%d " % gi + " ".join("%d/%d/%d" % (int(t[i, gi, ph, 0]) - base, int(t[i, gi, ph, 2]) - base,
                                                      int(t[i, gi, ph, 3]) - base) for ph in range(NPH)))
+    # item boundary: last epilogue of item i (incl. the allele sum) -> first issue of item i+1, per group
+    gap = (t[3:items, :, 0, 0] - t[2:items - 1, :, NPH - 1, 3]).float()
+    print("item boundary, epilogue end of the last phase -> first MMA issue of the next item (cycles): mean %.0f, per group %s"
+          % (gap.mean().item(), [round(x) for x in gap.mean(0).tolist()]))
+    idle = (t[3:items, :, 0, 0].min(1).values - t[2:items - 1, :, NPH - 1, 1].max(1).values).float()
+    print("tensor pipe: last MMA issue of item i -> first MMA issue of item i+1 (cycles): mean %.0f" % idle.mean().item())
+    # where the boundary goes (spare phase slot NPH): times relative to the previous item's last epilogue end
+    prev_end = t[2:items - 1, :, NPH - 1, 3]
+    names = ["operand load start", "pileup bytes in registers (thread 0)", "operand stored", "operand arrive", "issuer: weights landed",
+             "issuer: operand seen", "issuer: token received", "first MMA issue"]
+    vals = [t[3:items, :, NPH, k] for k in (0, 6, 1, 2, 3, 4, 5)] + [t[3:items, :, 0, 0]]
+    for nm, v in zip(names, vals):
+        print("  %-32s +%6.0f" % (nm, (v - prev_end).float().mean().item()))
+
