@@ -222,6 +222,29 @@ def test_readconv_tc_ragged_counts_and_layouts(gpu, n_reads):
     assert (a - ref).abs().max().item() < TC_LAYER_REL["bf16x3"] * scale
 
 
+@pytest.mark.parametrize("name", ["single_tech", "single_tech_hp"])
+def test_readconv_tc_unaligned_read_buffers(gpu, name):
+    """The kernel stages each work item's rows with 16-byte aligned bulk copies; groups whose aligned superset would leave
+    the launch's buffer (start / end of an unaligned buffer) take the global-load path.  Any base alignment, any count,
+    both layouts: bit-identical to the same rows in a freshly allocated (aligned) tensor."""
+    from hello_b200 import _lib
+    cfg = arch.CONFIGS[name]
+    pl = synth.make_pileups(60, coverage=9, channels=cfg.read_cin, seed=77)
+    big = pl.reads[0].to(DEV)
+    eng = net_for(gpu, cfg, "bf16x3").engine
+    for k, n in ((1, 40), (2, 9), (3, 10), (5, 1), (7, 2), (4, 200), (9, big.shape[0] - 9)):
+        view = big[k:k + n]
+        assert view.is_contiguous()
+        a, _ = eng.readconv_debug(view, -1, _lib.LAYOUT_RLC)
+        b, _ = eng.readconv_debug(view.clone(), -1, _lib.LAYOUT_RLC)
+        assert torch.equal(a, b), (k, n)
+    rcl = big.transpose(1, 2).contiguous()
+    for k, n in ((1, 13), (3, 100)):
+        a, _ = eng.readconv_debug(rcl[k:k + n], -1, _lib.LAYOUT_RCL)
+        b, _ = eng.readconv_debug(big[k:k + n].clone(), -1, _lib.LAYOUT_RLC)
+        assert torch.equal(a, b), (k, n)
+
+
 def test_readconv_tc_is_deterministic(gpu):
     cfg = arch.CONFIGS["single_tech"]
     pl = synth.make_pileups(200, coverage=10, channels=cfg.read_cin, seed=8)
