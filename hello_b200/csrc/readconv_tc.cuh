@@ -166,21 +166,22 @@ __device__ __forceinline__ StageDesc stage_desc(const uint8_t* reads, long long 
     return d;
 }
 
-// uint8 pileup rows of one group -> layer-1 operand (two row-shifted copies, bf16, channels padded to 8).
+// uint8 pileup rows of one group -> layer-1 operand (two row-shifted copies, bf16, channels padded to 8), in two steps so
+// that the bytes of the NEXT item can be fetched into registers before the current item's output is summed (the fetch then
+// overlaps the wait for this group's turn in the allele sum), and stored once the activation buffer is free.
+constexpr int IN_IT = (ROWS1 + 8 + EW * 32 - 1) / (EW * 32);      // rows per thread
 // STAGED: `reads` + r0 rows is the group's staging buffer in shared memory instead of global memory.
 template <bool STAGED>
-__device__ __forceinline__ void load_input(uint8_t* act, const uint8_t* __restrict__ reads, long long r0, int n_reads,
-                                           int C, int layout, int tid, long long* tr = nullptr) {
-    // All global loads of the thread's rows are issued before the first one is used: one trip to L2 per work item
-    // instead of one per 128 rows (the item cannot start before its operand is written, so this latency is exposed).
-    constexpr int IT = (ROWS1 + 8 + EW * 32 - 1) / (EW * 32);
-    uint32_t raw[IT][8];
+__device__ __forceinline__ void fetch_rows(uint32_t (&raw)[IN_IT][2], const uint8_t* __restrict__ reads, long long r0,
+                                           int n_reads, int C, int layout, int tid) {
+    // all loads of the thread's rows are issued before the first one is used
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
+    for (int it = 0; it < IN_IT; ++it) {
         const int m = tid + it * (EW * 32);
         const int i = m / P1, p = m - i * P1;
         const bool ok = m < ROWS1 + 8 && i < n_reads && p < LIN;
         const uint8_t* src = reads + (r0 + (ok ? i : 0)) * (long long)(LIN * C);
+        uint32_t b[8];
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
             uint32_t x = 0u;
@@ -188,25 +189,24 @@ __device__ __forceinline__ void load_input(uint8_t* act, const uint8_t* __restri
                 const uint8_t* q = layout == HELLO_LAYOUT_RLC ? src + p * C + ch : src + ch * LIN + p;
                 x = STAGED ? *q : __ldg(q);
             }
-            raw[it][ch] = x;
+            b[ch] = x;
         }
+        raw[it][0] = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);     // kept packed: 2 registers per row
+        raw[it][1] = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
     }
-    if (tr && tid == 0) {                       // debug timeline: when the loads have landed
-        uint32_t sum = 0u;
+}
+
+__device__ __forceinline__ void store_rows(uint8_t* act, const uint32_t (&raw)[IN_IT][2], int tid) {
 #pragma unroll
-        for (int it = 0; it < IT; ++it)
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) sum += raw[it][ch];
-        tr[N_PHASES * 8 + 6] = clock64() + (sum == 0xffffffffu ? 1 : 0);
-    }
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
+    for (int it = 0; it < IN_IT; ++it) {
         const int m = tid + it * (EW * 32);
         if (m < ROWS1 + 8) {
             uint32_t w[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q)                               // 0..255 are exact in bf16
-                w[q] = (__float_as_uint((float)raw[it][2 * q]) >> 16) | (__float_as_uint((float)raw[it][2 * q + 1]) & 0xffff0000u);
+            for (int q = 0; q < 4; ++q) {                             // 0..255 are exact in bf16
+                const uint32_t two = raw[it][q >> 1] >> (16 * (q & 1));
+                w[q] = (__float_as_uint((float)(two & 0xffu)) >> 16) | (__float_as_uint((float)((two >> 8) & 0xffu)) & 0xffff0000u);
+            }
             const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
             *reinterpret_cast<uint4*>(act + (uint32_t)m * 16) = v;
             if (m >= 1) *reinterpret_cast<uint4*>(act + X_STRIDE + (uint32_t)(m - 1) * 16) = v;
@@ -635,23 +635,32 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
         float rr[32];                                  // first half of this row's fp32 residual stream
 #pragma unroll
         for (int c = 0; c < 32; ++c) rr[c] = 0.f;
+        uint32_t raw[IN_IT][2];                        // pileup bytes of the item about to start (8 per row, packed)
+        auto fetch_item = [&](int item) {              // item's rows -> `raw` (from the staging buffer when it was staged)
+            const long long r0 = R0 + ((long long)item * NG + g) * G;
+            const int n = (int)max(0LL, min((long long)G, R - r0));
+            if (n <= 0) return;
+            const StageDesc sd = stage_desc(prm.reads, prm.n_reads, prm.channels, r0, n);
+            if (sd.ok) {
+                ptx::mbar_wait(bar(BAR_SFULL + g), stg_n & 1u);            // the producer staged this item's rows
+                ++stg_n;
+                fetch_rows<true>(raw, smem + OFF_STG + g * STG_BYTES + sd.off, 0, n, prm.channels, prm.layout, tid);
+                ptx::mbar_arrive(bar(BAR_SFREE + g));                       // staging may take the next item (the arrive
+                                                                            // is ordered after the loads it follows)
+            } else {
+                fetch_rows<false>(raw, prm.reads, r0, n, prm.channels, prm.layout, tid);
+            }
+        };
+        if (n_items_cta > 0) fetch_item(0);
         for (int item = 0; item < n_items_cta; ++item) {
             const long long r0 = R0 + ((long long)item * NG + g) * G;
             const int n = (int)max(0LL, min((long long)G, R - r0));
             if (n <= 0) continue;
             long long* tr = DBG ? trace_slot(prm, item, g) : nullptr;
-            // item-level stamps live in the first spare phase slot: {operand load start, end, after the arrive;
+            // item-level stamps live in the first spare phase slot: {operand store start, end, after the arrive;
             // issuer: weights landed, operand seen, token received} for phase 0
             if (tr && tid == 0) tr[N_PHASES * 8 + 0] = clock64();
-            const StageDesc sd = stage_desc(prm.reads, prm.n_reads, prm.channels, r0, n);
-            if (sd.ok) {
-                ptx::mbar_wait(bar(BAR_SFULL + g), stg_n & 1u);            // the producer staged this item's rows
-                ++stg_n;
-                load_input<true>(act, smem + OFF_STG + g * STG_BYTES + sd.off, 0, n, prm.channels, prm.layout, tid, tr);
-                ptx::mbar_arrive(bar(BAR_SFREE + g));                       // staging may take the next item
-            } else {
-                load_input<false>(act, prm.reads, r0, n, prm.channels, prm.layout, tid, tr);
-            }
+            store_rows(act, raw, tid);
             if (tr && tid == 0) tr[N_PHASES * 8 + 1] = clock64();
             ptx::tc_fence_before();
             ptx::fence_proxy_async();
@@ -701,6 +710,8 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                     else {
                         epi_conv<MODE, true, 64, T3, P3, LV4, true, false, false, false, OUT_GLOBAL, 1>(
                             prm, act, tl, b, 0, n, 0, 0, gout, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                        // the next item's bytes travel to registers while this group waits for its turn in the sum
+                        if (item + 1 < n_items_cta) fetch_item(item + 1);
                         if (prm.allele_out) accumulate_out(smem, act, prm, r0, n, item * NG + g, g, tid);
                         else copy_out(act, gout, n, g, tid);
                     }

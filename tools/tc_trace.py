@@ -67,9 +67,9 @@ if __name__ == "__main__":
     print("tensor pipe: last MMA issue of item i -> first MMA issue of item i+1 (cycles): mean %.0f" % idle.mean().item())
     # where the boundary goes (spare phase slot NPH): times relative to the previous item's last epilogue end
     prev_end = t[2:items - 1, :, NPH - 1, 3]
-    names = ["operand load start", "pileup bytes in registers (thread 0)", "operand stored", "operand arrive", "issuer: weights landed",
+    names = ["operand store start", "operand stored", "operand arrive", "issuer: weights landed",
              "issuer: operand seen", "issuer: token received", "first MMA issue"]
-    vals = [t[3:items, :, NPH, k] for k in (0, 6, 1, 2, 3, 4, 5)] + [t[3:items, :, 0, 0]]
+    vals = [t[3:items, :, NPH, k] for k in (0, 1, 2, 3, 4, 5)] + [t[3:items, :, 0, 0]]
     for nm, v in zip(names, vals):
         print("  %-32s +%6.0f" % (nm, (v - prev_end).float().mean().item()))
 
