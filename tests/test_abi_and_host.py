@@ -214,3 +214,22 @@ def test_gpu_numa_binding_helpers(tmp_path, monkeypatch):
         assert shard.bind_rank_to_gpu_numa(0) == before
     finally:
         os.sched_setaffinity(0, mine)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the driver's reference arm, CPU only): stdout is exactly one JSON line with the contract's
+    keys; anything else a library writes to file descriptor 1 goes to stderr."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sites", "32", "--cpu-workers", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "candidate_sites_per_sec" and d["unit"] == "sites/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2
+    assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("illumina_30x")
