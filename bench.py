@@ -4,12 +4,12 @@ allele/site heads -> genotype posteriors + argmax), BASELINE.json config 2 ("Ill
 sites, 1 B200") by default.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+    python bench.py --impl reference --steps K --warmup W    # the reference's own modules on the host CPU cores
 
 One JSON line on stdout (rank 0).  `value` = sites/s with inputs resident in HBM; `e2e` = the same job through
 MoEEngine.forward_host with pinned HOST buffers (H2D of the pileups and D2H of the per-site results inside the
 timed region); `roofline` = the read-convolver stage (dominant kernel) timed with CUDA events by the library;
-`cpu_baseline` = the oracle port of the reference forward on a bounded sample of the same workload.
+`cpu_baseline` = the reference's own per-site call (oracle/_ref/python) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -59,12 +59,61 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sites", type=int, default=0, help="sites per CPU step (0 = 128 per worker)")
     ap.add_argument("--cpu-workers", type=int, default=0)
+    ap.add_argument("--cpu-port", action="store_true", help="CPU arm: time the oracle port instead of the reference modules")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference forward on the host cores
+# reference arm / cpu baseline: the reference's own per-site call on the host cores
+#   kind "reference": oracle/_ref/python (the reference's unmodified MixtureOfExpertsAdvanced / NNTools / architectures,
+#                     copied there by oracle/Makefile) -- MoEMergedWrapperAdvanced(featureDict, segment), one site per call,
+#                     under no_grad, one torch thread per worker process: python/caller_calling.py:39,651-652, call.py:26,30
+#   kind "port":      labelled fallback when oracle/_ref/python is missing -- oracle/hello_oracle.py in 16-site calls
 _W = {}
+
+
+def _ref_worker_init(cfg_name):
+    import torch
+    torch.set_num_threads(1)                      # python/caller_calling.py:39
+    from hello_b200 import arch, weights
+    from oracle import ref_model
+    cfg = arch.CONFIGS[cfg_name]
+    _W["net"] = ref_model.build_wrapper(cfg_name, weights.init_params(cfg, seed=13), provide_predictions=True)
+
+
+def _ref_worker_run(task):
+    """scoreSite (python/caller_calling.py:612-654): uint8 arrays -> torch.Tensor floats -> network(featureDict, segment)."""
+    import torch
+    net = _W["net"]
+    done = 0
+    for alleles, seg in task:
+        fd = {name: (torch.Tensor(t0), torch.Tensor(t1) if t1 is not None else None) for name, t0, t1 in alleles}
+        with torch.no_grad():
+            out = net(fd, seg)
+        best = sorted([(v, k) for k, v in out[0].items()], reverse=True)[0]        # caller_calling.py:702-705
+        done += best is not None
+    return done
+
+
+def _ref_tasks(pl, cfg, sites_per_task):
+    tasks, cur = [], []
+    sao = pl.site_allele_off
+    for s in range(pl.n_sites):
+        a0, a1 = int(sao[s]), int(sao[s + 1])
+        alleles = []
+        for k, a in enumerate(range(a0, a1)):
+            parts = []
+            for t in range(len(cfg.read_cin)):
+                r0, r1 = int(pl.allele_read_off[t][a]), int(pl.allele_read_off[t][a + 1])
+                parts.append(pl.reads[t][r0:r1].numpy())
+            alleles.append(("ACGT"[k % 4] * (1 + k // 4), parts[0], parts[1] if len(parts) > 1 else None))
+        cur.append((alleles, pl.ref_onehot[s:s + 1].clone()))
+        if len(cur) == sites_per_task:
+            tasks.append(cur)
+            cur = []
+    if cur:
+        tasks.append(cur)
+    return tasks
 
 
 def _cpu_worker_init(cfg_name):
@@ -108,23 +157,33 @@ def _cpu_tasks(pl, cfg, batch_sites):
 
 
 def run_reference(args):
-    """Times the reference algorithm (oracle port: same torch-CPU ops, same per-worker threading model as
-    python/call.py's Pool of single-threaded callers) on `cpu_sites` sites per step."""
+    """Times the reference's implementation of the path on the host cores: its own modules, its own per-site call and its
+    own threading model (a pool of single-threaded worker processes, python/call.py:111,215-221), on `cpu_sites` sites per
+    step.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
     from hello_b200 import arch, synth
+    from oracle import ref_model
     cfg_name, cov, desc = WORKLOADS[args.workload]
     cfg = arch.CONFIGS[cfg_name]
     workers = args.cpu_workers or len(os.sched_getaffinity(0))
-    n_sites = args.cpu_sites or 128 * workers
+    kind = "reference" if (ref_model.available() and not args.cpu_port) else "port"
+    # a bounded sample: ~60 sites/s/core through the stock per-site call, so 64 sites per worker and step is ~1 s of work
+    n_sites = args.cpu_sites or (64 if kind == "reference" else 128) * workers
     pl = synth.make_pileups(n_sites, coverage=cov, channels=cfg.read_cin, seed=13)
-    tasks = _cpu_tasks(pl, cfg, 16)
+    if kind == "reference":
+        tasks, init, run = _ref_tasks(pl, cfg, 4), _ref_worker_init, _ref_worker_run
+        how = "the reference's own modules (oracle/_ref/python, unmodified): MoEMergedWrapperAdvanced(featureDict, segment) " \
+              "once per site under no_grad + the caller's argmax, as python/caller_calling.py:651-652,702-705"
+    else:
+        tasks, init, run = _cpu_tasks(pl, cfg, 16), _cpu_worker_init, _cpu_worker_run
+        how = "oracle/hello_oracle.py (a port of the reference forward: oracle/_ref/python is missing), 16-site calls"
     ctx = mp.get_context("fork")
-    with ctx.Pool(workers, initializer=_cpu_worker_init, initargs=(cfg_name,)) as pool:
+    with ctx.Pool(workers, initializer=init, initargs=(cfg_name,)) as pool:
         def step():
-            return sum(pool.map(_cpu_worker_run, tasks, chunksize=1))
+            return sum(pool.map(run, tasks, chunksize=1))
         for _ in range(args.warmup):
             step()
         t0 = time.perf_counter()
@@ -133,14 +192,14 @@ def run_reference(args):
             done += step()
         dt = time.perf_counter() - t0
     value = done / dt
-    sample = "%d synthetic %s sites per step (seed 13, CPU generator), 16-site calls, %d worker processes x 1 torch " \
-             "thread" % (n_sites, args.workload, workers)
+    sample = "%d synthetic %s sites per step (seed 13, CPU generator); %s; %d worker processes x 1 torch thread" % (
+        n_sites, args.workload, how, workers)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "wiring": cfg_name, "sites_per_step": n_sites, "coverage": cov},
-        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": workers, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

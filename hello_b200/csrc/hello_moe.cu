@@ -49,6 +49,8 @@ struct Arena {
 
 }  // namespace
 
+constexpr size_t MAX_PROFILE_REGIONS = 4096;   // regions bracketed between two hello_moe_profile_collect calls
+
 struct hello_moe {
     hello_cfg cfg;
     int device = 0;
@@ -68,7 +70,7 @@ struct hello_moe {
     // MixtureOfExpertsAdvancedXferLearning.py:94-183): the fused kernel runs the original layers, `tail` the added ones.
     std::vector<LayerDesc> tail[N_NETS];
     bool profile = false;
-    std::vector<cudaEvent_t> ev_pool;            // pairs (start, stop), created lazily
+    std::vector<cudaEvent_t> ev_pool;            // pairs (start, stop), created lazily, at most MAX_PROFILE_REGIONS pairs
     size_t ev_used = 0;
 };
 
@@ -335,7 +337,9 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         // read convolver (architectures/read_convolver.py) on uint8 rows
         const uint8_t* reads = dry ? nullptr : in->d_reads[t] + (size_t)ck.r0[t] * L * C;
         cudaEvent_t ev_stop = nullptr;
-        if (!dry && h->profile && nr > 0) {
+        // Profiling brackets at most MAX_PROFILE_REGIONS regions between two hello_moe_profile_collect calls: a caller that
+        // enables profiling and never collects does not grow the event pool without bound.
+        if (!dry && h->profile && nr > 0 && h->ev_used + 2 <= 2 * MAX_PROFILE_REGIONS) {
             if (h->ev_used + 2 > h->ev_pool.size()) {
                 cudaEvent_t a = nullptr, b = nullptr;
                 if (!run.check(cudaEventCreate(&a), "cudaEventCreate") || !run.check(cudaEventCreate(&b), "cudaEventCreate"))
@@ -495,9 +499,17 @@ bool parse_blob(hello_moe* h, const void* blob, size_t nbytes, std::string& err)
     h->n_floats = n_floats;
     h->h_weights.resize(n_floats);
     std::memcpy(h->h_weights.data(), p + data_off, n_floats * 4);
-    auto conv_from = [&](const int32_t* r, ConvDesc* c) -> bool {
+    // `used`: the record's convolution slot is live (conv_a always for conv / residual / pooled-linear records, conv_b for
+    // residual records, conv_s for residual records with a convolution shortcut).  Live slots must describe a real layer
+    // whose weights [k*cin, cout] and bias [cout] lie inside the data section.
+    auto conv_from = [&](const int32_t* r, ConvDesc* c, bool used) -> bool {
         c->cin = r[0]; c->cout = r[1]; c->k = r[2]; c->stride = r[3]; c->pad = r[4]; c->relu = r[5];
-        if ((uint64_t)r[6] >= n_floats + 1 || (uint64_t)r[7] >= n_floats + 1) return false;
+        if (r[6] < 0 || r[7] < 0 || (uint64_t)r[6] > n_floats || (uint64_t)r[7] > n_floats) return false;
+        if (used) {
+            if (r[0] <= 0 || r[1] <= 0 || r[2] <= 0 || r[3] <= 0 || r[4] < 0) return false;
+            const uint64_t wn = (uint64_t)r[2] * (uint64_t)r[0] * (uint64_t)r[1];
+            if ((uint64_t)r[6] + wn > n_floats || (uint64_t)r[7] + (uint64_t)r[1] > n_floats) return false;
+        }
         c->w = h->d_weights + r[6]; c->b = h->d_weights + r[7];
         return true;
     };
@@ -508,10 +520,17 @@ bool parse_blob(hello_moe* h, const void* blob, size_t nbytes, std::string& err)
             std::memcpy(r, p + rec_off + (size_t)(first[n] + i) * 128, 128);
             LayerDesc L{};
             L.kind = r[0]; L.has_shortcut = r[1];
-            if (!conv_from(r + 2, &L.a) || !conv_from(r + 10, &L.b) || !conv_from(r + 18, &L.s)) {
-                err = "weight offset out of range"; return false;
-            }
             if (L.kind < 0 || L.kind > KIND_GAP_LINEAR) { err = "unknown layer kind"; return false; }
+            const bool res = L.kind == KIND_RES;
+            if (L.kind == KIND_MAXPOOL) {
+                if (r[4] <= 0 || r[5] <= 0) { err = "max-pool record with k or stride <= 0"; return false; }
+            }
+            if (!conv_from(r + 2, &L.a, L.kind != KIND_MAXPOOL) || !conv_from(r + 10, &L.b, res) ||
+                !conv_from(r + 18, &L.s, res && L.has_shortcut != 0)) {
+                err = "layer record out of range (cin / cout / k / stride must be positive, pad non-negative, weights and "
+                      "bias inside the data section)";
+                return false;
+            }
             h->nets[n].push_back(L);
         }
     }
@@ -532,6 +551,10 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
     *out = nullptr;
     if (cfg->n_tech < 1 || cfg->n_tech > 2 || cfg->feature_length <= 0) {
         g_create_error = "hello_moe_create: n_tech must be 1 or 2"; return HELLO_ERR_ARG;
+    }
+    if (cfg->precision != HELLO_PREC_FP32 && cfg->precision != HELLO_PREC_BF16X3 && cfg->precision != HELLO_PREC_BF16) {
+        g_create_error = "hello_moe_create: precision must be one of HELLO_PREC_FP32 / HELLO_PREC_BF16X3 / HELLO_PREC_BF16";
+        return HELLO_ERR_ARG;
     }
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
@@ -718,9 +741,12 @@ static int forward_impl(hello_moe* h, const hello_batch* in, const hello_result*
         h->err = "bad input_layout"; return HELLO_ERR_ARG;
     }
     if (cfg.meta_kind == HELLO_META_REF && !in->d_ref_onehot) { h->err = "reference segment required"; return HELLO_ERR_ARG; }
-    // reduceSlots (python/MixtureOfExpertsAdvanced.py:23-34) indexes cumsum(slots) - 1: an empty slot silently reads the
-    // previous allele's row in the reference; here it is an error (the caller supplies one all-zero row instead,
-    // AlleleSearcherLiteFiltered.cpp:1037-1043)
+    // Intentional deviation, stricter than the reference: reduceSlots (python/MixtureOfExpertsAdvanced.py:23-34) takes
+    // results[cumsum(slots) - 1] minus the previous selection, so an empty slot after the first yields an all-zero sum
+    // (and an empty FIRST slot indexes row -1, i.e. wraps to the last row).  The reference's own callers never produce
+    // one -- an allele without support in a technology contributes one all-zero row
+    // (AlleleSearcherLiteFiltered.cpp:1037-1043, AlleleSearcherLite.py:245-247) -- so an empty slot here means a broken
+    // CSR and is reported as HELLO_ERR_ARG instead of being scored.  O(alleles of the range) on the host per call.
     for (int t = 0; t < cfg.n_tech; ++t) {
         const int32_t* off = in->h_allele_read_off[t];
         for (long long al = in->h_site_allele_off[sb]; al < in->h_site_allele_off[se]; ++al)

@@ -119,7 +119,7 @@ class MoEEngine:
     """Owns one hello_moe handle (weights on one GPU) plus its workspace."""
 
     def __init__(self, cfg: arch.ModelConfig, params: Dict[str, torch.Tensor], device="cuda:0",
-                 precision: str = "fp32", workspace_bytes: int = 4 << 30, max_chunk_sites: int = 0):
+                 precision: str = "bf16x3", workspace_bytes: int = 4 << 30, max_chunk_sites: int = 0):
         if not torch.cuda.is_available():
             raise _lib.HelloMoEError("hello_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -271,16 +271,23 @@ class MoEEngine:
                                                   workspace.data_ptr(), workspace.numel(), C.c_void_p(stream))
         self._check(rc, "hello_moe_forward_range")
 
-    def forward_host(self, hb: "HostBatch", chunk_sites: int = 65536) -> "HostResult":
+    def forward_host(self, hb: "HostBatch", chunk_sites: int = 65536, sync: bool = True,
+                     fresh_result: bool = False) -> "HostResult":
         """End-to-end call on HOST buffers.  The device-side batch (read rows, CSR, results) is allocated once per
         HostBatch; every call streams the read rows host -> device in ranges of `chunk_sites` sites on a copy stream
-        while the previous range computes (hello_moe_forward_range), then brings the per-site results back."""
+        while the previous range computes (hello_moe_forward_range), then brings the per-site results back.
+
+        With ``sync=True`` (default) the call returns when the results ARE in the returned host buffers.  With
+        ``sync=False`` it returns as soon as everything is queued: the device -> host copies may still be in flight, so
+        call ``result.wait()`` (or poll ``result.ready()``) before reading any field.
+        The returned HostResult aliases pinned buffers cached on the HostBatch -- a second forward_host on the same batch
+        overwrites them -- unless ``fresh_result=True`` asks for newly allocated ones."""
         st = hb.device_state(self)
         main = torch.cuda.current_stream(self.device)
         copy_s, comp_s = st["copy"], st["compute"]
         copy_s.wait_stream(main)
         comp_s.wait_stream(main)
-        db, res, out = st["batch"], st["result"], hb.result_buffers()
+        db, res, out = st["batch"], st["result"], hb.result_buffers(fresh=fresh_result)
         S = hb.n_sites
         with torch.cuda.stream(copy_s):                       # the CSR arrays first (a few MB), then the rows
             for dst, src in st["small"]:
@@ -307,8 +314,13 @@ class MoEEngine:
         with torch.cuda.stream(comp_s):
             for dst, src in zip(out.tensors(), res.tensors()):
                 dst.copy_(src, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(comp_s)
+        out.done_event = done
         main.wait_stream(comp_s)
         main.wait_stream(copy_s)
+        if sync:
+            done.synchronize()
         return out
 
     def run_net(self, net: str, x: torch.Tensor, layout: int = _lib.LAYOUT_RLC) -> torch.Tensor:
@@ -383,6 +395,7 @@ class HostResult:
     call_pair: torch.Tensor
     call_qual: torch.Tensor
     best_expert: torch.Tensor
+    done_event: Optional["torch.cuda.Event"] = None     # recorded after the last device -> host copy of the call
 
     def tensors(self):
         return (self.logits, self.meta, self.pair_prob, self.pair_mix64, self.best_pair, self.best_prob,
@@ -390,6 +403,16 @@ class HostResult:
 
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.tensors())
+
+    def ready(self) -> bool:
+        """True once the results of the forward_host call that produced this object are in host memory."""
+        return self.done_event is None or self.done_event.query()
+
+    def wait(self) -> "HostResult":
+        """Block the host until the results are in host memory (needed after forward_host(..., sync=False))."""
+        if self.done_event is not None:
+            self.done_event.synchronize()
+        return self
 
 
 class HostBatch:
@@ -418,13 +441,19 @@ class HostBatch:
             n += self.ref_onehot.numel() * 4
         return n
 
-    def result_buffers(self) -> HostResult:
-        if self._out is None:
+    def result_buffers(self, fresh: bool = False) -> HostResult:
+        """Pinned host buffers for the per-site results.  The default returns the SAME cached buffers on every call
+        (pinning is expensive); ``fresh=True`` allocates new ones the caller owns."""
+        def make():
             A, S, P = int(self.site_allele_off[-1]), self.n_sites, int(self.pair_off[-1])
             mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=self.pin)
-            self._out = HostResult(mk((3, A), torch.float32), mk((S, 3), torch.float32), mk((4, P), torch.float32),
-                                   mk((P,), torch.float64), mk((S, 2), torch.int32), mk((S,), torch.float32),
-                                   mk((S, 5, 2), torch.int32), mk((S, 5), torch.float64), mk((S,), torch.int32))
+            return HostResult(mk((3, A), torch.float32), mk((S, 3), torch.float32), mk((4, P), torch.float32),
+                              mk((P,), torch.float64), mk((S, 2), torch.int32), mk((S,), torch.float32),
+                              mk((S, 5, 2), torch.int32), mk((S, 5), torch.float64), mk((S,), torch.int32))
+        if fresh:
+            return make()
+        if self._out is None:
+            self._out = make()
         return self._out
 
     def device_state(self, engine: "MoEEngine"):
@@ -482,7 +511,7 @@ class MoEAttentionB200:
     """Drop-in for ``MoEAttention``: same ``forward`` signature and return convention, computed on the GPU."""
 
     def __init__(self, cfg: arch.ModelConfig, params: Dict[str, torch.Tensor], device="cuda:0",
-                 precision: str = "fp32", **engine_kwargs):
+                 precision: str = "bf16x3", **engine_kwargs):
         self.cfg = cfg
         self.engine = MoEEngine(cfg, params, device, precision, **engine_kwargs)
         self.meta = object() if cfg.meta is not None else None   # wrapper tests `moeMerged.meta is not None`
@@ -490,7 +519,7 @@ class MoEAttentionB200:
 
     @classmethod
     def from_state_dict(cls, state_dict, **kw) -> "MoEAttentionB200":
-        sd = {k: v for k, v in state_dict.items() if not k.endswith(".weight")}
+        sd = weights.weight_norm_state(state_dict)
         return cls(weights.cfg_from_state_dict(sd), sd, **kw)
 
     @classmethod
@@ -596,6 +625,44 @@ def feature_records(expert_prob, meta, pair_off, alleles_per_site: Sequence[Sequ
 def result_feature_records(res: "BatchResult", alleles_per_site, loci):
     """feature_records of a whole batch result (device or host)."""
     return feature_records(res.pair_prob[1:], res.meta, res.pair_off, alleles_per_site, loci)
+
+
+def read_wrapper(path: str, reference_python: Optional[str] = None):
+    """Unpickle a reference ``.wrapper.dnn`` on the CPU: -> (ModelConfig, weight-norm state dict, providePredictions).
+
+    The files are whole-module pickles of ``MoEMergedWrapperAdvanced`` (python/create_model_wrapper.py:7-10,
+    ``torch.save(wrapper, path)``), so unpickling needs the reference's own ``NNTools`` / ``MixtureOfExpertsAdvanced``
+    importable -- a user of the reference has them on ``sys.path`` (it is how python/caller_calling.py:863 loads the same
+    file); ``reference_python`` adds a directory for that.  ``NNTools`` must be imported first: it patches its layer
+    classes onto ``torch.nn`` (python/NNTools.py:841-855) and the pickle refers to them there.  ``weights_only=False``
+    because the file is a pickled module tree (with the legacy WeightNorm forward-pre-hooks), not a state dict."""
+    import importlib
+    import sys
+    if reference_python and reference_python not in sys.path:
+        sys.path.insert(0, reference_python)
+    try:
+        importlib.import_module("NNTools")
+        importlib.import_module("MixtureOfExpertsAdvanced")
+    except ImportError as exc:
+        raise _lib.HelloMoEError(
+            "load_wrapper: a .wrapper.dnn is a pickle of the reference's module tree; put the reference's python/ "
+            "directory on sys.path (or pass reference_python=...) so that NNTools and MixtureOfExpertsAdvanced import: %s"
+            % exc) from exc
+    net = torch.load(path, map_location="cpu", weights_only=False)
+    moe = getattr(net, "moeMerged", net)                     # the wrapper, or a bare MoEAttention
+    if not hasattr(moe, "state_dict"):
+        raise _lib.HelloMoEError("load_wrapper: %s does not hold a torch module" % path)
+    sd = weights.weight_norm_state(moe.state_dict())
+    return weights.cfg_from_state_dict(sd), sd, bool(getattr(net, "providePredictions", False))
+
+
+def load_wrapper(path: str, device="cuda:0", precision: str = "bf16x3", reference_python: Optional[str] = None,
+                 **engine_kwargs) -> "MoEMergedWrapperB200":
+    """Drop-in for ``network = torch.load(path, map_location='cpu')`` (python/caller_calling.py:863-867): the same file,
+    scored on the GPU.  ``.eval()`` and ``.providePredictions`` work as on the reference object."""
+    cfg, sd, provide = read_wrapper(path, reference_python)
+    moe = MoEAttentionB200(cfg, sd, device=device, precision=precision, **engine_kwargs)
+    return MoEMergedWrapperB200(moe, providePredictions=provide)
 
 
 class MoEMergedWrapperB200:

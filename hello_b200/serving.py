@@ -19,6 +19,7 @@ the CPU with an injected scoring function; the product ``ScoringServer`` has no 
 from __future__ import annotations
 
 import multiprocessing as mp
+import os
 import queue
 import time
 from dataclasses import dataclass
@@ -69,7 +70,24 @@ class BatchPlanner:
         self.n_tech = n_tech
         self.reqs: List[SiteRequest] = []
 
+    def validate(self, req: SiteRequest) -> None:
+        """Raise ValueError for a request that cannot be part of a batch (so that it is answered on its own instead of
+        failing the whole batch it would have joined)."""
+        n = len(req.alleles)
+        if n < 1:
+            raise ValueError("a site needs at least one allele")
+        if len(req.reads) != self.n_tech or any(len(per) != n for per in req.reads):
+            raise ValueError("featureDict does not hold %d technologies x %d alleles" % (self.n_tech, n))
+        for t, per in enumerate(req.reads):
+            for x in per:
+                if x.ndim != 3 or x.shape[0] < 1:
+                    raise ValueError("every allele needs at least one [r, L, C] row per technology (reduceSlots requires "
+                                     "it; an allele without support carries one all-zero row)")
+                if x.shape[1:] != per[0].shape[1:]:
+                    raise ValueError("technology %d tensors of one site differ in shape" % t)
+
     def add(self, req: SiteRequest):
+        self.validate(req)
         self.reqs.append(req)
 
     def __len__(self):
@@ -117,35 +135,69 @@ class BatchPlanner:
 
 
 def serve_loop(run_batch: Callable, n_tech: int, requests, responses: Sequence, max_sites: int = 4096,
-               max_wait_s: float = 0.002, stats: Optional[dict] = None):
+               max_wait_s: float = 0.002, stats: Optional[dict] = None, heartbeat=None, idle_tick_s: float = 0.5):
     """Drain `requests` (SiteRequest objects; the string _STOP ends the loop), score up to `max_sites` pending sites
     per call of `run_batch(reads, allele_read_off, site_allele_off, allele_rank, ref_onehot)` -> dict of numpy arrays
-    (pair_prob, meta, best_pair, call_pair, call_qual, best_expert) and answer on responses[client]."""
+    (pair_prob, meta, best_pair, call_pair, call_qual, best_expert) and answer on responses[client].
+
+    A request that fails validation is answered with its exception on its own; if a whole batch fails, its sites are
+    re-scored one by one so that only the offending client sees the exception.  `heartbeat` (a shared double) is stamped
+    with time.time() at least every `idle_tick_s` seconds; clients use it to tell a busy server from a dead one."""
+    def tick():
+        if heartbeat is not None:
+            heartbeat.value = time.time()
+
+    def score(plan):
+        res = run_batch(*plan.build())
+        for req, site in plan.split(res["pair_prob"], res["meta"], res["best_pair"], res["call_pair"], res["call_qual"],
+                                    res["best_expert"]):
+            responses[req.client].put((req.seq, site))
+
+    def admit(plan, item) -> bool:
+        """item -> plan, or straight back to its client when it is malformed.  False on _STOP."""
+        if isinstance(item, str) and item == _STOP:
+            return False
+        try:
+            plan.add(item)
+        except Exception as exc:
+            responses[item.client].put((item.seq, exc))
+        return True
+
     stop = False
     while not stop:
-        first = requests.get()
-        if isinstance(first, str) and first == _STOP:
-            break
+        tick()
+        try:
+            first = requests.get(timeout=idle_tick_s)
+        except queue.Empty:
+            continue
         plan = BatchPlanner(n_tech)
-        plan.add(first)
+        if not admit(plan, first):
+            break
         deadline = time.perf_counter() + max_wait_s
         while len(plan) < max_sites:
             try:
                 nxt = requests.get(timeout=max(0.0, deadline - time.perf_counter()))
             except queue.Empty:
                 break
-            if isinstance(nxt, str) and nxt == _STOP:
+            if not admit(plan, nxt):
                 stop = True
                 break
-            plan.add(nxt)
+        if len(plan) == 0:
+            continue
+        tick()
         try:
-            res = run_batch(*plan.build())
-            for req, site in plan.split(res["pair_prob"], res["meta"], res["best_pair"], res["call_pair"], res["call_qual"],
-                                        res["best_expert"]):
-                responses[req.client].put((req.seq, site))
-        except Exception as exc:                     # the worker re-raises: same failure path as a failing network call
+            score(plan)
+        except Exception:
+            # one bad site must not poison up to max_sites others: score them one at a time, the worker of the failing
+            # site re-raises (same failure path as a failing network call), everybody else gets a result
             for req in plan.reqs:
-                responses[req.client].put((req.seq, exc))
+                single = BatchPlanner(n_tech)
+                single.reqs.append(req)
+                try:
+                    score(single)
+                except Exception as exc:
+                    responses[req.client].put((req.seq, exc))
+                tick()
         if stats is not None:
             stats["batches"] = stats.get("batches", 0) + 1
             stats["sites"] = stats.get("sites", 0) + len(plan)
@@ -155,8 +207,10 @@ class RemoteNetwork:
     """Client-side stand-in for ``MoEMergedWrapperAdvanced``: ``network(featureDict, ref_segment)`` scores the site on the
     server's GPU.  Picklable; inherited by forked pool workers."""
 
-    def __init__(self, requests, response, client: int, n_tech: int, has_meta_ref: bool):
+    def __init__(self, requests, response, client: int, n_tech: int, has_meta_ref: bool, server_pid: Optional[int] = None,
+                 heartbeat=None, dead_after_s: float = 60.0):
         self._req, self._resp, self.client, self.n_tech, self._ref = requests, response, client, n_tech, has_meta_ref
+        self._pid, self._hb, self._dead_after = server_pid, heartbeat, dead_after_s
         self.providePredictions = False
         self._seq = 0
         self.last_calls = None
@@ -164,11 +218,37 @@ class RemoteNetwork:
     def eval(self):
         return self
 
+    def _server_problem(self) -> Optional[str]:
+        """Why the server cannot answer any more, or None.  Works from any process (forked pool workers are siblings of
+        the server, not its parent): /proc tells a gone or zombie process, the heartbeat a hung one."""
+        if self._pid is not None:
+            try:
+                with open("/proc/%d/stat" % self._pid) as f:
+                    state = f.read().rsplit(")", 1)[1].split()[0]
+                if state in ("Z", "X"):
+                    return "the scoring server process (pid %d) has exited" % self._pid
+            except FileNotFoundError:
+                return "the scoring server process (pid %d) is gone" % self._pid
+            except (OSError, IndexError):
+                pass
+        if self._hb is not None and self._hb.value > 0 and time.time() - self._hb.value > self._dead_after:
+            return "the scoring server has not answered for %.0f s" % (time.time() - self._hb.value)
+        return None
+
+    def _await_response(self):
+        while True:
+            try:
+                return self._resp.get(timeout=1.0)
+            except queue.Empty:
+                why = self._server_problem()
+                if why:
+                    raise RuntimeError("RemoteNetwork: %s; site not scored" % why)
+
     def __call__(self, featureDict, segment):
         self._seq += 1
         req = request_from_feature_dict(self.client, self._seq, featureDict, segment if self._ref else None, self.n_tech)
         self._req.put(req)
-        seq, site = self._resp.get()
+        seq, site = self._await_response()
         if isinstance(site, Exception):
             raise site
         assert seq == self._seq, "response out of order"
@@ -185,10 +265,15 @@ class RemoteNetwork:
     forward = __call__
 
 
-def _gpu_server_main(cfg_name, params, device, precision, requests, responses, max_sites, max_wait_s, ready):
+def _gpu_server_main(cfg_name, params, device, precision, requests, responses, max_sites, max_wait_s, ready, heartbeat,
+                     failure):
     from . import _lib, model
     cfg = arch.CONFIGS[cfg_name]
-    net = model.MoEAttentionB200(cfg, params, device=device, precision=precision)
+    try:
+        net = model.MoEAttentionB200(cfg, params, device=device, precision=precision)
+    except Exception as exc:                         # missing library / no GPU / bad weights: tell the parent why
+        failure.put(repr(exc))
+        raise
 
     def run_batch(reads, offs, sao, rank, ref):
         batch = model.DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, offs, sao, ref if cfg.meta == "meta_convolver_ref" else None,
@@ -199,15 +284,17 @@ def _gpu_server_main(cfg_name, params, device, precision, requests, responses, m
                 "call_pair": r.call_pair.cpu().numpy(), "call_qual": r.call_qual.cpu().numpy(),
                 "best_expert": r.best_expert.cpu().numpy()}
 
+    heartbeat.value = time.time()
     ready.set()
-    serve_loop(run_batch, len(cfg.read_cin), requests, responses, max_sites, max_wait_s)
+    serve_loop(run_batch, len(cfg.read_cin), requests, responses, max_sites, max_wait_s, heartbeat=heartbeat)
 
 
 class ScoringServer:
     """Owns one GPU engine in its own (spawned) process.  ``client(i)`` gives worker i its ``RemoteNetwork``."""
 
     def __init__(self, cfg_name: str, params: Dict[str, torch.Tensor], n_clients: int, device="cuda:0",
-                 precision: str = "bf16x3", max_sites: int = 4096, max_wait_s: float = 0.002):
+                 precision: str = "bf16x3", max_sites: int = 4096, max_wait_s: float = 0.002,
+                 startup_timeout_s: float = 300.0):
         if not torch.cuda.is_available():
             from . import _lib
             raise _lib.HelloMoEError("ScoringServer needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -216,15 +303,27 @@ class ScoringServer:
         self.requests = ctx.Queue()
         self.responses = [ctx.Queue() for _ in range(n_clients)]
         ready = ctx.Event()
+        failure = ctx.Queue()
+        self.heartbeat = ctx.Value("d", 0.0, lock=False)
         self.proc = ctx.Process(target=_gpu_server_main, daemon=True,
                                 args=(cfg_name, {k: v.cpu() for k, v in params.items()}, device, precision, self.requests,
-                                      self.responses, max_sites, max_wait_s, ready))
+                                      self.responses, max_sites, max_wait_s, ready, self.heartbeat, failure))
         self.proc.start()
-        if not ready.wait(timeout=300):
-            raise RuntimeError("scoring server did not come up")
+        t_end = time.time() + startup_timeout_s
+        while not ready.wait(timeout=0.5):           # a child that died (no library, no GPU) is reported at once
+            if not self.proc.is_alive():
+                try:
+                    why = failure.get(timeout=1.0)
+                except queue.Empty:
+                    why = "no message"
+                raise RuntimeError("scoring server exited during start-up (exit code %s): %s" % (self.proc.exitcode, why))
+            if time.time() > t_end:
+                self.proc.terminate()
+                raise RuntimeError("scoring server did not come up within %.0f s" % startup_timeout_s)
 
     def client(self, i: int) -> RemoteNetwork:
-        return RemoteNetwork(self.requests, self.responses[i], i, len(self.cfg.read_cin), self.cfg.meta == "meta_convolver_ref")
+        return RemoteNetwork(self.requests, self.responses[i], i, len(self.cfg.read_cin), self.cfg.meta == "meta_convolver_ref",
+                             server_pid=self.proc.pid, heartbeat=self.heartbeat)
 
     def close(self):
         if self.proc.is_alive():

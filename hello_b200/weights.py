@@ -113,6 +113,29 @@ def folded(params: Dict[str, torch.Tensor], prefix: str) -> Tuple[torch.Tensor, 
     return w, params[prefix + ".bias"].float()
 
 
+def weight_norm_state(state_dict) -> Dict[str, torch.Tensor]:
+    """A reference state dict reduced to what the packer reads: ``weight_g`` / ``weight_v`` / ``bias`` per layer.
+
+    A materialised ``<layer>.weight`` next to its ``weight_g`` / ``weight_v`` (some torch versions keep the hook's last
+    product in the state dict) is redundant and dropped.  Any other ``.weight`` -- a plain Conv1d/Linear, or the
+    BatchNorm1d / LayerNorm layers of the configurations built without weight-norm (python/NNTools.py:27-45,84-104) --
+    belongs to a model this build has no layer table for: refuse instead of silently losing the weights."""
+    out, plain = {}, []
+    for k, v in state_dict.items():
+        if k.endswith(".weight"):
+            if k[:-len(".weight")] + ".weight_v" in state_dict:
+                continue
+            plain.append(k)
+        elif k.endswith((".running_mean", ".running_var", ".num_batches_tracked")):
+            plain.append(k)
+        else:
+            out[k] = v
+    if plain:
+        raise ValueError("state dict holds layers without weight-norm (%s ...): BatchNorm / LayerNorm / plain-weight "
+                         "configurations are not supported; every shipped model uses weight_norm = True" % plain[:3])
+    return out
+
+
 def cfg_from_state_dict(params: Dict[str, torch.Tensor]) -> arch.ModelConfig:
     """Recognise which reference config a MoEAttention state dict belongs to."""
     for cfg in arch.CONFIGS.values():

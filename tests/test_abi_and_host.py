@@ -230,6 +230,13 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "candidate_sites_per_sec" and d["unit"] == "sites/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2
+    from oracle import ref_model
+    # the reference's own modules wherever oracle/_ref/python exists (make -C oracle; it travels to the GPU box),
+    # the labelled port otherwise
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_model.available() else "port")
+    assert d["cpu_baseline"]["cores"] == 2
     assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("illumina_30x")
+    port = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                           "--cpu-sites", "32", "--cpu-workers", "2", "--cpu-port"], capture_output=True, text=True, timeout=300)
+    assert port.returncode == 0 and json.loads(port.stdout.splitlines()[-1])["cpu_baseline"]["kind"] == "port"

@@ -15,6 +15,15 @@ pytestmark = pytest.mark.gpu
 # layer.  bf16 (single MMA) is the "fast" mode, reported separately and only checked loosely.
 TOL_LOGIT = {"fp32": 2e-4, "bf16x3": 1e-3}
 TOL_PROB = {"fp32": 5e-5, "bf16x3": 5e-4}
+# north_star speaks of log-posteriors: pair probabilities above LOG_FLOOR must also agree in log space (an absolute bound
+# alone would let p = 1e-6 be off by a factor of 500).  |d log P| <= (number of alleles) * |d logit|, so with the logit
+# tolerances above and up to ~6 alleles per site:
+TOL_LOGP = {"fp32": 2e-3, "bf16x3": 6e-3}
+LOG_FLOOR = 1e-6
+# Sites whose reference top-2 margin is below twice the probability tolerance are not required to give the same call
+# (CPU and GPU exp/log/sigmoid are not bit-identical); their share must stay small and is printed.
+MAX_TIGHT_SHARE = 0.02
+PRECISIONS = ["bf16x3", "fp32"]          # the shipped default first
 TC_LAYER_REL = {"bf16x3": 5e-5, "bf16": 4e-2}
 DEV = "cuda:0"
 
@@ -30,7 +39,7 @@ def gpu():
 _engines = {}
 
 
-def net_for(model, cfg, precision="fp32", **kw):
+def net_for(model, cfg, precision="bf16x3", **kw):
     key = (cfg.name, precision, tuple(sorted(kw.items())))
     if key not in _engines:
         _engines[key] = model.MoEAttentionB200(cfg, params_for(cfg), device=DEV, precision=precision, **kw)
@@ -47,7 +56,7 @@ def oracle_for(cfg):
 def test_read_convolver_per_read(gpu, name):
     cfg = arch.CONFIGS[name]
     pl = synth.make_pileups(5, coverage=9, channels=cfg.read_cin, seed=21)
-    net = net_for(gpu, cfg)
+    net = net_for(gpu, cfg, "fp32")              # the CUDA-core path; the tensor-core path has its own per-layer tests
     from hello_b200 import _lib
     got_rlc = net.engine.run_net("read_convolver0", pl.reads[0], _lib.LAYOUT_RLC).cpu()
     got_rcl = net.engine.run_net("read_convolver0", pl.reads[0].transpose(1, 2).contiguous(), _lib.LAYOUT_RCL).cpu()
@@ -63,7 +72,7 @@ def test_head_networks(gpu, net_name, shape):
     cfg = arch.CONFIGS["single_tech"]
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(shape, generator=g) * 40).float()
-    got = net_for(gpu, cfg).engine.run_net(net_name, x).cpu()
+    got = net_for(gpu, cfg, "fp32").engine.run_net(net_name, x).cpu()
     ref = oracle_for(cfg).nets[net_name](x.transpose(1, 2))
     if ref.dim() == 3:
         ref = ref.transpose(1, 2)
@@ -116,18 +125,20 @@ def test_standard_models_run_on_the_fused_kernels(gpu):
         assert eng.launch_count() - before == n_launch + 1, name     # + fill_meta_default (no meta network)
 
 
-def test_combiner_and_meta_networks(gpu):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_combiner_and_meta_networks(gpu, precision):
     cfg = arch.CONFIGS["hybrid_full"]
     g = torch.Generator().manual_seed(6)
-    net, orc = net_for(gpu, cfg), oracle_for(cfg)
+    net, orc = net_for(gpu, cfg, precision), oracle_for(cfg)
+    rel = TC_LAYER_REL["bf16x3"] if precision == "bf16x3" else 2e-5
     x = (torch.randn((5, 18, 256), generator=g) * 20).float()
     got = net.engine.run_net("combiner0", x).cpu()
     ref = orc.nets["combiner0"](x.transpose(1, 2)).transpose(1, 2)
-    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() < rel * max(1.0, ref.abs().max().item())
     s = (torch.randn((4, 18, 128), generator=g) * 20).float()
     got = net.engine.run_net("meta", s).cpu().reshape(4, 3)
     ref = orc.nets["meta"](s.transpose(1, 2))
-    assert (got - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    assert (got - ref).abs().max().item() < rel * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
@@ -343,21 +354,41 @@ def test_forward_matches_reference_golden(gpu, case, precision):
              np.repeat(g["site_meta"].astype(np.float64), np.diff(r.pair_off.numpy()), axis=0).T).sum(0)
     np.testing.assert_allclose(r.pair_mix64.cpu().numpy(), mix64, rtol=0, atol=TOL_PROB[precision])
     # genotype call: bit-exact wherever the reference's own top-2 margin exceeds the posterior tolerance
-    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB[precision])
+    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB[precision], case + "/" + precision)
+    check_log_probs(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], precision, case)
+    check_log_probs(r.pair_prob[1:].cpu().numpy(), g["pair_experts"], precision, case)
 
 
-def check_calls(result, ref_mixed, ref_best, tol):
+def check_calls(result, ref_mixed, ref_best, tol, what="", max_tight_share=MAX_TIGHT_SHARE):
+    """Genotype calls bit-exact wherever the reference's own top-2 margin exceeds 2*tol; the number of tight-margin
+    sites (compared only through their probabilities) is printed and bounded."""
     off = result.pair_off.numpy()
     got = result.best_pair.cpu().numpy()
-    n_tight = 0
-    for s in range(len(off) - 1):
+    n_sites = len(off) - 1
+    n_tight = n_tight_differs = 0
+    for s in range(n_sites):
         probs = np.sort(ref_mixed[off[s]:off[s + 1]])[::-1]
         margin = probs[0] - probs[1] if probs.size > 1 else np.inf
         if margin > 2 * tol:
             assert tuple(got[s]) == tuple(ref_best[s]), (s, got[s], ref_best[s], probs[:3])
         else:
             n_tight += 1
+            n_tight_differs += tuple(got[s]) != tuple(ref_best[s])
+    print("check_calls[%s]: %d sites, %d exact-call checks, %d tight-margin sites (top-2 margin <= %.1e), %d of them "
+          "called differently" % (what, n_sites, n_sites - n_tight, n_tight, 2 * tol, n_tight_differs))
+    assert n_tight <= max(1, int(max_tight_share * n_sites)), (what, n_tight, n_sites)
     return n_tight
+
+
+def check_log_probs(got, ref, precision, what=""):
+    """Pair probabilities in log space wherever the reference value is above LOG_FLOOR."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    m = ref > LOG_FLOOR
+    if not m.any():
+        return 0.0
+    err = np.abs(np.log(np.maximum(got[m], 1e-300)) - np.log(ref[m])).max()
+    assert err <= TOL_LOGP[precision], (what, precision, err)
+    return float(err)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
@@ -379,9 +410,46 @@ def test_forward_matches_oracle_seeded(gpu, name, precision):
     best = np.array([p[3] for p in post], np.int32)
     r = net.last_result
     np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=TOL_PROB[precision])
-    check_calls(r, mixed, best, TOL_PROB[precision])
+    check_calls(r, mixed, best, TOL_PROB[precision], name + "/" + precision)
+    check_log_probs(r.pair_prob[0].cpu().numpy(), mixed, precision, name)
     np.testing.assert_allclose(r.best_prob.cpu().numpy(), np.array([p[4] for p in post], np.float32), rtol=0,
                                atol=TOL_PROB[precision])
+
+
+@pytest.mark.parametrize("gain", [4.0, 8.0])
+def test_rescaled_weight_norm_gains(gpu, gain):
+    """Random-init weights keep activations small; a trained model's weight-norm gains need not.  The gain g of the three
+    stem convolutions of the read convolver is multiplied by `gain` each (every activation behind them grows by up to
+    gain^3 = 64x / 512x: per-read features in the thousands, allele sums in the tens of thousands) and the pooled linear
+    head's gain is divided by the same factor, so logits stay O(10) and the absolute 1e-3 bound keeps its meaning.
+    bf16x3 is a relative-error scheme (hi+lo operands, fp32 accumulate), so it must hold the same tolerance."""
+    from oracle import hello_oracle as O
+    cfg = arch.CONFIGS["single_tech"]
+    params = {k: v.clone() for k, v in params_for(cfg).items()}
+    stem = [k for k, _, _ in weights.conv_keys(cfg, "read_convolver0")][:3]
+    head = [k for k, _, kind in weights.conv_keys(cfg, "xattn0") if kind == "linear"]
+    assert len(head) == 1
+    for k in stem:
+        params[k + ".weight_g"] *= gain
+    params[head[0] + ".weight_g"] /= gain ** 3
+    pl = synth.make_pileups(48, coverage=20, channels=cfg.read_cin, seed=314)
+    orc = O.OracleModel(cfg, params)
+    ref = orc.forward(*pl.forward_args())
+    feat = orc.read_features(pl.reads[0].transpose(1, 2))
+    base = oracle_for(cfg).read_features(pl.reads[0].transpose(1, 2))
+    growth = feat.abs().max().item() / base.abs().max().item()
+    assert growth > gain ** 3 / 4, growth                   # the activations really are that much larger
+    net = gpu.MoEAttentionB200(cfg, params, device=DEV, precision="bf16x3")
+    res = net.forward(*pl.forward_args())
+    err = (res.cpu() - ref).abs().max().item()
+    print("rescaled gains x%g: read features up to %.3g (%.0fx the random-init model), logits in [%.2f, %.2f], "
+          "max |dlogit| = %.2e" % (gain, feat.abs().max().item(), growth, ref.min().item(), ref.max().item(), err))
+    assert err < TOL_LOGIT["bf16x3"], err
+    post = O.batched_posteriors(cfg, ref, pl.num_alleles_per_site())
+    mixed = torch.cat([p[0] for p in post]).numpy()
+    np.testing.assert_allclose(net.last_result.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=TOL_PROB["bf16x3"])
+    check_calls(net.last_result, mixed, np.array([p[3] for p in post], np.int32), TOL_PROB["bf16x3"], "gain x%g" % gain)
+    check_log_probs(net.last_result.pair_prob[0].cpu().numpy(), mixed, "bf16x3", "gain")
 
 
 @pytest.mark.parametrize("name", ["single_tech", "hybrid_no_ensemble", "hybrid_full"])
@@ -400,16 +468,18 @@ def test_fast_mode_is_close(gpu, name):
     post = O.batched_posteriors(cfg, ref, pl.num_alleles_per_site())
     mixed = torch.cat([p[0] for p in post]).numpy()
     np.testing.assert_allclose(net.last_result.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=2e-2)
-    check_calls(net.last_result, mixed, np.array([p[3] for p in post], np.int32), 2.5e-2)
+    check_calls(net.last_result, mixed, np.array([p[3] for p in post], np.int32), 2.5e-2, name + "/bf16",
+                max_tight_share=0.25)        # the fast mode's loose margin (5e-2) covers ~10 % of the sites
 
 
-def test_strict_drop_in_wrapper_call(gpu):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_strict_drop_in_wrapper_call(gpu, precision):
     """network(featureDict, segment) with providePredictions, as python/caller_calling.py:651-652 calls it."""
     from oracle import hello_oracle as O
     for name in ("single_tech", "hybrid_full"):
         cfg = arch.CONFIGS[name]
         pl = synth.make_pileups(4, coverage=8, channels=cfg.read_cin, seed=9)
-        network = gpu.MoEMergedWrapperB200(net_for(gpu, cfg)).eval()
+        network = gpu.MoEMergedWrapperB200(net_for(gpu, cfg, precision)).eval()
         network.providePredictions = True
         orc = oracle_for(cfg)
         for s in range(pl.n_sites):
@@ -421,11 +491,12 @@ def test_strict_drop_in_wrapper_call(gpu):
             for dg, dr in zip(got[:4], ref[:4]):
                 assert list(dg.keys()) == list(dr.keys())
                 for k in dg:
-                    assert dg[k].dim() == 0 and abs(float(dg[k]) - float(dr[k])) < TOL_PROB["fp32"]
-            assert (got[4] - ref[4]).abs().max().item() < TOL_PROB["fp32"]
+                    assert dg[k].dim() == 0 and abs(float(dg[k]) - float(dr[k])) < TOL_PROB[precision]
+                check_log_probs([float(dg[k]) for k in dg], [float(dr[k]) for k in dg], precision, name)
+            assert (got[4] - ref[4]).abs().max().item() < TOL_PROB[precision]
             key, value, _ = O.call_genotype(ref[0])
             vals = sorted((float(v) for v in ref[0].values()), reverse=True)
-            if len(vals) == 1 or vals[0] - vals[1] > 2 * TOL_PROB["fp32"]:
+            if len(vals) == 1 or vals[0] - vals[1] > 2 * TOL_PROB[precision]:
                 assert network.last_call[0] == key
         network.providePredictions = False
         assert isinstance(network(fd, seg), dict)
@@ -466,18 +537,19 @@ def test_final_call_records(gpu):
 
 
 # ------------------------------------------------------------------------------------------------ edge cases
-def test_chunking_does_not_change_results(gpu):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_chunking_does_not_change_results(gpu, precision):
     cfg = arch.CONFIGS["single_tech"]
     pl = synth.make_pileups(40, coverage=10, channels=cfg.read_cin, seed=31)
-    whole = net_for(gpu, cfg)
+    whole = net_for(gpu, cfg, precision)
     res_a = whole.forward(*pl.forward_args())
     ra = whole.last_result
-    tiny = net_for(gpu, cfg, max_chunk_sites=7)
+    tiny = net_for(gpu, cfg, precision, max_chunk_sites=7)
     res_b = tiny.forward(*pl.forward_args())
     rb = tiny.last_result
     assert torch.equal(res_a, res_b)
     assert torch.equal(ra.pair_prob, rb.pair_prob) and torch.equal(ra.best_pair, rb.best_pair)
-    small_ws = net_for(gpu, cfg, workspace_bytes=48 << 20)
+    small_ws = net_for(gpu, cfg, precision, workspace_bytes=48 << 20)
     res_c = small_ws.forward(*pl.forward_args())
     assert torch.equal(res_a, res_c)
 
@@ -493,13 +565,20 @@ def test_forward_host_streams_ranges(gpu, name):
     from hello_b200 import _lib
     hb = gpu.HostBatch(pl.reads, _lib.LAYOUT_RLC, pl.allele_read_off, pl.site_allele_off, pl.ref_onehot)
     for chunk in (7, 16, 50, 1000):
-        out = net.engine.forward_host(hb, chunk)
-        torch.cuda.synchronize()
+        out = net.engine.forward_host(hb, chunk)                 # sync=True: results are in host memory on return
+        assert out.ready()
         for got, want in zip(out.tensors(), ref.tensors()):
             assert torch.equal(got, want.cpu()), chunk
+    # asynchronous form: wait() before reading; fresh buffers are not overwritten by the next call
+    keep = net.engine.forward_host(hb, 16, sync=False, fresh_result=True).wait()
+    again = net.engine.forward_host(hb, 16)
+    assert keep.logits.data_ptr() != again.logits.data_ptr()
+    for got, want in zip(keep.tensors(), ref.tensors()):
+        assert torch.equal(got, want.cpu())
 
 
-def test_ragged_edges(gpu):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_ragged_edges(gpu, precision):
     """One read / one allele sites, a many-allele site, an all-zero technology row."""
     from oracle import hello_oracle as O
     cfg = arch.CONFIGS["hybrid_ensemble2"]
@@ -512,18 +591,19 @@ def test_ragged_edges(gpu):
     r1[0] = 0                                              # technology without support: one all-zero row
     onehot = torch.nn.functional.one_hot(torch.randint(0, 5, (4, 150), generator=g), 5).float()
     tensors = (r0.transpose(1, 2), r1.transpose(1, 2))
-    net = net_for(gpu, cfg)
+    net = net_for(gpu, cfg, precision)
     res = net.forward(tensors, n_alleles, (nr0, nr1), onehot)
     ref = oracle_for(cfg).forward(tensors, n_alleles, (nr0, nr1), onehot)
     lg, mg = flat_result(cfg, res)
     lr, mr = flat_result(cfg, ref)
-    scale = max(1.0, lr.abs().max().item())
-    assert (lg - lr).abs().max().item() < TOL_LOGIT["fp32"] * scale
-    assert (mg - mr).abs().max().item() < TOL_PROB["fp32"]
+    scale = max(1.0, lr.abs().max().item())      # uniform random bytes: logits reach the hundreds
+    assert (lg - lr).abs().max().item() < TOL_LOGIT[precision] * scale
+    assert (mg - mr).abs().max().item() < TOL_PROB[precision]
     assert net.last_result.pair_prob.shape[1] == 1 + 21 + 1 + 3
     post = O.batched_posteriors(cfg, ref, n_alleles)
     mixed = torch.cat([p[0] for p in post]).numpy()
-    np.testing.assert_allclose(net.last_result.pair_prob[0].cpu().numpy(), mixed, rtol=0, atol=TOL_PROB["fp32"])
+    np.testing.assert_allclose(net.last_result.pair_prob[0].cpu().numpy(), mixed, rtol=0,
+                               atol=TOL_PROB[precision] * (scale if precision != "fp32" else 1.0))
 
 
 def test_empty_batch_and_many_allele_site(gpu):
@@ -551,10 +631,11 @@ def test_empty_batch_and_many_allele_site(gpu):
     assert top == i * 40 - i * (i - 1) // 2 + (j - i)
 
 
-def test_float_inputs_and_errors(gpu):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_float_inputs_and_errors(gpu, precision):
     cfg = arch.CONFIGS["single_tech"]
     pl = synth.make_pileups(3, coverage=6, channels=cfg.read_cin, seed=4)
-    net = net_for(gpu, cfg)
+    net = net_for(gpu, cfg, precision)
     tensors, naps, nrpa, ref = pl.forward_args()
     a = net.forward(tensors, naps, nrpa, ref)
     b = net.forward((tensors[0].float(), None), naps, nrpa, ref)       # the reference passes floats
@@ -567,12 +648,13 @@ def test_float_inputs_and_errors(gpu):
         net.forward(tensors, naps[:-1], nrpa, ref)                      # inconsistent CSR
 
 
-def test_tie_break_uses_allele_rank(gpu):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_tie_break_uses_allele_rank(gpu, precision):
     """Two identical alleles give exactly equal pair probabilities; the reference's sort picks the greatest key."""
     cfg = arch.CONFIGS["single_tech"]
     g = torch.Generator().manual_seed(8)
     row = torch.randint(0, 256, (3, 150, 6), generator=g, dtype=torch.uint8).float()
-    network = gpu.MoEMergedWrapperB200(net_for(gpu, cfg))
+    network = gpu.MoEMergedWrapperB200(net_for(gpu, cfg, precision))
     for names in (["A", "C"], ["C", "A"]):
         fd = {names[0]: (row.clone(), None), names[1]: (row.clone(), None)}
         out = network(fd, torch.zeros(1, 150, 5))
@@ -583,11 +665,12 @@ def test_tie_break_uses_allele_rank(gpu):
 
 
 # ------------------------------------------------------------------------------------------------ properties
-def test_read_order_and_site_independence(gpu):
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_read_order_and_site_independence(gpu, precision):
     """Sites are independent: a site's result does not depend on which other sites share the batch."""
     cfg = arch.CONFIGS["single_tech"]
     pl = synth.make_pileups(12, coverage=10, channels=cfg.read_cin, seed=55)
-    net = net_for(gpu, cfg)
+    net = net_for(gpu, cfg, precision)
     full = net.forward(*pl.forward_args())
     sao = pl.site_allele_off
     aro = pl.allele_read_off[0]

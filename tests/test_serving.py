@@ -127,3 +127,66 @@ def test_gpu_scoring_server_equals_direct_calls():
     for s in range(24):
         assert got[s][0] == want[s][0], "batched-on-the-server results must equal the direct per-site call bit for bit"
         assert got[s][1] == want[s][1]
+
+
+def test_one_bad_site_does_not_poison_the_batch():
+    """A malformed request (an allele without rows) is answered with its exception on its own; a site that makes the
+    scorer fail is isolated by re-scoring the batch site by site: every other client still gets its result."""
+    cfg = arch.CONFIGS["single_tech"]
+    pl = synth.make_pileups(6, coverage=5, channels=cfg.read_cin, seed=5)
+    good = oracle_run_batch(cfg)
+
+    def run(reads, offs, sao, rank, ref):
+        if int((reads[0][:, 0, 0] == 255).sum()) > 0:          # poisoned site: first byte of a row is 255
+            raise RuntimeError("scorer rejected the batch")
+        return good(reads, offs, sao, rank, ref)
+
+    import queue as pyqueue
+    requests, responses = pyqueue.Queue(), [pyqueue.Queue() for _ in range(3)]
+    reqs = []
+    for s in range(6):
+        fd, seg = pl.site_feature_dict(s)
+        reqs.append(serving.request_from_feature_dict(s % 3, s + 1, fd, None, 1))
+    reqs[1].reads[0][0] = np.zeros((0, 150, 6), np.uint8)       # malformed: allele without rows
+    reqs[4].reads[0][0] = reqs[4].reads[0][0].copy()
+    reqs[4].reads[0][0][0, 0, 0] = 255                          # makes the scorer fail
+    for r in reqs:
+        requests.put(r)
+    requests.put(serving._STOP)
+    stats = {}
+    serving.serve_loop(run, 1, requests, responses, max_sites=16, max_wait_s=0.05, stats=stats)
+    answers = {}
+    for c in range(3):
+        while not responses[c].empty():
+            seq, site = responses[c].get()
+            answers[seq] = site
+    assert sorted(answers) == [1, 2, 3, 4, 5, 6]
+    assert isinstance(answers[2], ValueError) and "at least one" in str(answers[2])
+    assert isinstance(answers[5], RuntimeError)
+    for seq in (1, 3, 4, 6):
+        assert isinstance(answers[seq], dict) and answers[seq]["pair_prob"].shape[0] == 4
+
+
+def _die_quietly(requests):
+    requests.get()                                              # take the request, never answer, exit
+
+
+def test_remote_network_notices_a_dead_server():
+    """The client polls with a timeout and checks the server's process state: a server that died mid-request raises a
+    clear error in the worker instead of hanging it forever."""
+    cfg = arch.CONFIGS["single_tech"]
+    pl = synth.make_pileups(1, coverage=4, channels=cfg.read_cin, seed=2)
+    ctx = mp.get_context("fork")
+    requests, response = ctx.Queue(), ctx.Queue()
+    server = ctx.Process(target=_die_quietly, args=(requests,))
+    server.start()
+    net = serving.RemoteNetwork(requests, response, 0, 1, False, server_pid=server.pid)
+    fd, seg = pl.site_feature_dict(0)
+    with pytest.raises(RuntimeError, match="scoring server process"):
+        net(fd, seg)
+    server.join(timeout=10)
+    # a hung (alive but silent) server is caught by the heartbeat
+    hb = ctx.Value("d", 1.0, lock=False)                        # last heartbeat: 1970
+    net2 = serving.RemoteNetwork(requests, response, 0, 1, False, server_pid=None, heartbeat=hb, dead_after_s=5.0)
+    with pytest.raises(RuntimeError, match="has not answered"):
+        net2(fd, seg)

@@ -1,0 +1,85 @@
+"""`.wrapper.dnn` drop-in (north_star: "keep ... the .wrapper.dnn model load"): the reference pickles the whole
+MoEMergedWrapperAdvanced module (python/create_model_wrapper.py:7-10) and python/caller_calling.py:863 loads it with
+torch.load.  Here the reference's own modules build such a file for every supported wiring, hello_b200 reads it back on the
+CPU (read_wrapper: no GPU needed) and the packed weight blob must be byte-identical to the one packed from the same
+parameters directly.  Needs the reference's python modules (oracle/_ref/python or /root/reference/python); skipped
+otherwise.  One configuration per subprocess: the reference's architecture modules are mutable singletons."""
+import hashlib
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import params_for
+from hello_b200 import arch, weights
+from oracle import ref_model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = ["single_tech", "single_tech_hp", "hybrid_no_ensemble", "hybrid_ensemble2", "hybrid_full", "single_tech_addendum"]
+
+CHILD = r"""
+import hashlib, sys, warnings
+warnings.filterwarnings("ignore")
+sys.path.insert(0, %(root)r)
+import torch
+from hello_b200 import arch, weights
+from oracle import ref_model
+name, path = sys.argv[1], sys.argv[2]
+cfg = arch.CONFIGS[name]
+net = ref_model.build_wrapper(name, weights.init_params(cfg, seed=13), provide_predictions=True)
+torch.save(net, path)                                   # python/create_model_wrapper.py:10
+del net
+from hello_b200 import model
+got_cfg, sd, provide = model.read_wrapper(path)         # NNTools is already importable: ref_model put it on sys.path
+blob = weights.pack_blob(got_cfg, sd)
+print("RESULT", got_cfg.name, provide, hashlib.sha256(blob).hexdigest(), len(sd))
+"""
+
+
+@pytest.mark.skipif(not ref_model.available(), reason="the reference's python modules are not available")
+@pytest.mark.parametrize("name", CASES)
+def test_wrapper_pickle_round_trip(name, tmp_path):
+    path = str(tmp_path / (name + ".wrapper.dnn"))
+    out = subprocess.run([sys.executable, "-c", CHILD % {"root": ROOT}, name, path], capture_output=True, text=True,
+                         timeout=600, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+    cfg = arch.CONFIGS[name]
+    want = hashlib.sha256(weights.pack_blob(cfg, params_for(cfg))).hexdigest()
+    assert line[1] == name and line[2] == "True"
+    assert line[3] == want, "blob packed from the unpickled wrapper differs from the blob packed from the parameters"
+    assert int(line[4]) == len(weights.param_shapes(cfg))
+    assert os.path.getsize(path) > 1_000_000
+
+
+def test_state_dict_without_weight_norm_is_refused():
+    """A model built without weight-norm (plain Conv1d weights, BatchNorm statistics) must be refused, not silently
+    stripped of its weights (python/NNTools.py:27-45,84-104; moe_attention_config_single_tech_old_equivalent_layer_norm.py)."""
+    cfg = arch.CONFIGS["single_tech"]
+    sd = dict(params_for(cfg))
+    k = next(iter(sd)).rsplit(".", 1)[0]
+    # a materialised weight next to weight_g / weight_v is redundant and dropped
+    with_copy = dict(sd)
+    with_copy[k + ".weight"] = weights.fold_weight_norm(sd[k + ".weight_v"], sd[k + ".weight_g"])
+    assert set(weights.weight_norm_state(with_copy)) == set(sd)
+    assert weights.cfg_from_state_dict(weights.weight_norm_state(with_copy)).name == "single_tech"
+    plain = {kk: v for kk, v in sd.items() if not kk.startswith(k + ".weight_")}
+    plain[k + ".weight"] = with_copy[k + ".weight"]
+    with pytest.raises(ValueError, match="without weight-norm"):
+        weights.weight_norm_state(plain)
+    bn = dict(sd)
+    bn["read_convolver0.network.1.running_mean"] = torch.zeros(16)
+    with pytest.raises(ValueError, match="without weight-norm"):
+        weights.weight_norm_state(bn)
+
+
+def test_load_wrapper_reports_missing_reference_modules(tmp_path):
+    """Without NNTools importable the pickle cannot be read: a clear error, not an AttributeError from the unpickler."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from hello_b200 import model, _lib\n"
+            "try:\n    model.read_wrapper('/nonexistent.wrapper.dnn')\n"
+            "except _lib.HelloMoEError as e:\n    print('OK', 'NNTools' in str(e))\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.stdout.strip() == "OK True", out.stdout + out.stderr[-500:]
