@@ -52,6 +52,15 @@ def parse_args():
                     help="bf16x3 (default): read convolver on tcgen05 with hi+lo bf16 operands, fp32 accumulate, "
                          "posteriors within 1e-3 of the reference; bf16: single-MMA fast mode; fp32: CUDA cores only")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL gather of per-site results")
+    ap.add_argument("--partition", default="replicate-shape", choices=["replicate-shape", "balanced"],
+                    help="replicate-shape (default): every rank generates --sites sites of its own (weak scaling); "
+                         "balanced: ONE deterministic dataset of --total-sites sites (default --sites x ranks) is cut into "
+                         "contiguous site ranges of equal algorithmic cost (shard.site_costs / balanced_ranges), each rank "
+                         "generates and scores only its own range")
+    ap.add_argument("--total-sites", type=int, default=0, help="--partition balanced: sites of the whole dataset")
+    ap.add_argument("--no-other-workloads", action="store_true",
+                    help="skip the other_workloads legs (BASELINE configs 3-5 at --other-sites sites, 1 GPU only)")
+    ap.add_argument("--other-sites", type=int, default=131072)
     ap.add_argument("--workspace-gb", type=float, default=6.0)
     ap.add_argument("--chunk-sites", type=int, default=0, help="cap on sites per internal chunk (0 = auto)")
     ap.add_argument("--e2e-chunk-sites", type=int, default=0, help="sites per streamed range (0 = min(65536, sites/8))")
@@ -283,6 +292,129 @@ def generate_on_device(cfg, cov, n_sites, device, seed, gen_chunk=16384):
     return reads, tuple(csr(r) for r in rpa), csr(apS), (torch.cat(refs) if refs else None)
 
 
+def generate_balanced_shard(cfg, cov, total_sites, world, rank, device, seed, block=16384):
+    """--partition balanced: the dataset is `total_sites` sites in blocks of `block` (block b = synth.make_pileups with seed
+    + 7919 b, so it does not depend on the number of ranks).  Every rank replays the cheap head of each block's random
+    stream (synth.site_counts) to get alleles and reads per site, prices the sites with shard.site_costs, cuts the prefix
+    sum with shard.balanced_ranges and generates only the blocks that overlap its own range (shard.take_shard trims the
+    first and last one).  Mirrors the reference's shardHotspots.py:78-137 (contiguous hotspot shards, python/call.py:171-221)."""
+    import numpy as np
+    import torch
+    from hello_b200 import shard, synth
+    n_blocks = (total_sites + block - 1) // block
+    na, nr = [], []
+    for b in range(n_blocks):
+        n = min(block, total_sites - b * block)
+        a, r = synth.site_counts(n, cov, cfg.read_cin, seed + 7919 * b, device)
+        na.append(a.cpu())
+        nr.append(r.cpu())
+    na, nr = torch.cat(na).numpy(), torch.cat(nr).numpy()
+    sao_all = np.concatenate(([0], np.cumsum(na)))
+    cost = shard.site_costs(cfg, sao_all, reads_per_site=[nr])
+    ranges = shard.balanced_ranges(cost, world)
+    s0, s1 = ranges[rank]
+    reads, rpa, apS = [], [], []
+    for b in range(s0 // block, (max(s1, s0 + 1) - 1) // block + 1):
+        if s1 <= s0:
+            break
+        n = min(block, total_sites - b * block)
+        pl = synth.make_pileups(n, coverage=cov, channels=cfg.read_cin, seed=seed + 7919 * b, device=device)
+        lo, hi = max(s0 - b * block, 0), min(s1 - b * block, n)
+        sh = shard.take_shard(pl.site_allele_off, pl.allele_read_off, lo, hi)
+        r0, r1 = sh.read_range[0]
+        reads.append(pl.reads[0][r0:r1].clone() if (lo, hi) != (0, n) else pl.reads[0])
+        rpa.append(torch.diff(sh.allele_read_off[0]))
+        apS.append(torch.diff(sh.site_allele_off))
+        del pl
+
+    def csr(parts):
+        c = torch.cat(parts).to(torch.int64) if parts else torch.zeros(0, dtype=torch.int64)
+        off = torch.zeros(c.numel() + 1, dtype=torch.int64)
+        off[1:] = torch.cumsum(c, 0)
+        return off.to(torch.int32)
+    reads_t = torch.cat(reads) if reads else torch.zeros((0, 150, cfg.read_cin[0]), dtype=torch.uint8, device=device)
+    total_cost = float(cost.sum())
+    info = {"mode": "balanced", "total_sites": int(total_sites), "block_sites": block,
+            "site_ranges": [[int(a), int(b)] for a, b in ranges],
+            "cost_share": [float(cost[a:b].sum() / total_cost) for a, b in ranges],
+            "reads_per_rank": [int(nr[a:b].sum()) for a, b in ranges]}
+    return (reads_t,), (csr(rpa),), csr(apS), None, info
+
+
+def _oracle_logit_check(cfg, params, reads, aro, sao, ref, logits, n_check=32):
+    """Checker only (never timed): max |dlogit| of the first `n_check` sites against the CPU oracle."""
+    import torch
+    from oracle import hello_oracle as O
+    n = min(n_check, sao.numel() - 1)
+    a1 = int(sao[n])
+    tensors, nrpa = [], []
+    for t in range(len(cfg.read_cin)):
+        r1 = int(aro[t][a1])
+        tensors.append(reads[t][:r1].cpu().transpose(1, 2).contiguous())
+        nrpa.append(torch.diff(aro[t][:a1 + 1]).tolist())
+    if len(tensors) == 1:
+        tensors.append(None)
+        nrpa.append(None)
+    torch.set_num_threads(max(1, min(16, len(os.sched_getaffinity(0)))))
+    res = O.OracleModel(cfg, params).forward(tuple(tensors), torch.diff(sao[:n + 1]).tolist(), tuple(nrpa),
+                                             ref[:n].cpu() if ref is not None else None)
+    got = logits[:, :a1].cpu()
+    if cfg.returns_meta:
+        want = torch.stack([e.reshape(-1) for e in res[0]])
+        present = [e for e in range(3) if cfg.xattn_present[e]]
+        return float((got[present] - want[present]).abs().max()), n
+    head = 0 if cfg.xattn_present[0] else 2
+    return float((got[head] - res.reshape(-1)).abs().max()), n
+
+
+def run_other_workloads(args, dev, skip):
+    """BASELINE.json configs 3-5 next to the headline (config 2): each at --other-sites sites on this GPU, resident inputs,
+    2 timed steps after 1 warm-up; sites/s, share of the step spent in the read-convolver stage and max |dlogit| against the
+    CPU oracle on a sample.  Does not touch the headline fields."""
+    import torch
+    from hello_b200 import _lib, arch, model, weights
+    out = {}
+    for name in ("pacbio_hp_30x", "hybrid_no_ensemble_30x", "hybrid_ensemble2_30x", "wgs_ragged_15_60x"):
+        if name == skip:
+            continue
+        cfg_name, cov, desc = WORKLOADS[name]
+        cfg = arch.CONFIGS[cfg_name]
+        try:
+            params = weights.init_params(cfg, seed=13)
+            eng = model.MoEEngine(cfg, params, device=dev, precision=args.precision,
+                                  workspace_bytes=int(args.workspace_gb * (1 << 30)))
+            reads, aro, sao, ref = generate_on_device(cfg, cov, args.other_sites, dev, seed=4242)
+            batch = model.DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, aro, sao, ref, dev)
+            res = eng.alloc_result(batch)
+            eng.run(batch, res)
+            torch.cuda.synchronize(dev)
+            eng.profile_enable(True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                eng.run(batch, res)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1)
+            rc_ms, _ = eng.profile_collect()
+            eng.profile_enable(False)
+            f_read, f_allele, f_site = arch.flops_model(cfg)
+            R = [int(r.shape[0]) for r in reads]
+            flops = sum(R[t] * f_read[t] for t in range(len(R))) + batch.n_alleles * f_allele + batch.n_sites * f_site
+            err, n_checked = _oracle_logit_check(cfg, params, reads, aro, sao, ref, res.logits)
+            out[name] = {"description": desc, "wiring": cfg_name, "sites": batch.n_sites, "reads": R,
+                         "sites_per_sec": 2 * batch.n_sites / (ms / 1e3), "ms_per_step": ms / 2,
+                         "read_convolver_stage_share": rc_ms / ms if ms > 0 else None,
+                         "algorithmic_tflops": 2 * flops / (ms / 1e3) / 1e12,
+                         "max_abs_dlogit_vs_oracle": err, "oracle_sample_sites": n_checked}
+            eng.close()
+            del eng, batch, res, reads
+            torch.cuda.empty_cache()
+        except Exception as exc:                   # report, never hide
+            out[name] = {"error": repr(exc)[:300]}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -307,10 +439,21 @@ def run_ours(args):
     engine = model.MoEEngine(cfg, params, device=dev, precision=args.precision,
                              workspace_bytes=int(args.workspace_gb * (1 << 30)), max_chunk_sites=args.chunk_sites)
 
-    reads, aro, sao, ref = generate_on_device(cfg, cov, args.sites, dev, seed=13 + 1000 * rank)
+    partition_info = None
+    if args.partition == "balanced":
+        total_sites = args.total_sites or args.sites * world
+        reads, aro, sao, ref, partition_info = generate_balanced_shard(cfg, cov, total_sites, world, rank, dev, seed=13)
+    else:
+        reads, aro, sao, ref = generate_on_device(cfg, cov, args.sites, dev, seed=13 + 1000 * rank)
     batch = model.DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, aro, sao, ref, dev)
-    result = engine.alloc_result(batch)
     S, A = batch.n_sites, batch.n_alleles
+    gather = world > 1 and not args.no_gather
+    # N>1: the per-site results live in one packed buffer per rank (two slots), so the gather is ONE all_gather per step, queued
+    # on a side stream where it overlaps the next step's forward (shard.SiteGatherer)
+    gatherer = shard.SiteGatherer(dev).plan(S, A, batch.n_pairs) if gather else None
+    results = [engine.result_from_views(batch, gatherer.result_views(k)) for k in range(2)] if gather \
+        else [engine.alloc_result(batch)]
+    result = results[0]
     R = [int(r.shape[0]) for r in reads]
     input_gb = sum(r.numel() for r in reads) / 1e9
     f_read, f_allele, f_site = arch.flops_model(cfg)
@@ -330,16 +473,25 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    gather = world > 1 and not args.no_gather
+    step_no = [0]
+    fwd_events = []
 
-    def step():
+    def step(timed=False):
         """One pass of the hot path over this rank's shard; with N>1 the per-site results are then gathered over
         NCCL (the only collective of the path -- nothing is exchanged inside the forward)."""
-        engine.run(batch, result)
+        slot = step_no[0] % len(results)
+        step_no[0] += 1
         if gather:
-            return shard.gather_site_results(result.best_pair, result.best_prob, result.meta, result.pair_prob,
-                                             result.pair_mix64, result.logits)
-        return None
+            gatherer.before_overwrite(slot)          # the gather of two steps ago has finished reading this slot
+        if timed:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        engine.run(batch, results[slot])
+        if timed:
+            b.record()
+            fwd_events.append((a, b))
+        if gather:
+            gatherer.gather_async(slot)
 
     # ---- value: inputs resident in HBM ---------------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -352,7 +504,9 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
-        step()
+        step(timed=True)
+    if gather:
+        gatherer.wait()                              # every queued gather is inside the timed region
     ev1.record()
     barrier()
     clocks = sampler.stop()
@@ -360,7 +514,22 @@ def run_ours(args):
     launches = engine.launch_count() - launches0
     rc_ms, rc_regions = engine.profile_collect()
     engine.profile_enable(False)
-    value = world * S * args.steps / (ms_total / 1e3)
+    sites_all = S
+    if world > 1:
+        t = torch.tensor([S], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        sites_all = int(t.item())
+    value = (sites_all if args.partition == "balanced" else world * S) * args.steps / (ms_total / 1e3)
+    # per-rank forward time (load balance of the partition): mean over the timed steps, gathered to every rank
+    my_fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_events) / max(len(fwd_events), 1)
+    rank_ms = [my_fwd_ms]
+    if world > 1:
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = my_fwd_ms
+        dist.all_reduce(t)
+        rank_ms = [float(x) for x in t.tolist()]
+    if partition_info is not None:
+        partition_info.update(rank_forward_ms=rank_ms, imbalance_max_over_mean=max(rank_ms) / (sum(rank_ms) / len(rank_ms)))
 
     # ---- e2e: host buffers, copies inside the timed region -------------------------------------------------------
     e2e = None
@@ -387,7 +556,8 @@ def run_ours(args):
         hb = model.HostBatch([pinned_copy(r, int(aro[t][a_e])) for t, r in enumerate(reads)], _lib.LAYOUT_RLC,
                              [o[:a_e + 1].clone() for o in aro], sao[:S_e + 1].clone(),
                              pinned_copy(ref, S_e) if ref is not None else None, pin=True)
-        del batch, reads
+        del batch, reads, results, result
+        gatherer = None
         torch.cuda.empty_cache()
         engine.forward_host(hb, args.e2e_chunk_sites)                       # warm-up (allocations, pinned outputs)
         barrier()
@@ -397,7 +567,12 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * S_e * args.steps / dt, "unit": "sites/s", "h2d_bytes_per_step": hb.input_nbytes(),
+        S_e_all = S_e
+        if world > 1 and args.partition == "balanced":
+            t = torch.tensor([S_e], dtype=torch.int64, device=dev)
+            dist.all_reduce(t)
+            S_e_all = int(t.item())
+        e2e = {"value": (S_e_all if args.partition == "balanced" else world * S_e) * args.steps / dt, "unit": "sites/s", "h2d_bytes_per_step": hb.input_nbytes(),
                "d2h_bytes_per_step": out.nbytes(), "sites_per_gpu": S_e,
                "api": "MoEEngine.forward_host (pinned host buffers, read rows streamed in %d-site ranges on a copy "
                       "stream while the previous range computes)" % args.e2e_chunk_sites}
@@ -453,21 +628,35 @@ def run_ours(args):
             cpu_baseline = json.loads(out_.stdout.strip().splitlines()[-1])["cpu_baseline"]
         except Exception as exc:  # report, never hide
             cpu_baseline = {"error": repr(exc)[:200]}
+    other = None
+    if world == 1 and not args.no_other_workloads:
+        batch = reads = results = result = hb = out = None          # release the headline workload (HBM and pinned host memory)
+        engine.close()
+        torch.cuda.empty_cache()
+        other = run_other_workloads(args, dev, skip=args.workload)
+    scaling = "weak" if (args.partition != "balanced" or not args.total_sites) else "strong"
     line = {
         "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / max(args.steps, 1), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": scaling, "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": "%s_%dk_sites_per_gpu" % (args.workload, args.sites // 1000), "wiring": cfg_name,
                    "weights": "random-init (seed 13), shipped blobs are git-lfs pointers", "sites_per_gpu": S,
                    "alleles_per_gpu": A, "reads_per_gpu": R, "coverage": cov, "precision": args.precision,
-                   "partition": "sites sharded across ranks, no collective inside the forward" +
-                                (", NCCL all_gather of per-site results each step" if gather else ""),
+                   "partition": ("one dataset cut into contiguous site ranges of equal algorithmic cost, " if partition_info
+                                 else "every rank scores its own sites, ") + "no collective inside the forward" +
+                                (", ONE packed NCCL all_gather of the per-site results per step on a side stream "
+                                 "(overlaps the next step's forward)" if gather else ""),
                    "l2": "inputs (%.1f GB per step) are far larger than L2; no flush needed" % input_gb,
                    "flops_per_step_per_gpu": flops_step},
         "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "rank_forward_ms": rank_ms,
     }
+    if partition_info is not None:
+        line["partition"] = partition_info
+    if other is not None:
+        line["other_workloads"] = other
     text = json.dumps(line)
     print(text, flush=True)
     print("bench.py: rank 0 wrote the result line (%d bytes)" % len(text), file=sys.stderr, flush=True)

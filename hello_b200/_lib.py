@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhello_moe.so")
+# HELLO_MOE_LIB: developer hook for A/B runs of two builds of the library on one GPU box (tools/ab/); never a CPU path.
+LIB_PATH = os.environ.get("HELLO_MOE_LIB") or os.path.join(HERE, "libhello_moe.so")
 ABI_VERSION = 3
 
 LAYOUT_RCL, LAYOUT_RLC = 0, 1

@@ -208,6 +208,18 @@ class MoEEngine:
             call_qual=torch.empty((S, 5), dtype=torch.float64, device=dev),
             best_expert=torch.empty((S,), dtype=torch.int32, device=dev))
 
+    def result_from_views(self, b: DeviceBatch, views: Dict[str, torch.Tensor]) -> BatchResult:
+        """A BatchResult whose tensors are caller-provided views (e.g. shard.SiteGatherer.result_views: one packed buffer
+        per rank, so that the multi-GPU gather is a single collective)."""
+        dev, A, S, P = self.device, b.n_alleles, b.n_sites, b.n_pairs
+        want = {"logits": (3, A), "meta": (S, 3), "pair_prob": (4, P), "pair_mix64": (P,), "best_pair": (S, 2),
+                "best_prob": (S,), "call_pair": (S, 5, 2), "call_qual": (S, 5), "best_expert": (S,)}
+        for k, shp in want.items():
+            t = views[k]
+            if tuple(t.shape) != shp or t.device != dev or not t.is_contiguous():
+                raise ValueError("result view %s has shape %s on %s, expected %s on %s" % (k, tuple(t.shape), t.device, shp, dev))
+        return BatchResult(pair_off=b.pair_off_h, **{k: views[k] for k in want})
+
     def _abi_structs(self, b: DeviceBatch, out: BatchResult):
         n_tech = len(self.cfg.read_cin)
         if len(b.reads) < n_tech:

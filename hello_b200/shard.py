@@ -20,11 +20,20 @@ import torch.distributed as dist
 from . import arch
 
 
-def site_costs(cfg: arch.ModelConfig, site_allele_off: np.ndarray, allele_read_offs: Sequence[np.ndarray]) -> np.ndarray:
-    """Algorithmic FLOPs of every site: sum_t R_t*F_read_t + A*F_allele + F_site."""
+def site_costs(cfg: arch.ModelConfig, site_allele_off: np.ndarray, allele_read_offs: Optional[Sequence[np.ndarray]] = None,
+               reads_per_site: Optional[Sequence[np.ndarray]] = None) -> np.ndarray:
+    """Algorithmic FLOPs of every site: sum_t R_t*F_read_t + A*F_allele + F_site.  The reads of a
+    site are given either through the allele CSR (`allele_read_offs`, [A+1] per technology) or directly
+    (`reads_per_site`, [S] per technology)."""
     f_read, f_allele, f_site = arch.flops_model(cfg)
     sao = np.asarray(site_allele_off, dtype=np.int64)
     cost = np.diff(sao).astype(np.float64) * f_allele + f_site
+    if (allele_read_offs is None) == (reads_per_site is None):
+        raise ValueError("give exactly one of allele_read_offs / reads_per_site")
+    if reads_per_site is not None:
+        for t, rps in enumerate(reads_per_site):
+            cost += np.asarray(rps, dtype=np.float64) * f_read[t]
+        return cost
     for t, aro in enumerate(allele_read_offs):
         aro = np.asarray(aro, dtype=np.int64)
         cost += (aro[sao[1:]] - aro[sao[:-1]]).astype(np.float64) * f_read[t]
@@ -74,49 +83,169 @@ def take_shard(site_allele_off: torch.Tensor, allele_read_off: Sequence[torch.Te
     return SiteShard(s0, s1, (sao[s0:s1 + 1] - a0).to(torch.int32), tuple(offs), tuple(rr), (a0, a1))
 
 
-def _all_gather_ragged(x: torch.Tensor, group=None) -> torch.Tensor:
-    """Concatenate a per-rank tensor whose first dimension differs across ranks (counts exchanged first)."""
-    world = dist.get_world_size(group)
-    n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
-    counts = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
-    cap = max(counts) if counts else 0
-    if cap == 0:
-        return x[:0]
-    pad = torch.zeros((cap,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
-    pad[:x.shape[0]] = x
-    bufs = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+# ------------------------------------------------------------------------------------------------ packed gather
+# The per-site results of a rank live in ONE contiguous buffer (PackedSiteResults: the nine result tensors of
+# hello_moe_forward are views into it), so gathering them is ONE collective: counts are exchanged once per batch shape,
+# then every step does a single all_gather of `cap` bytes per rank -- on a side stream when asked, so that it overlaps the
+# next step's forward.  (Round 1 did twelve list-form all_gathers per step, padded and re-concatenated, on the compute
+# stream: 2 % of an 8-GPU step.)
+RESULT_FIELDS = (
+    # name, dtype, shape as a function of (S, A, P)
+    ("logits", torch.float32, lambda S, A, P: (3, A)),
+    ("meta", torch.float32, lambda S, A, P: (S, 3)),
+    ("pair_prob", torch.float32, lambda S, A, P: (4, P)),
+    ("pair_mix64", torch.float64, lambda S, A, P: (P,)),
+    ("best_pair", torch.int32, lambda S, A, P: (S, 2)),
+    ("best_prob", torch.float32, lambda S, A, P: (S,)),
+    ("call_pair", torch.int32, lambda S, A, P: (S, 5, 2)),
+    ("call_qual", torch.float64, lambda S, A, P: (S, 5)),
+    ("best_expert", torch.int32, lambda S, A, P: (S,)),
+)
+_ALIGN = 256
+
+
+def packed_layout(S: int, A: int, P: int):
+    """-> ({name: (byte offset, shape, dtype)}, total bytes) of one rank's packed per-site results."""
+    off, out = 0, {}
+    for name, dt, shape in RESULT_FIELDS:
+        shp = shape(S, A, P)
+        n = int(np.prod(shp)) * torch.empty(0, dtype=dt).element_size()
+        out[name] = (off, shp, dt)
+        off = (off + n + _ALIGN - 1) // _ALIGN * _ALIGN
+    return out, max(off, _ALIGN)
+
+
+def packed_views(buf: torch.Tensor, S: int, A: int, P: int):
+    """The nine result tensors as views into a uint8 buffer laid out by packed_layout."""
+    layout, total = packed_layout(S, A, P)
+    if buf.numel() < total:
+        raise ValueError("packed result buffer too small")
+    out = {}
+    for name, (off, shp, dt) in layout.items():
+        n = int(np.prod(shp)) * torch.empty(0, dtype=dt).element_size()
+        out[name] = buf[off:off + n].view(dt).reshape(shp)
+    return out
 
 
 @dataclass
 class GatheredSites:
+    """Results of all ranks, sites in global order (rank order == site order because shards are contiguous)."""
     best_pair: torch.Tensor    # int32 [S, 2]
     best_prob: torch.Tensor    # fp32 [S]
     meta: torch.Tensor         # fp32 [S, 3]
-    pair_prob: torch.Tensor    # fp32 [P, 4]  (mixed, P_e0, P_e1, P_e2) per genotype pair, sites in global order
+    pair_prob: torch.Tensor    # fp32 [4, P]  (mixed, P_e0, P_e1, P_e2) per genotype pair
     pair_mix64: torch.Tensor   # fp64 [P]
-    logits: torch.Tensor       # fp32 [A, 3]
+    logits: torch.Tensor       # fp32 [3, A]
+    call_pair: Optional[torch.Tensor] = None     # int32 [S, 5, 2]
+    call_qual: Optional[torch.Tensor] = None     # fp64 [S, 5]
+    best_expert: Optional[torch.Tensor] = None   # int32 [S]
+
+
+class SiteGatherer:
+    """One all_gather per step for the per-site results of every rank.
+
+        g = SiteGatherer(device)                       # after init_process_group
+        g.plan(S_r, A_r, P_r)                          # once per batch shape: exchanges the counts, allocates buffers
+        res = g.result_views(slot)                     # dict of tensors to hand to hello_moe_forward (slot 0 / 1)
+        g.gather_async(slot)                           # after the forward was queued on the current stream
+        ...                                            # next step's forward into the other slot overlaps the gather
+        g.wait(); all_ranks = g.concat(slot)           # when the gathered results are needed
+
+    Works with NCCL (device tensors, side stream) and gloo (CPU tensors, synchronous) alike."""
+
+    def __init__(self, device, group=None, slots: int = 2):
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.slots = slots
+        self.cuda = self.device.type == "cuda"
+        self.stream = torch.cuda.Stream(self.device) if self.cuda else None
+        self.counts = None
+        self.collectives = 0
+
+    def plan(self, S: int, A: int, P: int):
+        mine = torch.tensor([S, A, P], dtype=torch.int64, device=self.device)
+        if self.world > 1:
+            allc = torch.empty(self.world * 3, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(allc, mine, group=self.group)
+            self.collectives += 1
+            self.counts = [tuple(int(x) for x in row) for row in allc.reshape(self.world, 3).cpu().tolist()]
+        else:
+            self.counts = [(S, A, P)]
+        self.cap = max(packed_layout(*c)[1] for c in self.counts)
+        self.local = [torch.zeros(self.cap, dtype=torch.uint8, device=self.device) for _ in range(self.slots)]
+        self.gathered = [torch.empty(self.world * self.cap, dtype=torch.uint8, device=self.device)
+                         for _ in range(self.slots)] if self.world > 1 else self.local
+        self._done = [None] * self.slots
+        return self
+
+    def result_views(self, slot: int = 0):
+        S, A, P = self.counts[self.rank]
+        return packed_views(self.local[slot], S, A, P)
+
+    def gather_async(self, slot: int = 0):
+        """Queue the gather of `slot` behind the work already queued on the current stream; returns at once."""
+        if self.world == 1:
+            return
+        if self.cuda:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ready)
+                dist.all_gather_into_tensor(self.gathered[slot], self.local[slot], group=self.group)
+                done = torch.cuda.Event()
+                done.record(self.stream)
+            self._done[slot] = done
+        else:
+            dist.all_gather_into_tensor(self.gathered[slot], self.local[slot], group=self.group)
+        self.collectives += 1
+
+    def before_overwrite(self, slot: int):
+        """Order the work queued next on the current stream (the forward that refills `slot`) behind the gather that is
+        still reading it; no host wait."""
+        if self._done[slot] is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done[slot])
+
+    def wait(self, slot: Optional[int] = None):
+        """Make the current stream (and the host) wait for the queued gathers."""
+        for k in range(self.slots) if slot is None else [slot]:
+            if self._done[k] is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._done[k])
+                self._done[k].synchronize()
+                self._done[k] = None
+
+    def rank_views(self, slot: int, rank: int):
+        """Zero-copy views of the results `rank` contributed to the gathered buffer of `slot`."""
+        buf = self.gathered[slot][rank * self.cap:(rank + 1) * self.cap] if self.world > 1 else self.local[slot]
+        return packed_views(buf, *self.counts[rank])
+
+    def concat(self, slot: int = 0) -> GatheredSites:
+        """All ranks' results concatenated in site order (copies; the per-rank views are there for zero-copy use)."""
+        v = [self.rank_views(slot, r) for r in range(self.world)]
+        cat = lambda name, dim=0: torch.cat([x[name] for x in v], dim=dim)
+        return GatheredSites(best_pair=cat("best_pair"), best_prob=cat("best_prob"), meta=cat("meta"),
+                             pair_prob=cat("pair_prob", 1), pair_mix64=cat("pair_mix64"), logits=cat("logits", 1),
+                             call_pair=cat("call_pair"), call_qual=cat("call_qual"), best_expert=cat("best_expert"))
 
 
 def gather_site_results(best_pair: torch.Tensor, best_prob: torch.Tensor, meta: torch.Tensor,
                         pair_prob: torch.Tensor, pair_mix64: torch.Tensor, logits: torch.Tensor,
                         group=None) -> GatheredSites:
-    """All-gather the per-site results of every rank (rank order == site order because shards are contiguous).
-    Inputs are this rank's tensors: best_pair [S_r,2], best_prob [S_r], meta [S_r,3], pair_prob [4,P_r],
-    pair_mix64 [P_r], logits [3,A_r]."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return GatheredSites(best_pair, best_prob, meta, pair_prob.t().contiguous(), pair_mix64,
-                             logits.t().contiguous())
-    return GatheredSites(
-        best_pair=_all_gather_ragged(best_pair.contiguous(), group),
-        best_prob=_all_gather_ragged(best_prob.contiguous(), group),
-        meta=_all_gather_ragged(meta.contiguous(), group),
-        pair_prob=_all_gather_ragged(pair_prob.t().contiguous(), group),
-        pair_mix64=_all_gather_ragged(pair_mix64.contiguous(), group),
-        logits=_all_gather_ragged(logits.t().contiguous(), group))
+    """Convenience form for results that are NOT already packed: copies this rank's tensors (best_pair [S_r,2],
+    best_prob [S_r], meta [S_r,3], pair_prob [4,P_r], pair_mix64 [P_r], logits [3,A_r]) into a packed buffer, then one
+    count exchange + one all_gather.  Steady-state callers use SiteGatherer with result_views() directly."""
+    S, A, P = int(best_pair.shape[0]), int(logits.shape[1]), int(pair_mix64.shape[0])
+    g = SiteGatherer(best_pair.device, group=group, slots=1).plan(S, A, P)
+    v = g.result_views(0)
+    for name, t in (("best_pair", best_pair), ("best_prob", best_prob), ("meta", meta), ("pair_prob", pair_prob),
+                    ("pair_mix64", pair_mix64), ("logits", logits)):
+        v[name].copy_(t)
+    g.gather_async(0)
+    g.wait()
+    out = g.concat(0)
+    out.call_pair = out.call_qual = out.best_expert = None          # not supplied by this form
+    return out
 
 
 def parse_cpulist(text: str) -> List[int]:

@@ -179,6 +179,23 @@ def make_pileups(n_sites: int, coverage=30, channels=(6,), seed: int = 13, devic
     return Pileups(tuple(reads), tuple(offs), sao, onehot)
 
 
+def site_counts(n_sites: int, coverage=30, channels=(6,), seed: int = 13, device="cpu"):
+    """(alleles per site, reads per site) of make_pileups(n_sites, coverage, channels, seed, device) WITHOUT building the read
+    tensors: replays the head of the same random stream.  Used to cut a large synthetic dataset into balanced shards before
+    any rank generates its own part (bench.py --partition balanced).  Single-technology workloads only: the counts of a
+    second technology come after the first one's read bytes in the stream."""
+    if len(channels) != 1:
+        raise ValueError("site_counts replays the stream of a single-technology workload")
+    device = torch.device(device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    torch.randint(0, 4, (n_sites, FEATURE_LENGTH), generator=gen, device=device)              # ref_idx
+    torch.rand(n_sites, generator=gen, device=device)                                         # span_len
+    torch.randint(2, 11, (n_sites,), generator=gen, device=device)
+    na, nr, _ = _counts(n_sites, coverage, gen, device, allow_empty_tech=False)
+    return na, torch.maximum(nr, na)
+
+
 def pair_offsets(site_allele_off: torch.Tensor) -> torch.Tensor:
     """int64 [S+1] prefix sum of A_s(A_s+1)/2 -- number of unordered genotype pairs per site."""
     n = torch.diff(site_allele_off.long())

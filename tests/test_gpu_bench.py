@@ -15,7 +15,7 @@ def test_bench_line_contract():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--sites", "4096", "--steps", "2", "--warmup", "3",
-                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+                          "--no-cpu-baseline", "--other-sites", "2048"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-800:]
     lines = out.stdout.splitlines()
     assert len(lines) == 1, lines
@@ -34,3 +34,26 @@ def test_bench_line_contract():
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1 / 3 + 1e-6
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # BASELINE configs 3-5 ride along without touching the headline fields
+    ow = d["other_workloads"]
+    assert set(ow) == {"pacbio_hp_30x", "hybrid_no_ensemble_30x", "hybrid_ensemble2_30x", "wgs_ragged_15_60x"}
+    for name, w in ow.items():
+        assert "error" not in w, (name, w)
+        assert w["sites"] == 2048 and w["sites_per_sec"] > 0 and 0 < w["read_convolver_stage_share"] < 1
+        assert w["max_abs_dlogit_vs_oracle"] < 1e-3 and w["oracle_sample_sites"] == 32
+
+
+def test_bench_balanced_partition_single_rank():
+    """--partition balanced on one rank: the whole deterministic dataset is this rank's shard; the line carries the
+    partition record (ranges, cost shares, per-rank forward time)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "wgs_ragged_15_60x", "--partition",
+                          "balanced", "--total-sites", "20000", "--steps", "2", "--warmup", "3", "--no-cpu-baseline",
+                          "--no-other-workloads", "--no-e2e"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-800:]
+    d = json.loads(out.stdout.splitlines()[-1])
+    p = d["partition"]
+    assert p["mode"] == "balanced" and p["total_sites"] == 20000 and p["site_ranges"] == [[0, 20000]]
+    assert abs(sum(p["cost_share"]) - 1.0) < 1e-9 and len(p["rank_forward_ms"]) == 1
+    assert d["config"]["sites_per_gpu"] == 20000 and d["scaling"] == "strong"

@@ -78,8 +78,8 @@ def _worker(rank, world, port, cfg_name, n_sites, out_path):
             bp, bq, meta, pair, mix64, logits = _forward_shard(cfg, params, pl, whole)
             close = lambda a, b: a.shape == b.shape and torch.allclose(a, b, rtol=0, atol=2e-4)
             ok = (torch.equal(got.best_pair, bp) and close(got.best_prob, bq) and close(got.meta, meta)
-                  and close(got.pair_prob, pair.t()) and close(got.pair_mix64, mix64)
-                  and close(got.logits, logits.t()))
+                  and close(got.pair_prob, pair) and close(got.pair_mix64, mix64)
+                  and close(got.logits, logits))
             with open(out_path, "w") as f:
                 f.write("ok" if ok else "mismatch")
     finally:
@@ -115,3 +115,57 @@ def test_site_costs_follow_the_flop_model():
     aro = np.array([0, 5, 9, 10])
     cost = shard.site_costs(cfg, sao, [aro])
     assert cost.tolist() == [9 * f_read[0] + 2 * f_allele + f_site, 1 * f_read[0] + 1 * f_allele + f_site]
+
+
+def _gatherer_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # ragged shard sizes, one rank without sites
+        shapes = [(5, 8, 13), (0, 0, 0), (3, 4, 5)][:world]
+        S, A, P = shapes[rank]
+        g = shard.SiteGatherer("cpu", slots=2).plan(S, A, P)
+        ok = g.collectives == 1
+        for step in range(3):                       # steady state: one collective per step, alternating slots
+            slot = step % 2
+            v = g.result_views(slot)
+            for k, (name, dt, _) in enumerate(shard.RESULT_FIELDS):
+                v[name].copy_((torch.arange(v[name].numel()).reshape(v[name].shape) + 1000 * rank + 10 * k + step).to(dt))
+            before = g.collectives
+            g.gather_async(slot)
+            g.wait()
+            ok = ok and g.collectives == before + 1
+            got = g.concat(slot)
+            for r in range(world):
+                rv = g.rank_views(slot, r)
+                Sr, Ar, Pr = shapes[r]
+                ok = ok and rv["logits"].shape == (3, Ar) and rv["pair_prob"].shape == (4, Pr) and rv["call_pair"].shape == (Sr, 5, 2)
+                for k, (name, dt, _) in enumerate(shard.RESULT_FIELDS):
+                    want = (torch.arange(rv[name].numel()).reshape(rv[name].shape) + 1000 * r + 10 * k + step).to(dt)
+                    ok = ok and torch.equal(rv[name], want)
+            ok = ok and got.best_pair.shape == (sum(s[0] for s in shapes), 2) and got.logits.shape == (3, sum(s[1] for s in shapes))
+            ok = ok and got.pair_prob.shape == (4, sum(s[2] for s in shapes)) and got.call_qual.dtype == torch.float64
+        if rank == 0:
+            with open(out_path, "w") as f:
+                f.write("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_packed_gather_is_one_collective_per_step(tmp_path, world):
+    """SiteGatherer: the nine per-site result tensors are views into one buffer per rank, the counts are exchanged once,
+    every step is a single all_gather, ragged (and empty) shards come back in rank == site order."""
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_gatherer_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert open(out).read() == "ok"
+
+
+def test_packed_layout_is_aligned_and_disjoint():
+    layout, total = shard.packed_layout(7, 11, 19)
+    spans = sorted((off, off + int(np.prod(shp)) * torch.empty(0, dtype=dt).element_size()) for off, shp, dt in layout.values())
+    assert all(a[1] <= b[0] for a, b in zip(spans[:-1], spans[1:])) and spans[-1][1] <= total
+    assert all(off % 256 == 0 for off, _, _ in layout.values())
+    v = shard.packed_views(torch.zeros(total, dtype=torch.uint8), 7, 11, 19)
+    assert v["pair_mix64"].dtype == torch.float64 and v["pair_mix64"].shape == (19,) and v["call_pair"].shape == (7, 5, 2)
