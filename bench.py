@@ -65,6 +65,9 @@ def parse_args():
     ap.add_argument("--chunk-sites", type=int, default=0, help="cap on sites per internal chunk (0 = auto)")
     ap.add_argument("--e2e-chunk-sites", type=int, default=0, help="sites per streamed range (0 = min(65536, sites/8))")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-packed", action="store_true",
+                    help="skip the second end-to-end figure (aligned reads on the host, rows encoded on the GPU)")
+    ap.add_argument("--e2e-packed-sites", type=int, default=262144, help="sites per GPU of the e2e_packed leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sites", type=int, default=0, help="sites per CPU step (0 = 128 per worker)")
     ap.add_argument("--cpu-workers", type=int, default=0)
@@ -579,6 +582,40 @@ def run_ours(args):
         if numa_cpus is not None:
             e2e["host_binding"] = "rank 0 runs on %d cores local to its GPU (pinned buffers first-touched there)" % len(numa_cpus)
 
+    # ---- e2e_packed: the host holds ALIGNED READS (what exists right after read sampling); the GPU encodes the rows --------
+    e2e_packed = None
+    if not args.no_e2e and not args.no_e2e_packed and len(cfg.read_cin) == 1 and not isinstance(cov, tuple):
+        import numpy as np
+        from hello_b200 import synth as _synth
+        batch = reads = results = result = hb = out = None
+        torch.cuda.empty_cache()
+        gen_sites = 32768
+        times = max(1, min(args.e2e_packed_sites, S) // gen_sites)
+        packed, rr, rs = _synth.make_packed_reads(gen_sites, coverage=cov, seed=13 + rank, hp=cfg.read_cin[0] == 7)
+        aro_p, sao_p = _synth.packed_allele_csr(np.diff(packed.read_base), seed=13 + rank)
+        packed, rr, rs = _synth.tile_packed_reads(packed, rr, rs, times)
+        rep = lambda off: torch.cat([off[:-1].long() + k * int(off[-1]) for k in range(times)] +
+                                    [torch.tensor([times * int(off[-1])])]).to(torch.int32)
+        hpb = model.HostPackedBatch(packed, (rr,), (rs,), (rep(aro_p),), rep(sao_p), pin=True)
+        S_p = hpb.n_sites
+        chunk_p = max(8192, min(65536, S_p // 8))
+        engine.forward_host_packed(hpb, chunk_p)                           # warm-up (allocations, pinned outputs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out_p = engine.forward_host_packed(hpb, chunk_p)
+            torch.cuda.synchronize(dev)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e_packed = {"value": world * S_p * args.steps / dt, "unit": "sites/s", "h2d_bytes_per_step": hpb.input_nbytes(),
+                      "d2h_bytes_per_step": out_p.nbytes(), "sites_per_gpu": S_p, "rows_per_gpu": int(rr.size),
+                      "h2d_bytes_per_row": hpb.input_nbytes() / max(int(rr.size), 1),
+                      "api": "MoEEngine.forward_host_packed (pinned host buffers of aligned reads -- bases, qualities, CIGARs, "
+                             "reference windows -- streamed in %d-site ranges; hello_encode_reads builds the [R,150,C] rows "
+                             "on the GPU; then hello_moe_forward_range)" % chunk_p,
+                      "data": "%d generated sites (synth.make_packed_reads) tiled %d times" % (gen_sites, times)}
+        hpb = out_p = None
+
     if rank != 0:
         print("bench.py: rank %d of %d done" % (rank, world), file=sys.stderr, flush=True)
         if world > 1:
@@ -650,8 +687,8 @@ def run_ours(args):
                                  "(overlaps the next step's forward)" if gather else ""),
                    "l2": "inputs (%.1f GB per step) are far larger than L2; no flush needed" % input_gb,
                    "flops_per_step_per_gpu": flops_step},
-        "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "rank_forward_ms": rank_ms,
+        "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "e2e_packed": e2e_packed, "roofline": roofline,
+        "cpu_baseline": cpu_baseline, "rank_forward_ms": rank_ms,
     }
     if partition_info is not None:
         line["partition"] = partition_info

@@ -14,6 +14,14 @@
 //   the unused rows of each pitch are kept at zero and double as the zero padding of the pad=1 convolutions.
 //   Stride-2 layers (MaxPool1d(3,2), the stride-2 residual block) read an even/odd de-interleaved copy that the
 //   previous epilogue writes, which turns stride 2 back into unit row shifts.
+//   The 32-channel stage (length 71) is run SPACE-TO-DEPTH: row r of a read holds positions 2r and 2r+1 side by side
+//   (64 "channels": [even 32 | odd 32], 36 rows per read, pitch 40 like the 64-channel stage), so a layer is ONE 128-row
+//   tile with N = 64 instead of two tiles with N = 32.  The k=3 convolution becomes a centre tap with K = 64 (all four
+//   parity blocks non-zero) plus two half taps with K = 32, N = 32 (x[2r-1] only feeds the even output, x[2r+2] only the
+//   odd one): no wasted MACs, and the 4 KB activation tile -- the dominant operand cost at small N -- is fetched 16 times
+//   per layer instead of 24 (800 instead of 1056 tensor-pipe cycles per group and layer).  The max-pool that opens the
+//   stage produces this layout directly: stem conv 3 is evaluated at positions 4r .. 4r+3 into four accumulators per row
+//   from a mod-4 de-interleaved copy of the stem conv 2 output.
 //
 // Pipeline (one CTA per SM, 16 warps, three independent groups of 3 reads in flight)
 //   warps 0-11       epilogue warpgroup of read group warp/4 (thread = packed row = TMEM lane): TMEM -> registers
@@ -71,12 +79,12 @@ constexpr int THREADS = (NG * EW + NG + 1) * 32;
 // byte layout of one group's activation buffer (offsets relative to its base)
 constexpr uint32_t X_STRIDE = (ROWS1 + 8) * 16;   // layer-1 operand: X0[m] = x[m], X1[m] = x[m+1]  (8 ch, hi only)
 constexpr uint32_t A1_CH = (ROWS1 + 2) * 16;      // layer-1 output: 2 chunks, natural rows
-constexpr uint32_t A2_ARR = (ROWS2 + 2) * 16;     // layer-2 output: (chunk, parity) arrays, pitch 80
-constexpr uint32_t S2_CH = (ROWS2 + 2) * 16;      // 32-channel stage: 4 chunks, lead zero row
+constexpr uint32_t Q4_ARR = (ROWS3 + 2) * 16;     // layer-2 output de-interleaved mod 4: (chunk, position & 3) arrays, pitch 40
+constexpr uint32_t D2_ARR = (ROWS3 + 2) * 16;     // 32-channel stage, space-to-depth: (chunk, parity) arrays, pitch 40, lead zero row
 constexpr uint32_t E3_ARR = (ROWS3 + 2) * 16;     // stage-2 output de-interleaved: (chunk, parity), pitch 40, lead row
 constexpr uint32_t S3_CH = (ROWS3 + 2) * 16;      // 64-channel stage: 8 chunks, lead zero row
-constexpr uint32_t XCHG_OFF = 16 * S3_CH;         // T2*4 x 32 floats for the max-pool row exchange
-constexpr uint32_t ACT_BYTES = XCHG_OFF + T2 * 4 * 128;
+constexpr uint32_t XCHG_OFF = 16 * S3_CH;         // 4 x 32 floats for the max-pool row exchange (first row of every warp slice)
+constexpr uint32_t ACT_BYTES = XCHG_OFF + 8 * 128;
 constexpr uint32_t WSLOT_BYTES = 49152;
 
 constexpr uint32_t OFF_ACT = 0;
@@ -94,7 +102,7 @@ constexpr uint32_t STG_BYTES = 3712;                   // >= 15 + G * LIN * 8 ro
 constexpr uint32_t OFF_STG = (OFF_SUM + LOUT * COUT * 4 + 127) & ~127u;
 constexpr uint32_t SMEM_BYTES = OFF_STG + NG * STG_BYTES;
 static_assert(SMEM_BYTES <= 232448 && OFF_SUM % 16 == 0 && STG_BYTES >= 16 + G * LIN * 8, "shared memory budget");
-static_assert(2 * A1_CH * 2 <= XCHG_OFF && 8 * A2_ARR <= XCHG_OFF && 8 * S2_CH <= XCHG_OFF &&
+static_assert(2 * A1_CH * 2 <= XCHG_OFF && 16 * Q4_ARR <= XCHG_OFF && 16 * D2_ARR <= XCHG_OFF && D2_ARR == E3_ARR &&
               16 * E3_ARR <= XCHG_OFF && 16 * S3_CH <= XCHG_OFF && 2 * X_STRIDE <= XCHG_OFF, "activation layouts");
 static_assert(T1 * 128 >= ROWS1 && T2 * 128 >= ROWS2 && T3 * 128 >= ROWS3, "tiles cover the packed rows");
 static_assert(T1 * 32 <= RES_COL && T2 * 64 <= RES_COL && T3 * 128 <= RES_COL && RES_COL + 32 <= GRP_COLS &&
@@ -127,9 +135,14 @@ struct TcParams {
 // Packed weights.  One B unit covers one tap and 16 input channels: [2 chunks of 8 channels][rows][8 bf16] with
 // rows = the N "hi" weight rows followed (bf16x3 only) by the N "lo" rows.  Units of a phase are stored tap-major.
 template <int MODE> __host__ __device__ constexpr uint32_t unit_bytes(int n) { return (MODE == 3 ? 2u : 1u) * n * 32u; }
-constexpr int UNITS_L1 = 2, UNITS_L2 = 3, UNITS_L3 = 3, UNITS_S2 = 6, UNITS_RC = 8, UNITS_S3 = 12;
+constexpr int UNITS_L1 = 2, UNITS_L2 = 3, UNITS_L3 = 3, UNITS_RC = 8, UNITS_S3 = 12;
+// Space-to-depth 32-channel layer: 4 centre units (input parity x two 16-channel steps) covering both output parities,
+// then 2 + 2 half units (tap -1: odd input -> even output; tap +1: even input -> odd output).
+constexpr int UNITS_S2_FULL = 4, UNITS_S2_HALF = 4;
+template <int MODE> __host__ __device__ constexpr uint32_t s2d_full_bytes() { return (MODE == 3 ? 128u : 64u) * 32u; }
+template <int MODE> __host__ __device__ constexpr uint32_t s2d_half_bytes() { return (MODE == 3 ? 64u : 32u) * 32u; }
 
-enum { OUT_NAT = 0, OUT_EO = 1, OUT_GLOBAL = 2 };
+enum { OUT_NAT = 0, OUT_EO = 1, OUT_GLOBAL = 2, OUT_Q4 = 3 };
 
 // ------------------------------------------------------------------------------------------------ device side
 template <int MODE>
@@ -222,8 +235,12 @@ __device__ __forceinline__ void store_rows(uint8_t* act, const uint32_t (&raw)[I
 //   STACK: the layer was issued in the stacked form (two accumulator halves per tile).
 //   MOVE_SC (stride-2 block): the shortcut accumulators sit next to conv a's in columns [64,128); move them to
 //   the residual storage before the next layer reuses the accumulator columns.
+//   S2D (32-channel stage, space-to-depth): the row holds two positions, block = (parity, 16-channel half); the
+//   accumulator columns are [hl even | hh even | hh odd | hl odd] (bf16x3) or [even | odd] (bf16), see issue_stage2_s2d;
+//   LVALID counts rows of the even positions, the odd ones have one fewer.
+//   OUT_Q4 (stem conv 2): output rows de-interleaved mod 4 into (chunk, position & 3) arrays of pitch P3.
 template <int MODE, bool STACK, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID,
-          bool MOVE_SC, int OUT, int LEAD>
+          bool MOVE_SC, int OUT, int LEAD, bool S2D = false>
 __device__ __forceinline__ void epi_conv(const TcParams& prm, uint8_t* act, uint32_t tl, int bias, int bias2, int n_reads,
                                          uint32_t out_stride, uint32_t out_lo, float* __restrict__ gout,
                                          float* __restrict__ dbg, int wrow, int lane, float (&rr)[32],
@@ -240,16 +257,19 @@ __device__ __forceinline__ void epi_conv(const TcParams& prm, uint8_t* act, uint
     auto block = [&](int blk, auto reg_tag, auto ro_tag) {
         constexpr bool REG = decltype(reg_tag)::value;
         constexpr int RO = decltype(ro_tag)::value;
-        const int tile = blk / BPT, c0 = (blk - tile * BPT) * 16;
+        const int tile = S2D ? 0 : blk / BPT, c0 = S2D ? (blk & 1) * 16 : (blk - tile * BPT) * 16;
+        const int par = S2D ? (blk >> 1) : 0;
         const int m = tile * 128 + wrow + lane;
         const int i = m / PITCH, p = m - i * PITCH;
-        const bool valid = (i < n_reads) && (p < LVALID);
+        const bool valid = (i < n_reads) && (p < LVALID - par);
         const bool in_buf = m < ROWS;
         float x[16];
         float w[TWO ? 16 : 1];
         float r[((RESID && !REG) || MOVE_SC) ? 16 : 1];
-        ptx::tmem_ld16(tl + tile * TILE_COLS + c0, x);
-        if (TWO) ptx::tmem_ld16(tl + tile * TILE_COLS + N + c0, w);
+        const uint32_t xcol = S2D ? (TWO ? (par ? 64u : 32u) : par * 32u) + c0 : tile * TILE_COLS + c0;
+        const uint32_t wcol = S2D ? (par ? 96u : 0u) + c0 : tile * TILE_COLS + N + c0;
+        ptx::tmem_ld16(tl + xcol, x);
+        if (TWO) ptx::tmem_ld16(tl + wcol, w);
         if (RESID && !REG) ptx::tmem_ld16(tl + RES_COL + (blk - 2) * 16, r);
         if (MOVE_SC) ptx::tmem_ld16(tl + 64 + c0, r);
         ptx::tmem_wait_ld();
@@ -278,7 +298,7 @@ __device__ __forceinline__ void epi_conv(const TcParams& prm, uint8_t* act, uint
         }
         if (dbg) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) dbg[m * 64 + c0 + c] = x[c];
+            for (int c = 0; c < 16; ++c) dbg[m * 64 + par * 32 + c0 + c] = x[c];
         }
         if (OUT == OUT_GLOBAL) {
             // Stage the fp32 row in the (now idle) operand buffer, 16-byte chunks XOR-swizzled by the row so that the 32
@@ -296,9 +316,10 @@ __device__ __forceinline__ void epi_conv(const TcParams& prm, uint8_t* act, uint
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int c8 = c0 / 8 + q;
-                uint8_t* dst = OUT == OUT_NAT
-                                   ? act + c8 * out_stride + (uint32_t)(m + LEAD) * 16
-                                   : act + (c8 * 2 + (m & 1)) * out_stride + (uint32_t)((m >> 1) + LEAD) * 16;
+                uint8_t* dst = S2D ? act + (c8 * 2 + par) * out_stride + (uint32_t)(m + LEAD) * 16
+                               : OUT == OUT_NAT ? act + c8 * out_stride + (uint32_t)(m + LEAD) * 16
+                               : OUT == OUT_Q4 ? act + (c8 * 4 + (p & 3)) * out_stride + (uint32_t)(i * P3 + (p >> 2)) * 16
+                                               : act + (c8 * 2 + (m & 1)) * out_stride + (uint32_t)((m >> 1) + LEAD) * 16;
                 store_chunk8<MODE>(dst, out_lo, x + 8 * q);
             }
         }
@@ -389,72 +410,83 @@ __device__ __forceinline__ void accumulate_out(uint8_t* smem, const uint8_t* act
     }
 }
 
-// Epilogue of stem conv 3 fused with MaxPool1d(3,2): E[m] = conv(2p), O[m] = conv(2p+1) sit in two accumulators
-// (each the sum of its three operand products), conv(2p+2) = E[m+1] comes from the neighbouring lane (shared-memory
-// exchange across warp / tile borders).  Starts the residual stream: tile 0 -> registers, tile 1 -> TMEM.
+// Epilogue of stem conv 3 fused with MaxPool1d(3,2), producing the space-to-depth layout of the 32-channel stage.  Row r of
+// a read holds the convolution at positions 4r .. 4r+3 in four accumulators a0..a3 (32 columns each, the sum of their three
+// operand products); pooled[2r] = max(a0, a1, a2), pooled[2r+1] = max(a2, a3, a0 of row r+1) -- the latter comes from the
+// neighbouring lane (shared-memory exchange across warp borders).  Starts the residual stream: the even position's 32
+// channels -> registers, the odd position's -> TMEM (blocks 0,1 / 2,3 of epi_conv<S2D>).
 template <int MODE>
 __device__ __forceinline__ void epi_pool(const TcParams& prm, uint8_t* act, uint32_t tl, int bias, int n_reads, int g, int wq,
                                          int lane, float* __restrict__ dbg, float (&rr)[32]) {
     float* xchg = reinterpret_cast<float*>(act + XCHG_OFF);
-    constexpr int N_SLICES = T2 * 4;
-#pragma unroll
-    for (int tile = 0; tile < T2; ++tile) {
+    {
         float e[32];
-        ptx::tmem_ld32(tl + tile * 64, e);
+        ptx::tmem_ld32(tl, e);
         ptx::tmem_wait_ld();
         if (lane == 0) {
-            float4* dst = reinterpret_cast<float4*>(xchg + (tile * 4 + wq) * 32);
+            float4* dst = reinterpret_cast<float4*>(xchg + wq * 32);
 #pragma unroll
             for (int q = 0; q < 8; ++q) dst[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
         }
     }
     ptx::named_bar_sync(1 + g, EW * 32);
+    const int m = wq * 32 + lane;
+    const int i = m / P3, p = m - i * P3;
+    const bool valid_e = (i < n_reads) && (p < LV4), valid_o = (i < n_reads) && (p < LV4 - 1);
+    // row m+1 of the last lane lives in the next warp slice: lane c fetches its column-c value once and broadcasts it
+    // (the very last row of the group is padding, any finite value will do)
+    const float xv = xchg[((wq + 1) & 3) * 32 + lane];
 #pragma unroll
-    for (int tile = 0; tile < T2; ++tile) {
-        const int m = tile * 128 + wq * 32 + lane;
-        const int i = m / P2, p = m - i * P2;
-        const bool valid = (i < n_reads) && (p < LV3);
-        const int nxt = tile * 4 + wq + 1;
-        // row m+1 of the last lane lives in the next warp slice: lane c fetches its column-c value once and
-        // broadcasts it (the very last row of the group is padding, any finite value will do)
-        const float xv = xchg[(nxt < N_SLICES ? nxt : 0) * 32 + lane];
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-            float e[16], o[16];
-            ptx::tmem_ld16(tl + tile * 64 + hb * 16, e);
-            ptx::tmem_ld16(tl + tile * 64 + 32 + hb * 16, o);
+    for (int hb = 0; hb < 2; ++hb) {
+        float ev[16], ov[16];
+        {
+            float a0[16], a1[16];
+            ptx::tmem_ld16(tl + hb * 16, a0);
+            ptx::tmem_ld16(tl + 32 + hb * 16, a1);
             ptx::tmem_wait_ld();
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
-                const float dn = __shfl_down_sync(0xffffffffu, e[c], 1);
+                const float dn = __shfl_down_sync(0xffffffffu, a0[c], 1);
                 const float nb = __shfl_sync(0xffffffffu, xv, hb * 16 + c);
-                const float e1 = lane == 31 ? nb : dn;
-                const float x = fmaxf(fmaxf(fmaxf(e[c], o[c]), e1) + prm.bias_tab[bias + hb * 16 + c], 0.f);
-                o[c] = valid ? x : 0.f;
+                ov[c] = lane == 31 ? nb : dn;                    // a0 of row m+1
+                ev[c] = fmaxf(a0[c], a1[c]);
             }
-            if (tile == 0) {
+        }
+        {
+            float a2[16], a3[16];
+            ptx::tmem_ld16(tl + 64 + hb * 16, a2);
+            ptx::tmem_ld16(tl + 96 + hb * 16, a3);
+            ptx::tmem_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 16; ++c) rr[hb * 16 + c] = o[c];
-            } else {
-                ptx::tmem_st16(tl + RES_COL + hb * 16, o);
+            for (int c = 0; c < 16; ++c) {
+                const float bb = prm.bias_tab[bias + hb * 16 + c];
+                const float e = fmaxf(fmaxf(ev[c], a2[c]) + bb, 0.f);
+                const float o = fmaxf(fmaxf(fmaxf(a2[c], a3[c]), ov[c]) + bb, 0.f);
+                ev[c] = valid_e ? e : 0.f;
+                ov[c] = valid_o ? o : 0.f;
             }
-            if (dbg) {
+        }
 #pragma unroll
-                for (int c = 0; c < 16; ++c) dbg[m * 64 + hb * 16 + c] = o[c];
-            }
-            if (m < ROWS2) {
+        for (int c = 0; c < 16; ++c) rr[hb * 16 + c] = ev[c];
+        ptx::tmem_st16(tl + RES_COL + hb * 16, ov);
+        if (dbg) {
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
-                    store_chunk8<MODE>(act + (hb * 2 + q) * S2_CH + (uint32_t)(m + 1) * 16, 4 * S2_CH, o + 8 * q);
+            for (int c = 0; c < 16; ++c) { dbg[m * 64 + hb * 16 + c] = ev[c]; dbg[m * 64 + 32 + hb * 16 + c] = ov[c]; }
+        }
+        if (m < ROWS3) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                store_chunk8<MODE>(act + ((hb * 2 + q) * 2 + 0) * D2_ARR + (uint32_t)(m + 1) * 16, 8 * D2_ARR, ev + 8 * q);
+                store_chunk8<MODE>(act + ((hb * 2 + q) * 2 + 1) * D2_ARR + (uint32_t)(m + 1) * 16, 8 * D2_ARR, ov + 8 * q);
             }
         }
     }
-    if (wq == 0 && lane == 0) {
+    if (wq == 0 && lane == 0) {                                   // zero padding row in front of the first read
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            *reinterpret_cast<uint4*>(act + a * S2_CH) = z;
-            if (MODE == 3) *reinterpret_cast<uint4*>(act + a * S2_CH + 4 * S2_CH) = z;
+        for (int a = 0; a < 8; ++a) {
+            *reinterpret_cast<uint4*>(act + a * D2_ARR) = z;
+            if (MODE == 3) *reinterpret_cast<uint4*>(act + a * D2_ARR + 8 * D2_ARR) = z;
         }
     }
     ptx::tmem_wait_st();
@@ -504,10 +536,66 @@ __device__ __forceinline__ void issue_tile(uint32_t act_lo, uint32_t w_lo, uint3
     }
 }
 
+// One layer of the 32-channel stage in its space-to-depth form (see the file header).  Activation arrays: (chunk c8,
+// parity) at (c8 * 2 + parity) * D2_ARR, lead zero row, "lo" copies 8 arrays further; a 16-channel K step of one parity is
+// the array pair (4 j + parity, 4 j + 2 + parity), i.e. LBO = 2 * D2_ARR and 4 * D2_ARR between steps.
+// Weight units in issue order (packed by pack_s2d_phase): 2 x centre / even input, 2 x centre / odd input (128 rows
+// [lo even | hi even | hi odd | lo odd]; the A_lo x W_hi product reads rows [32,96) of the same unit), 2 x tap -1 (odd input
+// of the row above -> even output, 64 rows [lo even | hi even]), 2 x tap +1 (even input of the row below -> odd output, 64
+// rows [hi odd | lo odd]).  Accumulator columns: [hl even | hh even | hh odd | hl odd].  bf16 (MODE 1): units hold the hi rows
+// only, accumulators [even | odd].  PART 1 = the two tap +1 steps (token hand-over tail).
+template <int MODE, int PART>
+__device__ __forceinline__ void issue_stage2_s2d(uint32_t act_lo, uint32_t w_lo, uint32_t d) {
+    constexpr uint32_t ARR = D2_ARR >> 4, A_LO = (8 * D2_ARR) >> 4;
+    constexpr uint32_t FULL = s2d_full_bytes<MODE>() >> 4, HALF = s2d_half_bytes<MODE>() >> 4;
+    constexpr uint32_t FROWS = MODE == 3 ? 128 : 64, HROWS = MODE == 3 ? 64 : 32;
+    const uint32_t a0 = act_lo | ((((2 * D2_ARR) >> 4) & 0x3FFFu) << 16);
+    const uint32_t bf = w_lo | (((FROWS * 16u) >> 4) << 16);            // full units: chunk distance = 128 (64) rows
+    const uint32_t bh = (w_lo + 4 * FULL) | (((HROWS * 16u) >> 4) << 16);
+    constexpr uint32_t i128 = ptx::idesc_bf16_m128(128), i64 = ptx::idesc_bf16_m128(64), i32 = ptx::idesc_bf16_m128(32);
+    if (PART == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {                                   // centre: row m of the tile = array row m + 1
+            const uint32_t par = u >> 1, j = u & 1;
+            const uint32_t a = a0 + par * ARR + 1u + j * 4 * ARR;
+            const uint32_t b = bf + u * FULL;
+            if (MODE == 3) {
+                ptx::mma_bf16_ss(d, a, b, i128, u == 0 ? 0u : 1u);
+                ptx::mma_bf16_ss(d + 32, a + A_LO, b + 32, i64, 1u);     // A_lo x [hi even | hi odd]
+            } else {
+                ptx::mma_bf16_ss(d, a, b, i64, u == 0 ? 0u : 1u);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                                   // tap -1: odd input of array row m -> even output
+            const uint32_t a = a0 + ARR + j * 4 * ARR;
+            const uint32_t b = bh + j * HALF;
+            if (MODE == 3) {
+                ptx::mma_bf16_ss(d, a, b, i64, 1u);
+                ptx::mma_bf16_ss(d + 32, a + A_LO, b + 32, i32, 1u);
+            } else {
+                ptx::mma_bf16_ss(d, a, b, i32, 1u);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                                   // tap +1: even input of array row m + 2 -> odd output
+            const uint32_t a = a0 + 2u + j * 4 * ARR;
+            const uint32_t b = bh + (2 + j) * HALF;
+            if (MODE == 3) {
+                ptx::mma_bf16_ss(d + 64, a, b, i64, 1u);
+                ptx::mma_bf16_ss(d + 64, a + A_LO, b, i32, 1u);
+            } else {
+                ptx::mma_bf16_ss(d + 32, a, b, i32, 1u);
+            }
+        }
+    }
+}
+
 // All MMAs of layer phase `ph` for one group.  act_lo / w_lo: shared-memory addresses >> 4; d0: TMEM base of the group.
 template <int MODE, int PART>
 __device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_lo, uint32_t d0) {
-    constexpr uint32_t TC16 = MODE == 3 ? 32 : 16, TC32 = MODE == 3 ? 64 : 32;   // accumulator columns per tile
+    constexpr uint32_t TC16 = MODE == 3 ? 32 : 16;   // accumulator columns per tile of the 16-channel stem layers
     if (ph == 0) {
 #pragma unroll 1
         for (uint32_t t = 0; t < T1; ++t)
@@ -517,18 +605,15 @@ __device__ __forceinline__ void issue_phase(int ph, uint32_t act_lo, uint32_t w_
         for (uint32_t t = 0; t < T1; ++t)
             issue_tile<MODE, PART, true, 16, 3, 1, true, 0, 16, 32, A1_CH, 2 * A1_CH, 0>(act_lo + t * 128u, w_lo, d0 + t * TC16);
     } else if (ph == 2) {
-#pragma unroll 1
-        for (uint32_t t = 0; t < T2; ++t) {
-            // E[m] = conv at position 2p (taps: even[p], odd[p], even[p+1]);  O[m] = conv at 2p+1.  Two accumulators
-            // per tile already fill the group's columns, so the three products go into the same 32 columns.
-            issue_tile<MODE, PART, false, 32, 3, 1, true, 0, A2_ARR, 16, 2 * A2_ARR, 4 * A2_ARR, 0>(act_lo + t * 128u, w_lo, d0 + t * 64u);
-            issue_tile<MODE, PART, false, 32, 3, 1, true, A2_ARR, 16, A2_ARR + 16, 2 * A2_ARR, 4 * A2_ARR, 0>(act_lo + t * 128u, w_lo,
-                                                                                                         d0 + t * 64u + 32u);
-        }
+        // Stem conv 3 at positions 4r + j (j = 0..3), one accumulator of 32 columns each, from the mod-4 de-interleaved
+        // layer-2 output: x[4r + j + t] sits in array (j + t) & 3 at row r + ((j + t) >> 2).  Four accumulators fill the
+        // group's columns, so the three products go into the same 32 columns.
+        issue_tile<MODE, PART, false, 32, 3, 1, true, 0, Q4_ARR, 2 * Q4_ARR, 4 * Q4_ARR, 8 * Q4_ARR, 0>(act_lo, w_lo, d0);
+        issue_tile<MODE, PART, false, 32, 3, 1, true, Q4_ARR, 2 * Q4_ARR, 3 * Q4_ARR, 4 * Q4_ARR, 8 * Q4_ARR, 0>(act_lo, w_lo, d0 + 32u);
+        issue_tile<MODE, PART, false, 32, 3, 1, true, 2 * Q4_ARR, 3 * Q4_ARR, 16, 4 * Q4_ARR, 8 * Q4_ARR, 0>(act_lo, w_lo, d0 + 64u);
+        issue_tile<MODE, PART, false, 32, 3, 1, true, 3 * Q4_ARR, 16, Q4_ARR + 16, 4 * Q4_ARR, 8 * Q4_ARR, 0>(act_lo, w_lo, d0 + 96u);
     } else if (ph < 9) {
-#pragma unroll 1
-        for (uint32_t t = 0; t < T2; ++t)
-            issue_tile<MODE, PART, true, 32, 3, 2, true, 0, 16, 32, S2_CH, 4 * S2_CH, 0>(act_lo + t * 128u, w_lo, d0 + t * TC32);
+        issue_stage2_s2d<MODE, PART>(act_lo, w_lo, d0);
     } else if (ph == 9) {
         // stride 2: x[2p-1], x[2p], x[2p+1] = odd[p-1], even[p], odd[p]; the 1x1 shortcut reads even[p].  Both results
         // must sit in the accumulator columns at once (conv a in [0,64), shortcut in [64,128)): unstacked form.
@@ -678,21 +763,23 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                     epi_conv<MODE, true, 16, T1, P1, LV1, false, false, false, false, OUT_NAT, 0>(
                         prm, act, tl, B_L1, 0, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 1) {
-                    epi_conv<MODE, true, 16, T1, P1, LV2, false, false, false, false, OUT_EO, 0>(
-                        prm, act, tl, B_L2, 0, n, A2_ARR, 4 * A2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                    epi_conv<MODE, true, 16, T1, P1, LV2, false, false, false, false, OUT_Q4, 0>(
+                        prm, act, tl, B_L2, 0, n, Q4_ARR, 8 * Q4_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 2) {
                     epi_pool<MODE>(prm, act, tl, B_L3, n, g, wq, lane, dbg, rr);
                 } else if (ph < 9) {
                     const int b = B_S2 + (ph - 3) * 32;
+                    // space-to-depth rows (two positions per row): same tile shape and operand layout as the 64-channel stage;
+                    // the last layer's output is already the (chunk, parity) layout the stride-2 block reads
                     if ((ph - 3) % 2 == 0)
-                        epi_conv<MODE, true, 32, T2, P2, LV3, false, false, false, false, OUT_NAT, 1>(
-                            prm, act, tl, b, 0, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                        epi_conv<MODE, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1, true>(
+                            prm, act, tl, b, 0, n, D2_ARR, 8 * D2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else if (ph < 8)
-                        epi_conv<MODE, true, 32, T2, P2, LV3, true, false, true, false, OUT_NAT, 1>(
-                            prm, act, tl, b, 0, n, S2_CH, 4 * S2_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                        epi_conv<MODE, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1, true>(
+                            prm, act, tl, b, 0, n, D2_ARR, 8 * D2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else
-                        epi_conv<MODE, true, 32, T2, P2, LV3, true, false, false, false, OUT_EO, 1>(
-                            prm, act, tl, b, 0, n, E3_ARR, 8 * E3_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
+                        epi_conv<MODE, true, 64, T3, P3, LV4, true, false, false, false, OUT_NAT, 1, true>(
+                            prm, act, tl, b, 0, n, D2_ARR, 8 * D2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 9) {
                     epi_conv<MODE, false, 64, T3, P3, LV4, false, false, false, true, OUT_NAT, 1>(
                         prm, act, tl, B_RCA, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
@@ -932,6 +1019,43 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
                t->prm.w_bytes[ph] <= WSLOT_BYTES && t->prm.w_bytes[ph] % 16 == 0;
     };
     auto copy_bias = [&](const HostConv& c, int off) { for (int i = 0; i < c.cout; ++i) bias[off + i] = c.b[i]; };
+    // A 32 -> 32 k=3 pad=1 convolution in the space-to-depth form of issue_stage2_s2d.  w_t multiplies x[p + t - 1]:
+    //   even output 2r:   w0 * odd[r-1]  + w1 * even[r] + w2 * odd[r]
+    //   odd output 2r+1:  w0 * even[r]   + w1 * odd[r]  + w2 * even[r+1]
+    // Row groups of 32 output channels; element (chunk c, row n, e) = W_t[n][ci = 16 j + 8 c + e] (hi or lo part).
+    auto pack_s2d_phase = [&](int ph, const HostConv& c) {
+        if (c.cin != 32 || c.cout != 32 || c.k != 3) return false;
+        std::vector<uint16_t> buf;
+        // groups: (tap, lo?) per 32 rows, in accumulator-column order
+        auto unit = [&](int j, std::vector<std::pair<int, bool>> groups) {
+            for (int ch = 0; ch < 2; ++ch)
+                for (auto& gp : groups)
+                    for (int n = 0; n < 32; ++n)
+                        for (int e = 0; e < 8; ++e) {
+                            const int ci = 16 * j + 8 * ch + e;
+                            const float w = c.w[(size_t)(gp.first * c.cin + ci) * c.cout + n];
+                            const uint16_t h = bf16_rne(w);
+                            buf.push_back(gp.second ? bf16_rne(w - bf16_to_float(h)) : h);
+                        }
+        };
+        const bool x3 = parts == 2;
+        using G2 = std::vector<std::pair<int, bool>>;
+        // centre, even input: even output takes w1, odd output takes w0;  centre, odd input: even <- w2, odd <- w1
+        for (int par = 0; par < 2; ++par)
+            for (int j = 0; j < 2; ++j) {
+                const int te = par == 0 ? 1 : 2, to = par == 0 ? 0 : 1;
+                unit(j, x3 ? G2{{te, true}, {te, false}, {to, false}, {to, true}} : G2{{te, false}, {to, false}});
+            }
+        for (int j = 0; j < 2; ++j) unit(j, x3 ? G2{{0, true}, {0, false}} : G2{{0, false}});      // tap -1: odd[r-1] -> even, w0
+        for (int j = 0; j < 2; ++j) unit(j, x3 ? G2{{2, false}, {2, true}} : G2{{2, false}});      // tap +1: even[r+1] -> odd, w2
+        t->prm.w_src[ph] = (uint32_t)blob.size();
+        t->prm.w_bytes[ph] = (uint32_t)(buf.size() * 2);
+        const uint8_t* pb = reinterpret_cast<const uint8_t*>(buf.data());
+        blob.insert(blob.end(), pb, pb + buf.size() * 2);
+        const uint32_t want = x3 ? UNITS_S2_FULL * s2d_full_bytes<3>() + UNITS_S2_HALF * s2d_half_bytes<3>()
+                                 : UNITS_S2_FULL * s2d_full_bytes<1>() + UNITS_S2_HALF * s2d_half_bytes<1>();
+        return t->prm.w_bytes[ph] == want && want <= WSLOT_BYTES;
+    };
 
     bool fit = true;
     // stem
@@ -947,7 +1071,7 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
         for (int h2 = 0; h2 < 2; ++h2) {
             const int ph = 3 + 2 * r + h2;
             const HostConv c = hc(h2 ? L.b : L.a);
-            fit &= pack_phase(ph, {{c, false}}, UNITS_S2);
+            fit &= pack_s2d_phase(ph, c);
             copy_bias(c, B_S2 + (ph - 3) * 32);
         }
     }

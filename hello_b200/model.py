@@ -335,6 +335,90 @@ class MoEEngine:
             done.synchronize()
         return out
 
+    def forward_host_packed(self, hp: "HostPackedBatch", chunk_sites: int = 65536, sync: bool = True,
+                            fresh_result: bool = False) -> "HostResult":
+        """End-to-end call on HOST buffers holding ALIGNED READS instead of encoded rows: per range of `chunk_sites` sites
+        the packed reads (bases, qualities, CIGARs, reference windows: ~370 bytes per row instead of 900) go host -> device
+        on a copy stream, `hello_encode_reads` (include/hello_encode.h, the GPU form of the reference's
+        computeFeaturesColoredSimple, c++/src/AlleleSearcherLiteFiltered.cpp:1031-1180) writes the [R, 150, C] rows of the
+        range straight into the batch's device buffer on the compute stream, and `hello_moe_forward_range` scores the range.
+        The 900-byte rows never exist in host memory or on PCIe.  Same result object and sync / fresh_result semantics as
+        forward_host."""
+        from . import encoder as E
+        st = hp.device_state(self)
+        main = torch.cuda.current_stream(self.device)
+        copy_s, comp_s = st["copy"], st["compute"]
+        copy_s.wait_stream(main)
+        comp_s.wait_stream(main)
+        db, res, out = st["batch"], st["result"], hp.result_buffers(fresh=fresh_result)
+        S = hp.n_sites
+        with torch.cuda.stream(copy_s):
+            for dst, src in st["small"]:
+                dst.copy_(src, non_blocking=True)
+            small_done = torch.cuda.Event()
+            small_done.record(copy_s)
+        comp_s.wait_event(small_done)
+        pk, dv = hp.packed_t, st["packed"]
+        sao = hp.site_allele_off
+        lib = E._load()
+        L = arch.FEATURE_LENGTH
+        for s0 in range(0, S, chunk_sites):
+            s1 = min(S, s0 + chunk_sites)
+            a0, a1 = int(sao[s0]), int(sao[s1])
+            rb0, rb1 = int(hp.read_base[s0]), int(hp.read_base[s1])
+            spans = {"bases": (int(hp.read_off[rb0]), int(hp.read_off[rb1])), "quals": (int(hp.read_off[rb0]), int(hp.read_off[rb1])),
+                     "cigars": (int(hp.cigar_off[rb0]), int(hp.cigar_off[rb1])),
+                     "reference": (int(hp.ref_off[s0]), int(hp.ref_off[s1]))}
+            for f in ("read_off", "cigar_off"):
+                spans[f] = (rb0, rb1 + 1)
+            for f in ("ref_start", "mapq", "orientation", "hp"):
+                spans[f] = (rb0, rb1)
+            spans["ref_off"] = (s0, s1 + 1)
+            for f in ("window_start", "assembly_start", "assembly_stop"):
+                spans[f] = (s0, s1)
+            ev = torch.cuda.Event()
+            with torch.cuda.stream(copy_s):
+                for f, (lo, hi) in spans.items():
+                    dv[f][lo:hi].copy_(pk[f][lo:hi], non_blocking=True)
+                for t in range(len(hp.row_read)):
+                    aro = hp.allele_read_off[t]
+                    r0, r1 = int(aro[a0]), int(aro[a1])
+                    st["row_read"][t][r0:r1].copy_(hp.row_read[t][r0:r1], non_blocking=True)
+                    st["row_site"][t][r0:r1].copy_(hp.row_site[t][r0:r1], non_blocking=True)
+                if hp.ref_onehot is not None and db.ref_onehot is not None:
+                    db.ref_onehot[s0:s1].copy_(hp.ref_onehot[s0:s1], non_blocking=True)
+                ev.record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(ev)
+                for t in range(len(hp.row_read)):
+                    aro = hp.allele_read_off[t]
+                    r0, r1 = int(aro[a0]), int(aro[a1])
+                    if r1 > r0:
+                        b = E.HelloEncodeBatch()
+                        b.n_rows, b.feature_length, b.channels = r1 - r0, L, self.cfg.read_cin[t]
+                        b.d_row_read = st["row_read"][t].data_ptr() + 4 * r0
+                        b.d_row_site = st["row_site"][t].data_ptr() + 4 * r0
+                        for f in ("read_off", "bases", "quals", "cigar_off", "cigars", "ref_start", "mapq", "orientation", "hp",
+                                  "ref_off", "reference", "window_start", "assembly_start", "assembly_stop"):
+                            setattr(b, "d_" + f, dv[f].data_ptr())
+                        with torch.cuda.device(self.device):
+                            rc = lib.hello_encode_reads(C.byref(b), db.reads[t].data_ptr() + r0 * L * self.cfg.read_cin[t],
+                                                        C.c_void_p(comp_s.cuda_stream))
+                        if rc != 0:
+                            raise _lib.HelloMoEError("hello_encode_reads failed (%d): %s" % (rc, lib.hello_encode_last_error().decode()))
+                self.run_range(db, res, s0, s1, st["workspace"])
+        with torch.cuda.stream(comp_s):
+            for dst, src in zip(out.tensors(), res.tensors()):
+                dst.copy_(src, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(comp_s)
+        out.done_event = done
+        main.wait_stream(comp_s)
+        main.wait_stream(copy_s)
+        if sync:
+            done.synchronize()
+        return out
+
     def run_net(self, net: str, x: torch.Tensor, layout: int = _lib.LAYOUT_RLC) -> torch.Tensor:
         """Test hook: one sub-network on `x` (uint8 reads, or fp32 channel-last [n, L, C])."""
         nid = weights.NET_IDS[net]
@@ -507,6 +591,72 @@ class HostBatch:
         ref = self.ref_onehot[s0:s1] if self.ref_onehot is not None else None
         db = DeviceBatch.from_host(reads, self.layout, offs, pin(sao[s0:s1 + 1] - a0), ref, device, pin=self.pin)
         return db, (a0, a1), (int(self.pair_off[s0]), int(self.pair_off[s1]))
+
+
+class HostPackedBatch(HostBatch):
+    """A ragged batch in HOST memory as ALIGNED READS (hello_b200.encoder.PackedReads) plus, per technology, the row plan
+    that turns them into the network's rows (row -> read, row -> site; site -> allele -> supporting reads order, -1 = the
+    all-zero row of an allele without support) and the usual CSR.  What a caller holds right after read sampling, before
+    the reference would run computeFeaturesColoredSimple per allele."""
+
+    def __init__(self, packed, row_read: Sequence, row_site: Sequence, allele_read_off: Sequence[torch.Tensor],
+                 site_allele_off: torch.Tensor, ref_onehot: Optional[torch.Tensor] = None, pin: bool = True):
+        pin_ = (lambda t: t if t.is_pinned() else t.pin_memory()) if pin else (lambda t: t)
+        as_t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+        self.packed = packed
+        self.packed_t = {f: pin_(as_t(getattr(packed, f).view(np.int32) if getattr(packed, f).dtype == np.uint32
+                                      else getattr(packed, f))) for f in packed.__dataclass_fields__ if f != "read_base"}
+        self.read_base = np.asarray(packed.read_base, np.int64)
+        self.read_off, self.cigar_off, self.ref_off = packed.read_off, packed.cigar_off, packed.ref_off
+        self.row_read = tuple(pin_(as_t(r).to(torch.int32).contiguous()) for r in row_read)
+        self.row_site = tuple(pin_(as_t(r).to(torch.int32).contiguous()) for r in row_site)
+        self.reads = ()                                   # no encoded rows on the host
+        self.layout = _lib.LAYOUT_RLC
+        self.allele_read_off = tuple(o.contiguous() for o in allele_read_off)
+        self.site_allele_off = site_allele_off.contiguous()
+        self.ref_onehot = pin_(ref_onehot.contiguous()) if ref_onehot is not None else None
+        self.pair_off = pair_offsets(self.site_allele_off)
+        self.pin = pin
+        self._out = None
+        for t, rr in enumerate(self.row_read):
+            if int(self.allele_read_off[t][-1]) != rr.numel() or self.row_site[t].numel() != rr.numel():
+                raise ValueError("technology %d: the row plan does not match allele_read_off" % t)
+
+    def input_nbytes(self) -> int:
+        n = sum(t.numel() * t.element_size() for t in self.packed_t.values())
+        n += sum(r.numel() * 4 for r in self.row_read) + sum(r.numel() * 4 for r in self.row_site)
+        n += sum(o.numel() * 4 for o in self.allele_read_off) + self.site_allele_off.numel() * 4
+        if self.ref_onehot is not None:
+            n += self.ref_onehot.numel() * 4
+        return n
+
+    def device_state(self, engine: "MoEEngine"):
+        st = getattr(self, "_dev", None)
+        if st is not None and st["engine"] is engine:
+            return st
+        dev = engine.device
+        pin = (lambda t: t if t.is_pinned() else t.pin_memory()) if self.pin else (lambda t: t)
+        aro_h = tuple(pin(o) for o in self.allele_read_off)
+        sao_h, po_h = pin(self.site_allele_off), pin(self.pair_off)
+        aro_d = tuple(torch.empty_like(o, device=dev) for o in aro_h)
+        sao_d, po_d = torch.empty_like(sao_h, device=dev), torch.empty_like(po_h, device=dev)
+        need_ref = engine.cfg.meta == "meta_convolver_ref" and self.ref_onehot is not None
+        L = arch.FEATURE_LENGTH
+        rows = tuple(torch.empty((r.numel(), L, engine.cfg.read_cin[t]), dtype=torch.uint8, device=dev)
+                     for t, r in enumerate(self.row_read))
+        batch = DeviceBatch(reads=rows, layout=_lib.LAYOUT_RLC, allele_read_off_h=self.allele_read_off,
+                            allele_read_off_d=aro_d, site_allele_off_h=self.site_allele_off, site_allele_off_d=sao_d,
+                            pair_off_h=self.pair_off, pair_off_d=po_d,
+                            ref_onehot=torch.empty(self.ref_onehot.shape, dtype=torch.float32, device=dev) if need_ref else None)
+        small = [(d, h) for d, h in zip(aro_d, aro_h)] + [(sao_d, sao_h), (po_d, po_h)]
+        st = {"engine": engine, "batch": batch, "result": engine.alloc_result(batch), "small": small,
+              "workspace": torch.empty(engine.workspace_cap, dtype=torch.uint8, device=dev),
+              "packed": {f: torch.empty_like(t, device=dev) for f, t in self.packed_t.items()},
+              "row_read": tuple(torch.empty_like(r, device=dev) for r in self.row_read),
+              "row_site": tuple(torch.empty_like(r, device=dev) for r in self.row_site),
+              "copy": torch.cuda.Stream(dev), "compute": torch.cuda.Stream(dev)}
+        self._dev = st
+        return st
 
 
 def _as_uint8(t: torch.Tensor) -> torch.Tensor:

@@ -204,6 +204,46 @@ def pair_offsets(site_allele_off: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def packed_allele_csr(per_site_reads, seed: int = 13):
+    """A synthetic allele structure over rows that are already in site order (one row per read): alleles per site from
+    ALLELE_PROBS (clipped to the site's read count), every alternative allele gets max(1, n / (2A)) consecutive rows, the
+    reference allele the rest.  -> (allele_read_off int32 [A+1], site_allele_off int32 [S+1])."""
+    import numpy as np
+    rng = np.random.default_rng(seed + 1)
+    n = np.asarray(per_site_reads, np.int64)
+    A = np.minimum(rng.choice(len(ALLELE_PROBS), size=n.size, p=np.asarray(ALLELE_PROBS) / np.sum(ALLELE_PROBS)) + 1, n)
+    sao = np.zeros(n.size + 1, np.int64)
+    np.cumsum(A, out=sao[1:])
+    alt = np.maximum(1, n // (2 * A))
+    site_of_allele = np.repeat(np.arange(n.size), A)
+    k = np.arange(int(sao[-1])) - sao[site_of_allele]                   # allele index inside its site
+    counts = np.where(k == 0, (n - (A - 1) * alt)[site_of_allele], alt[site_of_allele])
+    aro = np.zeros(counts.size + 1, np.int64)
+    np.cumsum(counts, out=aro[1:])
+    assert (counts >= 1).all() and aro[-1] == n.sum()
+    return torch.from_numpy(aro.astype(np.int32)), torch.from_numpy(sao.astype(np.int32))
+
+
+def tile_packed_reads(packed, row_read, row_site, times: int):
+    """`times` copies of a packed batch back to back (offsets rebased): a large synthetic batch from a small generated one."""
+    import numpy as np
+    from .encoder import PackedReads
+    if times <= 1:
+        return packed, row_read, row_site
+    n_reads, n_sites = packed.ref_start.size, packed.window_start.size
+    def offs(a):                                       # [n+1] offsets -> tiled offsets
+        step = a[-1]
+        return np.concatenate([a[:-1] + k * step for k in range(times)] + [np.array([times * step], a.dtype)])
+    rep = lambda a: np.tile(a, times)
+    out = PackedReads(offs(packed.read_off), rep(packed.bases), rep(packed.quals), offs(packed.cigar_off), rep(packed.cigars),
+                      rep(packed.ref_start), rep(packed.mapq), rep(packed.orientation), rep(packed.hp), offs(packed.read_base),
+                      offs(packed.ref_off), rep(packed.reference), rep(packed.window_start), rep(packed.assembly_start),
+                      rep(packed.assembly_stop))
+    rr = np.concatenate([np.where(row_read >= 0, row_read + k * n_reads, -1) for k in range(times)]).astype(np.int32)
+    rs = np.concatenate([row_site + k * n_sites for k in range(times)]).astype(np.int32)
+    return out, rr, rs
+
+
 def make_packed_reads(n_sites: int, coverage: int = 30, read_len: int = 150, seed: int = 13, hp: bool = False):
     """Aligned reads for the GPU feature encoder, generated vectorised (numpy) straight in the packed layout of
     include/hello_encode.h: every read is `M a, I b, M c, D d, M e` (b or d may be 0 -> the operation is dropped to a

@@ -161,7 +161,9 @@ int hello_moe_run_net(hello_moe* h, int net_id, const void* d_in, int64_t n_item
 /* Test hook for the fused tensor-core read convolver (HELLO_PREC_BF16X3 / HELLO_PREC_BF16 handles only): run it on
  * n_reads uint8 rows and, when d_dbg is not NULL, also dump the post-activation values of layer phase `phase`
  * (0-2 stem convs, 3-8 the six 32-channel convs, 9-10 the stride-2 block, 11-16 the six 64-channel convs) as
- * fp32 [ceil(n_reads/3), 512, 64]: row index = packed row of the 3-read group (pitch 160/80/40), 64 = channel slots. */
+ * fp32 [ceil(n_reads/3), 512, 64]: row index = packed row of the 3-read group, 64 = channel slots.  Phases 0-1: pitch 160,
+ * row = position, 16 channels.  Phases 2-8 (32-channel stage, run space-to-depth): pitch 40, row r holds positions 2r and 2r+1
+ * as channel slots [0,32) and [32,64).  Phases 9-16: pitch 40, row = position, 64 channels. */
 int hello_moe_readconv_debug(hello_moe* h, int tech, const uint8_t* d_reads, int64_t n_reads, int32_t input_layout,
                              int32_t phase, float* d_out, float* d_dbg, void* stream);
 

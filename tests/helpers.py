@@ -64,11 +64,18 @@ def readconv_phase_reference(cfg, params, reads_rlc, tech=0):
 
 def readconv_phase_from_dump(dump, phase, n_reads, length):
     """Undo the kernel's row packing: dump [groups, 512, 64] -> [R, C, L] for one phase (include/hello_moe.h)."""
-    pitch, ch = (160, 16) if phase < 2 else ((80, 32) if phase < 9 else (40, 64))
-    out = torch.zeros((n_reads, ch, length))
+    out_ch = 16 if phase < 2 else (32 if phase < 9 else 64)
+    out = torch.zeros((n_reads, out_ch, length))
     for r in range(n_reads):
         g, i = divmod(r, 3)
-        out[r] = dump[g, i * pitch:i * pitch + length, :ch].t()
+        if 2 <= phase < 9:
+            # 32-channel stage, space-to-depth: pitch 40, row q holds positions 2q (slots 0-31) and 2q+1 (slots 32-63)
+            rows = dump[g, i * 40:i * 40 + (length + 1) // 2, :64]                       # [ceil(L/2), 64]
+            both = rows.reshape(-1, 2, 32).reshape(-1, 32)[:length]                       # position-major
+            out[r] = both.t()
+        else:
+            pitch = 160 if phase < 2 else 40
+            out[r] = dump[g, i * pitch:i * pitch + length, :out_ch].t()
     return out
 
 

@@ -131,3 +131,26 @@ def test_encoder_at_scale_properties(encoder):
                             bytes(p.reference[p.ref_off[s]:p.ref_off[s + 1]]).decode(), int(p.window_start[s]),
                             int(p.assembly_start[s]), int(p.assembly_stop[s]), {"a": [0]})
         assert np.array_equal(host[r], E.compute_features_colored_simple(site, "a", 150, False, False)[0]), r
+
+
+@pytest.mark.parametrize("hp", [False, True])
+def test_forward_host_packed_equals_encode_then_forward(encoder, hp):
+    """MoEEngine.forward_host_packed (aligned reads on the host -> H2D of the packed reads per range -> hello_encode_reads ->
+    hello_moe_forward_range) gives bit-identical results to encoding the whole batch once and scoring the resident rows, for
+    any range size, including the all-zero row of an allele without support."""
+    from hello_b200 import model, synth
+    cfg = arch.CONFIGS["single_tech_hp" if hp else "single_tech"]
+    packed, rr, rs = synth.make_packed_reads(300, coverage=12, seed=21, hp=hp)
+    aro, sao = synth.packed_allele_csr(np.diff(packed.read_base), seed=21)
+    rr = rr.copy()
+    rr[int(aro[3])] = -1 if int(aro[4]) - int(aro[3]) == 1 else rr[int(aro[3])]      # an allele without support, if single-row
+    eng = model.MoEEngine(cfg, params_for(cfg), device=DEV, precision="bf16x3")
+    rows = encoder.DevicePackedReads(packed, DEV).encode(rr, rs, cfg.read_cin[0])
+    from hello_b200 import _lib
+    want = eng.run(model.DeviceBatch.from_host((rows,), _lib.LAYOUT_RLC, (aro,), sao, None, DEV))
+    hpb = model.HostPackedBatch(packed, (rr,), (rs,), (aro,), sao)
+    assert hpb.input_nbytes() < 0.5 * rows.numel()                   # ~370 B per row cross PCIe instead of 900 / 1050
+    for chunk in (37, 128, 1000):
+        got = eng.forward_host_packed(hpb, chunk)
+        for g, w in zip(got.tensors(), want.tensors()):
+            assert torch.equal(g, w.cpu()), chunk
