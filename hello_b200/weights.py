@@ -136,6 +136,50 @@ def weight_norm_state(state_dict) -> Dict[str, torch.Tensor]:
     return out
 
 
+LEGACY_PREFIXES = ("readConv", "alleleConv", "expert", "siteConvCombiner.")     # (`meta.` exists in both wirings)
+
+
+def legacy_state_to_attention(state_dict) -> Dict[str, torch.Tensor]:
+    """State dict of the legacy wiring ``MoEMergedAdvanced`` (python/MixtureOfExpertsAdvanced.py:255-484, built by
+    ``createMoEFullMergedAdvancedModel`` :614-654 from MoEReadConvolverDeeper / ExpertAlleleConvolverDeeper /
+    ExpertGraphConvolverDeeper with ``useAdditive``) -> the ``MoEAttention`` names this package uses.
+
+    Single technology only: there the legacy model computes exactly MoEAttention's function -- per-allele read sums,
+    allele convolver (= compressor), site frame = sum of the allele frames, expert input ``a - (s - a)`` (:374-379), the same
+    layers -- and its parameters are registered in the same order, so the k-th tensor of ``readConv0 / alleleConv0 /
+    expert0`` is the k-th tensor of ``read_convolver0 / compressor0 / xattn0`` (only the Sequential slot numbers differ: the
+    live xattn has two parameter-free front-end modules).  The legacy HYBRID wiring (allele features of the two technologies
+    added or ConvCombiner'ed, site frame = sum of THAT, meta on it, :408-436) is a different dataflow and is refused.
+    A state dict that is not legacy is returned unchanged."""
+    keys = list(state_dict.keys())
+    if not keys or not any(k.startswith(LEGACY_PREFIXES) for k in keys):
+        return dict(state_dict)
+    tops = {k.split(".", 1)[0] for k in keys}
+    if tops - {"readConv0", "alleleConv0", "expert0"}:
+        raise ValueError("legacy MoEMergedAdvanced hybrid wiring (%s) is not supported: only its single-technology form maps "
+                         "onto the MoEAttention layer tables" % sorted(tops - {"readConv0", "alleleConv0", "expert0"}))
+    sd = weight_norm_state(state_dict)
+    groups = {"readConv0": "read_convolver0", "alleleConv0": "compressor0", "expert0": "xattn0"}
+    for cfg in arch.CONFIGS.values():
+        if len(cfg.read_cin) != 1 or cfg.meta is not None:
+            continue
+        out, ok = {}, True
+        for old, new in groups.items():
+            theirs = [k for k in sd if k.startswith(old + ".")]
+            ours = []
+            for prefix, vshape, _ in conv_keys(cfg, new):
+                ours += [prefix + ".bias", prefix + ".weight_g", prefix + ".weight_v"]
+            shapes = param_shapes(cfg)
+            if len(theirs) != len(ours) or any(tuple(sd[a].shape) != shapes[b] or a.rsplit(".", 1)[1] != b.rsplit(".", 1)[1]
+                                               for a, b in zip(theirs, ours)):
+                ok = False
+                break
+            out.update({b: sd[a] for a, b in zip(theirs, ours)})
+        if ok:
+            return out
+    raise ValueError("legacy state dict does not match any supported single-technology configuration")
+
+
 def cfg_from_state_dict(params: Dict[str, torch.Tensor]) -> arch.ModelConfig:
     """Recognise which reference config a MoEAttention state dict belongs to."""
     for cfg in arch.CONFIGS.values():

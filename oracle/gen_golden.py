@@ -38,7 +38,12 @@ CASES = {
     "single_tech_uniform": (4, 8, 107, True),
     "single_tech_addendum": (5, 8, 108, False),
     "hybrid_no_ensemble_addendum": (4, 6, 109, False),
+    # the legacy wiring MoEMergedAdvanced (python/MixtureOfExpertsAdvanced.py:255-484) in its single-technology form, built by
+    # createMoEFullMergedAdvancedModel (:614-654) from the legacy architecture modules, useAdditive=True
+    "legacy_single_tech": (6, 9, 110, False),
 }
+LEGACY_CONFIG = {"readConvNGS": "MoEReadConvolverDeeper", "alleleConvSingleNGS": "ExpertAlleleConvolverDeeper",
+                 "graphConvSingleNGS": "ExpertGraphConvolverDeeper", "weight_norm": True, "kwargs": {"useAdditive": True}}
 
 
 def run_case(case: str) -> None:
@@ -50,10 +55,13 @@ def run_case(case: str) -> None:
     import MixtureOfExpertsAdvanced as M          # the reference
     from hello_b200 import arch, weights, synth
 
-    name = case.replace("_uniform", "")
+    name = case.replace("_uniform", "").replace("legacy_", "")
     n_sites, cov, seed, uniform = CASES[case]
     cfg = arch.CONFIGS[name]
-    if name in arch.REFERENCE_ADDENDUM_MODULE:
+    legacy = case.startswith("legacy_")
+    if legacy:
+        moe = M.createMoEFullMergedAdvancedModel(dict(LEGACY_CONFIG)).eval()
+    elif name in arch.REFERENCE_ADDENDUM_MODULE:
         # transfer-learning model: the reference's build_on_top stacks the addendum networks on a trained base model
         # (MixtureOfExpertsDNNFastXferLearning.py:494-502 does this on a DataParallel(WrapperForDataParallel(moe)))
         import types
@@ -69,17 +77,25 @@ def run_case(case: str) -> None:
         moe = M.create_moe_attention_model(mod.configDict).eval()
     shapes = weights.param_shapes(cfg)
     sd = moe.state_dict()
-    assert list(sd.keys()) == list(shapes.keys()), "arch.py does not describe the reference model"
-    for k in sd:
-        assert tuple(sd[k].shape) == shapes[k], k
+    params = weights.init_params(cfg, seed=13)
+    if legacy:
+        # same parameters in the same registration order under the legacy names: hello_b200's mapping must invert this
+        assert [tuple(v.shape) for v in sd.values()] == list(shapes.values())
+        legacy_sd = {k: params[k2] for k, k2 in zip(sd.keys(), shapes.keys())}
+        moe.load_state_dict(legacy_sd)
+        back = weights.legacy_state_to_attention(moe.state_dict())
+        assert list(back.keys()) == list(shapes.keys()) and all(torch.equal(back[k], params[k]) for k in shapes)
+    else:
+        assert list(sd.keys()) == list(shapes.keys()), "arch.py does not describe the reference model"
+        for k in sd:
+            assert tuple(sd[k].shape) == shapes[k], k
+        moe.load_state_dict(params)
     f_read, f_allele, f_site = arch.flops_model(cfg)
 
-    params = weights.init_params(cfg, seed=13)
-    moe.load_state_dict(params)
     pl = synth.make_pileups(n_sites, coverage=cov, channels=cfg.read_cin, seed=seed, uniform_bytes=uniform)
     args = pl.forward_args()
     with torch.no_grad():
-        res = moe(*args)
+        res = moe(*args[:3]) if legacy else moe(*args)      # MoEMergedAdvanced.forward(tensors, numAllelesPerSite, numReadsPerAllele)
     out = {
         "digest": np.array(weights.params_digest(params)),
         "torch_version": np.array(torch.__version__),

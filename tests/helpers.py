@@ -8,12 +8,13 @@ from hello_b200 import arch, synth, weights
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 GOLDEN_CASES = ["single_tech", "single_tech_hp", "hybrid_no_ensemble", "hybrid_ensemble2", "hybrid_full",
-                "hybrid_no_ensemble_wide", "single_tech_uniform", "single_tech_addendum", "hybrid_no_ensemble_addendum"]
+                "hybrid_no_ensemble_wide", "single_tech_uniform", "single_tech_addendum", "hybrid_no_ensemble_addendum",
+                "legacy_single_tech"]
 
 
 def load_golden(case):
     g = dict(np.load(os.path.join(GOLDEN, case + ".npz")))
-    cfg = arch.CONFIGS[case.replace("_uniform", "")]
+    cfg = arch.CONFIGS[case.replace("_uniform", "").replace("legacy_", "")]
     reads, offs = [], []
     for t in range(len(cfg.read_cin)):
         reads.append(torch.from_numpy(g["reads%d" % t]))

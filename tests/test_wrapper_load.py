@@ -83,3 +83,29 @@ def test_load_wrapper_reports_missing_reference_modules(tmp_path):
             "except _lib.HelloMoEError as e:\n    print('OK', 'NNTools' in str(e))\n") % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
     assert out.stdout.strip() == "OK True", out.stdout + out.stderr[-500:]
+
+
+def test_legacy_wiring_state_dict_maps_onto_single_tech():
+    """MoEMergedAdvanced (legacy wiring, python/MixtureOfExpertsAdvanced.py:255-484) in its single-technology form has the
+    parameters of MoEAttention in the same order under other names; tests/golden/legacy_single_tech.npz was produced by the
+    reference's createMoEFullMergedAdvancedModel with these very parameters, and the oracle / CUDA forward of `single_tech`
+    reproduce it (test_oracle_golden, test_forward_matches_reference_golden).  The hybrid legacy wiring is refused."""
+    cfg = arch.CONFIGS["single_tech"]
+    params = params_for(cfg)
+    legacy = {}
+    for k in weights.param_shapes(cfg):                       # the reference's registration order: bias, weight_g, weight_v
+        v = params[k]
+        net, rest = k.split(".", 1)
+        legacy[{"read_convolver0": "readConv0", "compressor0": "alleleConv0", "xattn0": "expert0"}[net] + "." + rest] = v
+    # the live xattn has two parameter-free front-end modules: the legacy expert's Sequential slots are shifted by two
+    legacy = {(k.replace("expert0.network.%d." % s, "expert0.network.%d." % (s - 2)) if k.startswith("expert0.") else k): v
+              for k, v in legacy.items() for s in [int(k.split(".")[2])]}
+    back = weights.legacy_state_to_attention(legacy)
+    assert list(back.keys()) == list(weights.param_shapes(cfg).keys())
+    assert all(torch.equal(back[k], params[k]) for k in params)
+    assert weights.cfg_from_state_dict(back).name == "single_tech"
+    assert weights.legacy_state_to_attention(params) == dict(params)               # non-legacy dicts pass through
+    hybrid = dict(legacy)
+    hybrid["readConv1.network.0.conv1d.bias"] = torch.zeros(16)
+    with pytest.raises(ValueError, match="hybrid wiring"):
+        weights.legacy_state_to_attention(hybrid)
