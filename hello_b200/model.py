@@ -681,7 +681,7 @@ class MoEAttentionB200:
 
     @classmethod
     def from_state_dict(cls, state_dict, **kw) -> "MoEAttentionB200":
-        sd = weights.weight_norm_state(weights.legacy_state_to_attention(state_dict))
+        sd = weights.supported_state(state_dict)
         return cls(weights.cfg_from_state_dict(sd), sd, **kw)
 
     @classmethod
@@ -814,7 +814,13 @@ def read_wrapper(path: str, reference_python: Optional[str] = None):
     moe = getattr(net, "moeMerged", net)                     # the wrapper, or a bare MoEAttention
     if not hasattr(moe, "state_dict"):
         raise _lib.HelloMoEError("load_wrapper: %s does not hold a torch module" % path)
-    sd = weights.weight_norm_state(weights.legacy_state_to_attention(moe.state_dict()))
+    # the activation and the kind of normalisation are not in a state dict: look at the modules
+    odd = sorted({type(m).__name__ for m in moe.modules()} & {"Softplus", "LayerNorm", "LayerNormModule", "GroupNorm", "ELU",
+                                                               "LeakyReLU", "Tanh", "Sigmoid", "Dropout"})
+    if odd:
+        raise _lib.HelloMoEError("load_wrapper: the model uses %s; this build covers the ReLU networks with weight-norm or "
+                                 "BatchNorm1d that the reference's shipped configurations use" % ", ".join(odd))
+    sd = weights.supported_state(moe.state_dict())
     return weights.cfg_from_state_dict(sd), sd, bool(getattr(net, "providePredictions", False))
 
 

@@ -180,6 +180,133 @@ def legacy_state_to_attention(state_dict) -> Dict[str, torch.Tensor]:
     raise ValueError("legacy state dict does not match any supported single-technology configuration")
 
 
+BN_EPS = 1e-5          # torch.nn.BatchNorm1d default, what NNTools builds (python/NNTools.py:84-104)
+
+
+def is_batchnorm_state(state_dict) -> bool:
+    return any(k.endswith(".running_mean") for k in state_dict)
+
+
+def batchnorm_state_to_weight_norm(state_dict, eps: float = BN_EPS) -> Dict[str, torch.Tensor]:
+    """State dict of a model built WITHOUT weight-norm -- plain Conv1d / Linear followed (or, in the pooled head, preceded)
+    by ``BatchNorm1d`` (``norm_type="BatchNorm1d"``, the default of python/NNTools.py:27-45,72-115,118-294,517-566 when an
+    architecture module has ``weight_norm = False``) -- folded for inference and renamed to this package's layer tables.
+
+    Eval-mode batch-norm is the affine map ``y = (x - mean) / sqrt(var + eps) * gamma + beta``, so
+      conv -> BN (same Sequential, next slot):   w' = w * s[o],  b' = (b - mean) * s + beta,   s = gamma / sqrt(var + eps)
+      BN -> linear (pooled head, AvgPool -> Flatten -> BN -> Linear):  w' = w * s[i],  b' = b + w @ (beta - mean * s)
+    A convolution without a following BN (the 1x1 shortcut of a stride-2 residual block) is taken as it is.  The layers come
+    in the same order as in the weight-norm model, so the k-th folded layer of a sub-network is the k-th entry of
+    ``conv_keys``.  The result is expressed as ``weight_v = w'``, ``weight_g = |w'|`` (folding it back gives w' exactly).
+    The activation is not part of a state dict: BatchNorm models are taken to use ReLU, as every BN configuration of the
+    reference does (the LayerNorm / Softplus experiment is refused by read_wrapper, which sees the modules)."""
+    nets = {}
+    for k in state_dict:
+        nets.setdefault(k.split(".", 1)[0], []).append(k)
+
+    def stem_of(k):
+        return k.rsplit(".", 1)[0]
+
+    def parent_slot(stem):
+        parent, slot = stem.rsplit(".", 1)
+        return parent, int(slot) if slot.isdigit() else None
+
+    folded_nets = {}
+    for net, keys in nets.items():
+        stems = []
+        for k in keys:
+            st = stem_of(k)
+            if not stems or stems[-1] != st:
+                stems.append(st)
+        layers = []                 # [w, b, stem] in order
+        pre_bn = None               # (scale, shift, stem) waiting for the linear of the pooled head
+        for st in stems:
+            g = lambda name: state_dict.get(st + "." + name)
+            if g("running_mean") is not None:
+                gamma, beta, mean, var = (g("weight").double(), g("bias").double(), g("running_mean").double(),
+                                          g("running_var").double())
+                sc = gamma / torch.sqrt(var + eps)
+                par, slot = parent_slot(st)
+                if layers and not layers[-1][3] and parent_slot(layers[-1][2]) == (par, slot - 1 if slot is not None else None) \
+                        and layers[-1][0].shape[0] == sc.numel():
+                    w, b = layers[-1][0], layers[-1][1]
+                    layers[-1][0] = w * sc.reshape((-1,) + (1,) * (w.dim() - 1))
+                    layers[-1][1] = (b - mean) * sc + beta
+                    layers[-1][3] = True
+                else:
+                    pre_bn = (sc, beta - mean * sc, st)
+            elif g("weight") is not None and g("weight").dim() >= 2:
+                w, b = g("weight").double(), g("bias").double()
+                if pre_bn is not None:
+                    sc, sh, bst = pre_bn
+                    if w.dim() != 2 or w.shape[1] != sc.numel() or parent_slot(bst)[0] != parent_slot(st)[0]:
+                        raise ValueError("BatchNorm %s is followed by %s: only conv -> BN and BN -> linear are folded" % (bst, st))
+                    b = b + w @ sh
+                    w = w * sc.reshape(1, -1)
+                    pre_bn = None
+                layers.append([w, b, st, False])
+            else:
+                raise ValueError("state dict entry %s.* is neither a convolution / linear layer nor a BatchNorm1d" % st)
+        if pre_bn is not None:
+            raise ValueError("BatchNorm %s has no layer to fold into" % pre_bn[2])
+        folded_nets[net] = layers
+    for cfg in arch.CONFIGS.values():
+        if set(cfg.networks()) != set(folded_nets):
+            continue
+        out, ok = {}, True
+        for net in cfg.networks():
+            ours = conv_keys(cfg, net)
+            theirs = folded_nets[net]
+            if len(ours) != len(theirs) or any(tuple(t[0].shape) != vs for t, (_, vs, _) in zip(theirs, ours)):
+                ok = False
+                break
+            for (w, b, _, _), (prefix, vshape, _) in zip(theirs, ours):
+                v = w.float().contiguous()
+                out[prefix + ".bias"] = b.float().contiguous()
+                out[prefix + ".weight_g"] = torch.norm_except_dim(v, 2, 0)
+                out[prefix + ".weight_v"] = v
+        if ok:
+            return out
+    raise ValueError("BatchNorm state dict does not match any supported HELLO MoE configuration")
+
+
+def init_batchnorm_state(keys_and_shapes, seed: int = 13) -> Dict[str, torch.Tensor]:
+    """Deterministic, machine-independent values for a BatchNorm-built reference model, filled in state-dict order: conv /
+    linear weights like init_params (uniform, bound 1/sqrt(fan_in)), gamma in [0.5, 1.5], beta in [-0.2, 0.2], running
+    means in [-0.5, 0.5] x a layer-dependent scale, running variances in [0.5, 2].  Used by oracle/gen_golden.py (which
+    loads it into the reference model) and by the tests (which fold it)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = {}
+    for key, shape in keys_and_shapes:
+        shape = tuple(int(x) for x in shape)
+        leaf = key.rsplit(".", 1)[1]
+        if leaf == "num_batches_tracked":
+            out[key] = torch.tensor(100, dtype=torch.int64)
+        elif leaf == "running_var":
+            out[key] = torch.from_numpy((0.5 + 1.5 * rng.random(shape)).astype(np.float32))
+        elif leaf == "running_mean":
+            out[key] = torch.from_numpy(((rng.random(shape) - 0.5) * 4.0).astype(np.float32))
+        elif leaf == "weight" and len(shape) == 1:
+            out[key] = torch.from_numpy((0.5 + rng.random(shape)).astype(np.float32))
+        elif leaf == "bias" and (key.rsplit(".", 1)[0] + ".running_mean") in dict(keys_and_shapes):
+            out[key] = torch.from_numpy(((rng.random(shape) - 0.5) * 0.4).astype(np.float32))
+        elif leaf == "weight":
+            bound = 1.0 / np.sqrt(float(np.prod(shape[1:])))
+            out[key] = torch.from_numpy(((rng.random(shape) * 2.0 - 1.0) * bound).astype(np.float32))
+        else:                                           # conv / linear bias
+            out[key] = torch.from_numpy(((rng.random(shape) * 2.0 - 1.0) * 0.1).astype(np.float32))
+    return out
+
+
+def supported_state(state_dict) -> Dict[str, torch.Tensor]:
+    """Any state dict this package can run -> its weight-norm form under MoEAttention names: the live wiring with weight-norm
+    (as it is), the legacy single-technology wiring (renamed), a BatchNorm1d-built model (folded).  Anything else raises."""
+    sd = legacy_state_to_attention(state_dict)
+    if is_batchnorm_state(sd):
+        return batchnorm_state_to_weight_norm(sd)
+    return weight_norm_state(sd)
+
+
 def cfg_from_state_dict(params: Dict[str, torch.Tensor]) -> arch.ModelConfig:
     """Recognise which reference config a MoEAttention state dict belongs to."""
     for cfg in arch.CONFIGS.values():

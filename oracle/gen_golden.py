@@ -41,6 +41,9 @@ CASES = {
     # the legacy wiring MoEMergedAdvanced (python/MixtureOfExpertsAdvanced.py:255-484) in its single-technology form, built by
     # createMoEFullMergedAdvancedModel (:614-654) from the legacy architecture modules, useAdditive=True
     "legacy_single_tech": (6, 9, 110, False),
+    # built WITHOUT weight-norm: plain Conv1d / Linear + BatchNorm1d (the architecture modules' default, weight_norm = False),
+    # eval mode, deterministic non-trivial running statistics; hello_b200 folds the batch-norms at load
+    "single_tech_batchnorm": (6, 9, 111, False),
 }
 LEGACY_CONFIG = {"readConvNGS": "MoEReadConvolverDeeper", "alleleConvSingleNGS": "ExpertAlleleConvolverDeeper",
                  "graphConvSingleNGS": "ExpertGraphConvolverDeeper", "weight_norm": True, "kwargs": {"useAdditive": True}}
@@ -55,11 +58,20 @@ def run_case(case: str) -> None:
     import MixtureOfExpertsAdvanced as M          # the reference
     from hello_b200 import arch, weights, synth
 
-    name = case.replace("_uniform", "").replace("legacy_", "")
+    name = case.replace("_uniform", "").replace("legacy_", "").replace("_batchnorm", "")
     n_sites, cov, seed, uniform = CASES[case]
     cfg = arch.CONFIGS[name]
     legacy = case.startswith("legacy_")
-    if legacy:
+    batchnorm = case.endswith("_batchnorm")
+    name = name.replace("_batchnorm", "")
+    cfg = arch.CONFIGS[name]
+    if batchnorm:
+        import architectures.read_convolver as rc_, architectures.compressor_conv_small as cc_, architectures.xattn_subtract as xa_
+        for m in (rc_, cc_, xa_):
+            m.weight_norm = False
+            m.gen_config()
+        moe = M.create_moe_attention_model({"read_conv0": rc_.config, "compressor0": cc_.config, "xattn0": xa_.config}).eval()
+    elif legacy:
         moe = M.createMoEFullMergedAdvancedModel(dict(LEGACY_CONFIG)).eval()
     elif name in arch.REFERENCE_ADDENDUM_MODULE:
         # transfer-learning model: the reference's build_on_top stacks the addendum networks on a trained base model
@@ -78,7 +90,15 @@ def run_case(case: str) -> None:
     shapes = weights.param_shapes(cfg)
     sd = moe.state_dict()
     params = weights.init_params(cfg, seed=13)
-    if legacy:
+    bn_keys = None
+    if batchnorm:
+        bn_keys = [(k, tuple(v.shape)) for k, v in sd.items()]
+        bn_state = weights.init_batchnorm_state(bn_keys, seed=13)
+        moe.load_state_dict(bn_state)
+        moe = moe.eval()                                  # running statistics, not batch statistics
+        params = weights.batchnorm_state_to_weight_norm(moe.state_dict())
+        assert list(params.keys()) == list(shapes.keys())
+    elif legacy:
         # same parameters in the same registration order under the legacy names: hello_b200's mapping must invert this
         assert [tuple(v.shape) for v in sd.values()] == list(shapes.values())
         legacy_sd = {k: params[k2] for k, k2 in zip(sd.keys(), shapes.keys())}
@@ -103,6 +123,9 @@ def run_case(case: str) -> None:
         "ref_onehot_idx": pl.ref_onehot.argmax(-1).to(torch.uint8).numpy(),
         "flops": np.array(list(f_read) + [f_allele, f_site], dtype=np.int64),
     }
+    if bn_keys is not None:                               # the reference model's own state-dict keys and shapes, in order
+        out["bn_keys"] = np.array([k for k, _ in bn_keys])
+        out["bn_shapes"] = np.array([",".join(str(x) for x in shp) for _, shp in bn_keys])
     for t, r in enumerate(pl.reads):
         out["reads%d" % t] = r.numpy()
         out["allele_read_off%d" % t] = pl.allele_read_off[t].numpy()

@@ -12,9 +12,19 @@ GOLDEN_CASES = ["single_tech", "single_tech_hp", "hybrid_no_ensemble", "hybrid_e
                 "legacy_single_tech"]
 
 
+def batchnorm_params(case="single_tech_batchnorm"):
+    """The folded parameters of the BatchNorm-built golden model: its reference state dict is re-created from the key /
+    shape list stored in the fixture (weights.init_batchnorm_state is deterministic) and folded by
+    weights.batchnorm_state_to_weight_norm -- the same two steps a user's BatchNorm model goes through in from_state_dict."""
+    g = np.load(os.path.join(GOLDEN, case + ".npz"))
+    keys = [(str(k), tuple(int(x) for x in str(s).split(",") if x)) for k, s in zip(g["bn_keys"], g["bn_shapes"])]
+    state = weights.init_batchnorm_state(keys, seed=13)
+    return state, weights.supported_state(state)
+
+
 def load_golden(case):
     g = dict(np.load(os.path.join(GOLDEN, case + ".npz")))
-    cfg = arch.CONFIGS[case.replace("_uniform", "").replace("legacy_", "")]
+    cfg = arch.CONFIGS[case.replace("_uniform", "").replace("legacy_", "").replace("_batchnorm", "")]
     reads, offs = [], []
     for t in range(len(cfg.read_cin)):
         reads.append(torch.from_numpy(g["reads%d" % t]))

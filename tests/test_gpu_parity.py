@@ -359,6 +359,23 @@ def test_forward_matches_reference_golden(gpu, case, precision):
     check_log_probs(r.pair_prob[1:].cpu().numpy(), g["pair_experts"], precision, case)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_batchnorm_built_model_matches_reference_golden(gpu, precision):
+    """A model built without weight-norm (Conv1d + BatchNorm1d, eval mode): from_state_dict folds the batch-norms and the
+    CUDA forward reproduces the reference's outputs (tests/golden/single_tech_batchnorm.npz, made by the reference)."""
+    from helpers import batchnorm_params
+    cfg, pl, g = load_golden("single_tech_batchnorm")
+    state, params = batchnorm_params()
+    net = gpu.MoEAttentionB200.from_state_dict(state, device=DEV, precision=precision)
+    assert net.cfg.name == "single_tech"
+    res = net.forward(*pl.forward_args())
+    np.testing.assert_allclose(res.reshape(1, -1).cpu().numpy(), g["logits"], rtol=0, atol=TOL_LOGIT[precision])
+    r = net.last_result
+    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], rtol=0, atol=TOL_PROB[precision])
+    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB[precision], "single_tech_batchnorm/" + precision)
+    check_log_probs(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], precision, "batchnorm")
+
+
 def check_calls(result, ref_mixed, ref_best, tol, what="", max_tight_share=MAX_TIGHT_SHARE):
     """Genotype calls bit-exact wherever the reference's own top-2 margin exceeds 2*tol; the number of tight-margin
     sites (compared only through their probabilities) is printed and bounded."""

@@ -61,6 +61,31 @@ def test_per_site_wrapper_matches_reference(case):
     assert np.array_equal(np.array(best, np.int32), g["best_pair"])
 
 
+def test_batchnorm_model_is_folded_like_the_reference_evaluates_it():
+    """tests/golden/single_tech_batchnorm.npz: the reference model built WITHOUT weight-norm (Conv1d -> BatchNorm1d -> ReLU,
+    BatchNorm1d -> Linear in the pooled head; python/NNTools.py:72-115,118-294,517-566) in eval mode.  Folding its state dict
+    (weights.batchnorm_state_to_weight_norm) must give the parameters the fixture was made with and the oracle must
+    reproduce the reference's logits and per-site probabilities."""
+    from helpers import batchnorm_params
+    cfg, pl, g = load_golden("single_tech_batchnorm")
+    state, params = batchnorm_params()
+    assert weights.is_batchnorm_state(state) and not weights.is_batchnorm_state(params)
+    assert weights.cfg_from_state_dict(params).name == "single_tech"
+    assert weights.params_digest(params) == str(g["digest"])
+    with pytest.raises(ValueError, match="without weight-norm"):
+        weights.weight_norm_state(state)                  # the strict weight-norm reader still refuses it
+    torch.set_num_threads(1)
+    model = O.OracleModel(cfg, params)
+    res = model.forward(*pl.forward_args())
+    np.testing.assert_allclose(res.reshape(1, -1).numpy(), g["logits"], rtol=0, atol=TOL)
+    mixed = []
+    for s in range(pl.n_sites):
+        fd, seg = pl.site_feature_dict(s)
+        r = O.wrapper_forward(model, fd, seg, provide_predictions=True)
+        mixed += [float(v) for v in r[0].values()]
+    np.testing.assert_allclose(np.array(mixed, np.float32), g["pair_mixed"], rtol=0, atol=TOL)
+
+
 def test_batched_equals_per_site_tail():
     cfg, pl, g = load_golden("hybrid_full")
     res = O.OracleModel(cfg, params_for(cfg)).forward(*pl.forward_args())

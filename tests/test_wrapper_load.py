@@ -109,3 +109,53 @@ def test_legacy_wiring_state_dict_maps_onto_single_tech():
     hybrid["readConv1.network.0.conv1d.bias"] = torch.zeros(16)
     with pytest.raises(ValueError, match="hybrid wiring"):
         weights.legacy_state_to_attention(hybrid)
+
+
+CHILD_BN = r"""
+import hashlib, importlib, sys, warnings
+warnings.filterwarnings("ignore")
+sys.path.insert(0, %(root)r)
+import torch
+from hello_b200 import arch, weights, _lib
+from oracle import ref_model
+M = ref_model.import_reference()
+kind, path = sys.argv[1], sys.argv[2]
+if kind == "batchnorm":
+    import architectures.read_convolver as rc, architectures.compressor_conv_small as cc, architectures.xattn_subtract as xa
+    for m in (rc, cc, xa):
+        m.weight_norm = False
+        m.gen_config()
+    moe = M.create_moe_attention_model({"read_conv0": rc.config, "compressor0": cc.config, "xattn0": xa.config}).eval()
+    state = weights.init_batchnorm_state([(k, tuple(v.shape)) for k, v in moe.state_dict().items()], seed=13)
+    moe.load_state_dict(state)
+else:                                                   # the Softplus / no-normalisation experiment configuration
+    cfgd = importlib.import_module("moe_attention_config_single_tech_old_equivalent_layer_norm").configDict
+    moe = M.create_moe_attention_model(cfgd).eval()
+torch.save(M.createMoEFullMergedAdvancedModelWrapper(moe.eval()).eval(), path)
+from hello_b200 import model
+try:
+    cfg, sd, provide = model.read_wrapper(path)
+    print("RESULT", cfg.name, hashlib.sha256(weights.pack_blob(cfg, sd)).hexdigest())
+except _lib.HelloMoEError as e:
+    print("REFUSED", str(e)[:160].replace("\n", " "))
+"""
+
+
+@pytest.mark.skipif(not ref_model.available(), reason="the reference's python modules are not available")
+def test_batchnorm_wrapper_is_folded_and_softplus_model_is_refused(tmp_path):
+    """A .wrapper.dnn of a model built without weight-norm loads (BatchNorm1d folded, same blob as folding the state dict
+    directly); the reference's Softplus experiment (moe_attention_config_single_tech_old_equivalent_layer_norm.py) is
+    refused by name instead of being run with the wrong activation."""
+    from helpers import batchnorm_params
+    run = lambda kind: subprocess.run([sys.executable, "-c", CHILD_BN % {"root": ROOT}, kind, str(tmp_path / (kind + ".dnn"))],
+                                      capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    out = run("batchnorm")
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+    _, params = batchnorm_params()
+    assert line[1] == "single_tech"
+    assert line[2] == hashlib.sha256(weights.pack_blob(arch.CONFIGS["single_tech"], params)).hexdigest()
+    out = run("softplus")
+    assert out.returncode == 0, out.stderr[-2000:]
+    refused = [l for l in out.stdout.splitlines() if l.startswith("REFUSED")]
+    assert refused and "Softplus" in refused[-1], out.stdout
