@@ -14,6 +14,7 @@ ABI_VERSION = 3
 
 LAYOUT_RCL, LAYOUT_RLC = 0, 1
 META_NONE, META_SITE, META_REF = 0, 1, 2
+COMBINE_NONE, COMBINE_CONV, COMBINE_SUM = 0, 1, 2
 PREC_FP32, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 

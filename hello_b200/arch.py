@@ -184,6 +184,8 @@ class ModelConfig:
     addendum: bool = False               # transfer-learning model: two more residual blocks on top of the read convolvers,
                                          # the compressors and the (single) expert head (architectures/*_addendum.py)
     addendum_blocks: int = 2             # the shipped addenda have two; other depths run too (fused kernels cover <= 2)
+    legacy_sum: bool = False             # legacy MoEMergedAdvanced hybrid wiring (useAdditive, no ConvCombiners): the hybrid
+                                         # allele feature is compressor0 + compressor1, the hybrid site frame its per-site sum
 
     @property
     def hybrid(self) -> bool:
@@ -245,6 +247,11 @@ CONFIGS = {
     "hybrid_full": ModelConfig("hybrid_full", (6, 6), (True, True, True), True, "meta_convolver"),
     # ..._no_ensemble_wide.py (2x channels everywhere)
     "hybrid_no_ensemble_wide": ModelConfig("hybrid_no_ensemble_wide", (6, 6), (False, False, True), True, None, 2),
+    # legacy wiring MoEMergedAdvanced (python/MixtureOfExpertsAdvanced.py:255-484) with two technologies, useAdditive, no
+    # ConvCombiners, built by createMoEFullMergedAdvancedModel (:614-654) from MoEReadConvolverDeeper / ExpertAlleleConvolverDeeper
+    # / ExpertGraphConvolverDeeper / MetaCombinerDeeper: three experts on 2a - s, meta on the summed site frame
+    "legacy_hybrid_additive": ModelConfig("legacy_hybrid_additive", (6, 6), (True, True, True), False, "meta_convolver",
+                                          legacy_sum=True),
     # moe_attention_config_single_tech_old_equivalent_weight_norm_addendum.py stacked on the single-tech model by
     # MixtureOfExpertsAdvancedXferLearning.build_on_top (:94-183)
     "single_tech_addendum": ModelConfig("single_tech_addendum", (6,), (True, False, False), False, None, 1, True),

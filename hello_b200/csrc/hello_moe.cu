@@ -283,6 +283,14 @@ struct Runner {
         return launched("two_a_minus_s");
     }
 
+    bool add2(const float* a, const float* b, float* out, long long elems) {
+        if (dry || elems == 0) return true;
+        add2_kernel<<<grid_for(elems / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a),
+                                                            reinterpret_cast<const float4*>(b),
+                                                            reinterpret_cast<float4*>(out), elems / 4);
+        return launched("add2");
+    }
+
     bool concat2(const float* a, const float* b, float* out, long long rows, int ca, int cb) {
         if (dry || rows == 0) return true;
         concat2_kernel<<<grid_for(rows * (ca + cb) / 4, 256), 256, 0, st>>>(
@@ -400,7 +408,12 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         float* c2 = ar.allocf(na * comp_e);
         float* s2 = ar.allocf(ns * comp_e);
         size_t m = ar.mark();
-        if (h->comb[0] && h->comb[1]) {
+        if (cfg.has_combiners == HELLO_COMBINE_SUM) {
+            // legacy wiring (MoEMergedAdvanced, useAdditive, no ConvCombiners; MixtureOfExpertsAdvanced.py:408-436): the hybrid
+            // allele feature is the sum of the two technologies' and the hybrid site frame is reduceSlots of THAT
+            if (!run.add2(c_t[0], c_t[1], c2, na * comp_e)) return false;
+            if (!run.segsum(c2, s2, dry ? nullptr : in->d_site_allele_off + ck.s0, ns, (int)ck.a0, comp_e)) return false;
+        } else if (h->comb[0] && h->comb[1]) {
             // the kernel reads the two technologies' tensors as the two K-halves: no concat buffer
             if (!run.comb(h->comb[0], c_t[0], c_t[1], cc, na, c2)) return false;
             if (!run.comb(h->comb[1], s_t[0], s_t[1], cc, ns, s2)) return false;
@@ -591,8 +604,8 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
     }
     if (ok && cfg->xattn_present[2]) {
         int l, c;
-        ok = cfg->n_tech == 2 && cfg->has_combiners;
-        for (int k = 0; k < 2 && ok; ++k)
+        ok = cfg->n_tech == 2 && (cfg->has_combiners == HELLO_COMBINE_CONV || cfg->has_combiners == HELLO_COMBINE_SUM);
+        for (int k = 0; k < 2 && ok && cfg->has_combiners == HELLO_COMBINE_CONV; ++k)
             ok = net_out_shape(h->nets[NET_CB0 + k], h->comp_len, 2 * h->comp_ch, &l, &c) && l == h->comp_len &&
                  c == h->comp_ch;
     }
@@ -634,7 +647,7 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
             h->head[id] = headconv_tc_create(net, in_len, h->d_weights, h->h_weights.data(), cfg->precision, terr, &fl);
             if (h->head[id]) h->tail[id].assign(net.begin() + fl, net.end());
         }
-        if (cfg->has_combiners && cfg->xattn_present[2] && h->comp_len == cc::L) {
+        if (cfg->has_combiners == HELLO_COMBINE_CONV && cfg->xattn_present[2] && h->comp_len == cc::L) {
             for (int k = 0; k < 2; ++k)
                 h->comb[k] = combconv_tc_create(h->nets[NET_CB0 + k], h->d_weights, h->h_weights.data(), cfg->precision, terr);
             if (!h->comb[0] || !h->comb[1]) {

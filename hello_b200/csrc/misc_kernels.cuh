@@ -81,6 +81,15 @@ __global__ void two_a_minus_s_kernel(const float4* __restrict__ allele, const fl
     }
 }
 
+// elementwise sum of two tensors: the legacy wiring's hybrid allele feature `alleleLevelConv0 + alleleLevelConv1`
+// (MoEMergedAdvanced.forward with useAdditive and no ConvCombiner, python/MixtureOfExpertsAdvanced.py:408-412)
+__global__ void add2_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = __ldg(a + i), y = __ldg(b + i);
+        out[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    }
+}
+
 // channel concat of two channel-last tensors (ConcatenateChannels, python/NNTools.py:727-733)
 __global__ void concat2_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ out,
                                long long rows, int ca4, int cb4) {

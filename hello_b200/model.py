@@ -138,7 +138,7 @@ class MoEEngine:
             c.read_channels[t] = ch
         for e in range(3):
             c.xattn_present[e] = int(cfg.xattn_present[e])
-        c.has_combiners = int(cfg.combiners)
+        c.has_combiners = _lib.COMBINE_SUM if cfg.legacy_sum else (_lib.COMBINE_CONV if cfg.combiners else _lib.COMBINE_NONE)
         c.meta_kind = {None: _lib.META_NONE, "meta_convolver": _lib.META_SITE,
                        "meta_convolver_ref": _lib.META_REF}[cfg.meta]
         c.feature_length = arch.FEATURE_LENGTH

@@ -142,42 +142,55 @@ LEGACY_PREFIXES = ("readConv", "alleleConv", "expert", "siteConvCombiner.")     
 def legacy_state_to_attention(state_dict) -> Dict[str, torch.Tensor]:
     """State dict of the legacy wiring ``MoEMergedAdvanced`` (python/MixtureOfExpertsAdvanced.py:255-484, built by
     ``createMoEFullMergedAdvancedModel`` :614-654 from MoEReadConvolverDeeper / ExpertAlleleConvolverDeeper /
-    ExpertGraphConvolverDeeper with ``useAdditive``) -> the ``MoEAttention`` names this package uses.
+    ExpertGraphConvolverDeeper / MetaCombinerDeeper with ``useAdditive``) -> the ``MoEAttention`` names this package uses.
 
-    Single technology only: there the legacy model computes exactly MoEAttention's function -- per-allele read sums,
-    allele convolver (= compressor), site frame = sum of the allele frames, expert input ``a - (s - a)`` (:374-379), the same
-    layers -- and its parameters are registered in the same order, so the k-th tensor of ``readConv0 / alleleConv0 /
-    expert0`` is the k-th tensor of ``read_convolver0 / compressor0 / xattn0`` (only the Sequential slot numbers differ: the
-    live xattn has two parameter-free front-end modules).  The legacy HYBRID wiring (allele features of the two technologies
-    added or ConvCombiner'ed, site frame = sum of THAT, meta on it, :408-436) is a different dataflow and is refused.
+    The legacy sub-networks have the layers of the live ones and register their parameters in the same order, so the k-th
+    tensor of ``readConv<t> / alleleConv<t> / expert<e> / meta`` is the k-th tensor of ``read_convolver<t> / compressor<t> /
+    xattn<e> / meta`` (only the Sequential slot numbers differ: the live xattn / meta have parameter-free front-end modules).
+    One technology: the legacy model computes exactly MoEAttention's function (expert input ``a - (s - a)``, :374-379) and maps
+    onto ``single_tech`` / ``single_tech_hp``.  Two technologies (three experts + meta): the hybrid allele feature is the SUM of
+    the two technologies' and the hybrid site frame its per-site sum (:408-436) -- ``legacy_hybrid_additive``.  The factory
+    builds ``meta`` without weight-norm (``make_network(configDict, "meta")``, :622), i.e. with BatchNorm1d even in a
+    weight-norm model: such a sub-network is folded (``_fold_batchnorm_net``).  ConvCombiner'ed legacy hybrids and separate
+    meta read convolvers (``alleleConvCombiner``, ``siteConvCombiner``, ``readConv*Meta``) are refused.
     A state dict that is not legacy is returned unchanged."""
     keys = list(state_dict.keys())
     if not keys or not any(k.startswith(LEGACY_PREFIXES) for k in keys):
         return dict(state_dict)
-    tops = {k.split(".", 1)[0] for k in keys}
-    if tops - {"readConv0", "alleleConv0", "expert0"}:
-        raise ValueError("legacy MoEMergedAdvanced hybrid wiring (%s) is not supported: only its single-technology form maps "
-                         "onto the MoEAttention layer tables" % sorted(tops - {"readConv0", "alleleConv0", "expert0"}))
-    sd = weight_norm_state(state_dict)
-    groups = {"readConv0": "read_convolver0", "alleleConv0": "compressor0", "expert0": "xattn0"}
+    rename = {"readConv0": "read_convolver0", "readConv1": "read_convolver1", "alleleConv0": "compressor0",
+              "alleleConv1": "compressor1", "expert0": "xattn0", "expert1": "xattn1", "expert2": "xattn2", "meta": "meta"}
+    groups = {}
+    for k in keys:
+        groups.setdefault(k.split(".", 1)[0], []).append(k)
+    extra = sorted(set(groups) - set(rename))
+    if extra:
+        raise ValueError("legacy MoEMergedAdvanced wiring with %s is not supported (ConvCombiner'ed hybrid features / separate "
+                         "meta read convolvers); supported: one technology, or two technologies with additive features" % extra)
+    want = {rename[g] for g in groups}
     for cfg in arch.CONFIGS.values():
-        if len(cfg.read_cin) != 1 or cfg.meta is not None:
+        if set(cfg.networks()) != want or cfg.addendum or (cfg.hybrid and not cfg.legacy_sum):
             continue
         out, ok = {}, True
-        for old, new in groups.items():
-            theirs = [k for k in sd if k.startswith(old + ".")]
-            ours = []
-            for prefix, vshape, _ in conv_keys(cfg, new):
-                ours += [prefix + ".bias", prefix + ".weight_g", prefix + ".weight_v"]
-            shapes = param_shapes(cfg)
-            if len(theirs) != len(ours) or any(tuple(sd[a].shape) != shapes[b] or a.rsplit(".", 1)[1] != b.rsplit(".", 1)[1]
-                                               for a, b in zip(theirs, ours)):
-                ok = False
+        shapes = param_shapes(cfg)
+        for old, ks in groups.items():
+            new = rename[old]
+            ours = conv_keys(cfg, new)
+            if any(k.endswith(".running_mean") for k in ks):
+                ok = _emit_folded(out, _fold_batchnorm_net(ks, state_dict), ours)
+            else:
+                theirs = [k for k in ks if not (k.endswith(".weight") and k[:-len(".weight")] + ".weight_v" in state_dict)]
+                names = []
+                for prefix, _, _ in ours:
+                    names += [prefix + ".bias", prefix + ".weight_g", prefix + ".weight_v"]
+                ok = len(theirs) == len(names) and all(tuple(state_dict[a].shape) == shapes[b] and
+                                                       a.rsplit(".", 1)[1] == b.rsplit(".", 1)[1] for a, b in zip(theirs, names))
+                if ok:
+                    out.update({b: state_dict[a] for a, b in zip(theirs, names)})
+            if not ok:
                 break
-            out.update({b: sd[a] for a, b in zip(theirs, ours)})
         if ok:
-            return out
-    raise ValueError("legacy state dict does not match any supported single-technology configuration")
+            return {k: out[k] for k in shapes}              # the live model's registration order
+    raise ValueError("legacy state dict does not match any supported configuration")
 
 
 BN_EPS = 1e-5          # torch.nn.BatchNorm1d default, what NNTools builds (python/NNTools.py:84-104)
@@ -187,85 +200,84 @@ def is_batchnorm_state(state_dict) -> bool:
     return any(k.endswith(".running_mean") for k in state_dict)
 
 
-def batchnorm_state_to_weight_norm(state_dict, eps: float = BN_EPS) -> Dict[str, torch.Tensor]:
-    """State dict of a model built WITHOUT weight-norm -- plain Conv1d / Linear followed (or, in the pooled head, preceded)
-    by ``BatchNorm1d`` (``norm_type="BatchNorm1d"``, the default of python/NNTools.py:27-45,72-115,118-294,517-566 when an
-    architecture module has ``weight_norm = False``) -- folded for inference and renamed to this package's layer tables.
-
-    Eval-mode batch-norm is the affine map ``y = (x - mean) / sqrt(var + eps) * gamma + beta``, so
+def _fold_batchnorm_net(keys, state_dict, eps: float = BN_EPS):
+    """[(w', b')] of one sub-network's convolution / linear layers in registration order, batch-norms folded:
       conv -> BN (same Sequential, next slot):   w' = w * s[o],  b' = (b - mean) * s + beta,   s = gamma / sqrt(var + eps)
       BN -> linear (pooled head, AvgPool -> Flatten -> BN -> Linear):  w' = w * s[i],  b' = b + w @ (beta - mean * s)
-    A convolution without a following BN (the 1x1 shortcut of a stride-2 residual block) is taken as it is.  The layers come
-    in the same order as in the weight-norm model, so the k-th folded layer of a sub-network is the k-th entry of
-    ``conv_keys``.  The result is expressed as ``weight_v = w'``, ``weight_g = |w'|`` (folding it back gives w' exactly).
-    The activation is not part of a state dict: BatchNorm models are taken to use ReLU, as every BN configuration of the
-    reference does (the LayerNorm / Softplus experiment is refused by read_wrapper, which sees the modules)."""
-    nets = {}
-    for k in state_dict:
-        nets.setdefault(k.split(".", 1)[0], []).append(k)
-
-    def stem_of(k):
-        return k.rsplit(".", 1)[0]
-
+    A convolution without a following BN (the 1x1 shortcut of a stride-2 residual block) is taken as it is."""
     def parent_slot(stem):
         parent, slot = stem.rsplit(".", 1)
         return parent, int(slot) if slot.isdigit() else None
 
-    folded_nets = {}
-    for net, keys in nets.items():
-        stems = []
-        for k in keys:
-            st = stem_of(k)
-            if not stems or stems[-1] != st:
-                stems.append(st)
-        layers = []                 # [w, b, stem] in order
-        pre_bn = None               # (scale, shift, stem) waiting for the linear of the pooled head
-        for st in stems:
-            g = lambda name: state_dict.get(st + "." + name)
-            if g("running_mean") is not None:
-                gamma, beta, mean, var = (g("weight").double(), g("bias").double(), g("running_mean").double(),
-                                          g("running_var").double())
-                sc = gamma / torch.sqrt(var + eps)
-                par, slot = parent_slot(st)
-                if layers and not layers[-1][3] and parent_slot(layers[-1][2]) == (par, slot - 1 if slot is not None else None) \
-                        and layers[-1][0].shape[0] == sc.numel():
-                    w, b = layers[-1][0], layers[-1][1]
-                    layers[-1][0] = w * sc.reshape((-1,) + (1,) * (w.dim() - 1))
-                    layers[-1][1] = (b - mean) * sc + beta
-                    layers[-1][3] = True
-                else:
-                    pre_bn = (sc, beta - mean * sc, st)
-            elif g("weight") is not None and g("weight").dim() >= 2:
-                w, b = g("weight").double(), g("bias").double()
-                if pre_bn is not None:
-                    sc, sh, bst = pre_bn
-                    if w.dim() != 2 or w.shape[1] != sc.numel() or parent_slot(bst)[0] != parent_slot(st)[0]:
-                        raise ValueError("BatchNorm %s is followed by %s: only conv -> BN and BN -> linear are folded" % (bst, st))
-                    b = b + w @ sh
-                    w = w * sc.reshape(1, -1)
-                    pre_bn = None
-                layers.append([w, b, st, False])
+    stems = []
+    for k in keys:
+        st = k.rsplit(".", 1)[0]
+        if not stems or stems[-1] != st:
+            stems.append(st)
+    layers = []                 # [w, b, stem, folded?] in order
+    pre_bn = None               # (scale, shift, stem) waiting for the linear of the pooled head
+    for st in stems:
+        g = lambda name: state_dict.get(st + "." + name)
+        if g("running_mean") is not None:
+            gamma, beta, mean, var = (g("weight").double(), g("bias").double(), g("running_mean").double(),
+                                      g("running_var").double())
+            sc = gamma / torch.sqrt(var + eps)
+            par, slot = parent_slot(st)
+            if layers and not layers[-1][3] and parent_slot(layers[-1][2]) == (par, slot - 1 if slot is not None else None) \
+                    and layers[-1][0].shape[0] == sc.numel():
+                w, b = layers[-1][0], layers[-1][1]
+                layers[-1][0] = w * sc.reshape((-1,) + (1,) * (w.dim() - 1))
+                layers[-1][1] = (b - mean) * sc + beta
+                layers[-1][3] = True
             else:
-                raise ValueError("state dict entry %s.* is neither a convolution / linear layer nor a BatchNorm1d" % st)
-        if pre_bn is not None:
-            raise ValueError("BatchNorm %s has no layer to fold into" % pre_bn[2])
-        folded_nets[net] = layers
+                pre_bn = (sc, beta - mean * sc, st)
+        elif g("weight") is not None and g("weight").dim() >= 2:
+            w, b = g("weight").double(), g("bias").double()
+            if pre_bn is not None:
+                sc, sh, bst = pre_bn
+                if w.dim() != 2 or w.shape[1] != sc.numel() or parent_slot(bst)[0] != parent_slot(st)[0]:
+                    raise ValueError("BatchNorm %s is followed by %s: only conv -> BN and BN -> linear are folded" % (bst, st))
+                b = b + w @ sh
+                w = w * sc.reshape(1, -1)
+                pre_bn = None
+            layers.append([w, b, st, False])
+        else:
+            raise ValueError("state dict entry %s.* is neither a convolution / linear layer nor a BatchNorm1d" % st)
+    if pre_bn is not None:
+        raise ValueError("BatchNorm %s has no layer to fold into" % pre_bn[2])
+    return [(w, b) for w, b, _, _ in layers]
+
+
+def _emit_folded(out, layers, ours) -> bool:
+    """Folded (w', b') layers -> weight_v = w', weight_g = |w'| (folding it back gives w' exactly), bias, under our names."""
+    if len(ours) != len(layers) or any(tuple(w.shape) != vs for (w, _), (_, vs, _) in zip(layers, ours)):
+        return False
+    for (w, b), (prefix, _, _) in zip(layers, ours):
+        v = w.float().contiguous()
+        out[prefix + ".bias"] = b.float().contiguous()
+        out[prefix + ".weight_g"] = torch.norm_except_dim(v, 2, 0)
+        out[prefix + ".weight_v"] = v
+    return True
+
+
+def batchnorm_state_to_weight_norm(state_dict, eps: float = BN_EPS) -> Dict[str, torch.Tensor]:
+    """State dict of a model built WITHOUT weight-norm -- plain Conv1d / Linear followed (or, in the pooled head, preceded)
+    by ``BatchNorm1d`` (``norm_type="BatchNorm1d"``, the default of python/NNTools.py:27-45,72-115,118-294,517-566 when an
+    architecture module has ``weight_norm = False``) -- folded for inference (``_fold_batchnorm_net``) and renamed to this
+    package's layer tables.  Eval-mode batch-norm is the affine map ``y = (x - mean) / sqrt(var + eps) * gamma + beta``.  The
+    layers come in the same order as in the weight-norm model, so the k-th folded layer of a sub-network is the k-th entry
+    of ``conv_keys``.  The activation is not part of a state dict: BatchNorm models are taken to use ReLU, as every BN
+    configuration of the reference does (the LayerNorm / Softplus experiment is refused by read_wrapper, which sees the
+    modules)."""
+    nets = {}
+    for k in state_dict:
+        nets.setdefault(k.split(".", 1)[0], []).append(k)
+    folded_nets = {net: _fold_batchnorm_net(keys, state_dict, eps) for net, keys in nets.items()}
     for cfg in arch.CONFIGS.values():
         if set(cfg.networks()) != set(folded_nets):
             continue
-        out, ok = {}, True
-        for net in cfg.networks():
-            ours = conv_keys(cfg, net)
-            theirs = folded_nets[net]
-            if len(ours) != len(theirs) or any(tuple(t[0].shape) != vs for t, (_, vs, _) in zip(theirs, ours)):
-                ok = False
-                break
-            for (w, b, _, _), (prefix, vshape, _) in zip(theirs, ours):
-                v = w.float().contiguous()
-                out[prefix + ".bias"] = b.float().contiguous()
-                out[prefix + ".weight_g"] = torch.norm_except_dim(v, 2, 0)
-                out[prefix + ".weight_v"] = v
-        if ok:
+        out = {}
+        if all(_emit_folded(out, folded_nets[net], conv_keys(cfg, net)) for net in cfg.networks()):
             return out
     raise ValueError("BatchNorm state dict does not match any supported HELLO MoE configuration")
 
@@ -305,6 +317,30 @@ def supported_state(state_dict) -> Dict[str, torch.Tensor]:
     if is_batchnorm_state(sd):
         return batchnorm_state_to_weight_norm(sd)
     return weight_norm_state(sd)
+
+
+def init_legacy_state(keys_and_shapes, cfg: arch.ModelConfig, seed: int = 13) -> Dict[str, torch.Tensor]:
+    """Deterministic values for a legacy-wiring reference model (``MoEMergedAdvanced``), in its own state-dict order: the
+    weight-normed sub-networks get ``init_params(cfg, seed)`` tensor by tensor (same registration order as the live
+    sub-network), a sub-network built with BatchNorm1d (the legacy factory's ``meta``) gets ``init_batchnorm_state``."""
+    rename = {"readConv0": "read_convolver0", "readConv1": "read_convolver1", "alleleConv0": "compressor0",
+              "alleleConv1": "compressor1", "expert0": "xattn0", "expert1": "xattn1", "expert2": "xattn2", "meta": "meta"}
+    params = init_params(cfg, seed)
+    shapes = param_shapes(cfg)
+    groups = {}
+    for k, shp in keys_and_shapes:
+        groups.setdefault(k.split(".", 1)[0], []).append((k, shp))
+    out = {}
+    for old, ks in groups.items():
+        if any(k.endswith(".running_mean") for k, _ in ks):
+            out.update(init_batchnorm_state(ks, seed))
+        else:
+            ours = [k for k in shapes if k.startswith(rename[old] + ".")]
+            assert len(ours) == len(ks), (old, len(ours), len(ks))
+            for (k, shp), k2 in zip(ks, ours):
+                assert tuple(shp) == shapes[k2], (k, k2)
+                out[k] = params[k2]
+    return {k: out[k] for k, _ in keys_and_shapes}
 
 
 def cfg_from_state_dict(params: Dict[str, torch.Tensor]) -> arch.ModelConfig:

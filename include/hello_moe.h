@@ -52,6 +52,11 @@ enum { HELLO_META_NONE = 0,
        HELLO_META_SITE = 1,    /* architectures/meta_convolver.py: input = combined site features             */
        HELLO_META_REF = 2 };   /* architectures/meta_convolver_ref.py: input = one-hot reference segment      */
 
+enum { HELLO_COMBINE_NONE = 0, /* no hybrid expert                                                            */
+       HELLO_COMBINE_CONV = 1, /* combiner0 (allele level) and combiner1 (site level): MoEAttention, :193-219       */
+       HELLO_COMBINE_SUM = 2 };/* legacy MoEMergedAdvanced with useAdditive and no ConvCombiners: allele features
+                                  added, site frame = sum of that over the site's alleles (:408-436)              */
+
 enum { HELLO_PREC_FP32 = 0,    /* fp32 FMA everywhere (CUDA cores)                                            */
        HELLO_PREC_BF16X3 = 1,  /* read convolver, compressor, combiner, xattn and meta_convolver on tcgen05:
                                   operands split into hi+lo bf16, three products, fp32 accumulate             */
@@ -63,7 +68,7 @@ typedef struct hello_cfg {
     int32_t n_tech;            /* 1 (single technology) or 2 (hybrid) */
     int32_t read_channels[2];  /* 6, or 7 with the haplotag channel */
     int32_t xattn_present[3];  /* expert heads xattn0/1/2 */
-    int32_t has_combiners;     /* combiner0 (allele level) and combiner1 (site level) */
+    int32_t has_combiners;     /* HELLO_COMBINE_*: how the two technologies' features become the hybrid expert's input */
     int32_t meta_kind;         /* HELLO_META_* */
     int32_t feature_length;    /* 150 */
     int32_t precision;         /* HELLO_PREC_* */

@@ -41,12 +41,18 @@ CASES = {
     # the legacy wiring MoEMergedAdvanced (python/MixtureOfExpertsAdvanced.py:255-484) in its single-technology form, built by
     # createMoEFullMergedAdvancedModel (:614-654) from the legacy architecture modules, useAdditive=True
     "legacy_single_tech": (6, 9, 110, False),
+    # the same legacy wiring with two technologies (three experts + meta, additive hybrid features, no ConvCombiners); the
+    # factory builds `meta` without weight-norm, i.e. with BatchNorm1d (make_network(configDict, "meta"), :622)
+    "legacy_hybrid_additive": (6, 8, 112, False),
     # built WITHOUT weight-norm: plain Conv1d / Linear + BatchNorm1d (the architecture modules' default, weight_norm = False),
     # eval mode, deterministic non-trivial running statistics; hello_b200 folds the batch-norms at load
     "single_tech_batchnorm": (6, 9, 111, False),
 }
 LEGACY_CONFIG = {"readConvNGS": "MoEReadConvolverDeeper", "alleleConvSingleNGS": "ExpertAlleleConvolverDeeper",
                  "graphConvSingleNGS": "ExpertGraphConvolverDeeper", "weight_norm": True, "kwargs": {"useAdditive": True}}
+LEGACY_HYBRID_CONFIG = dict(LEGACY_CONFIG, readConvTGS="MoEReadConvolverDeeper", alleleConvSingleTGS="ExpertAlleleConvolverDeeper",
+                            graphConvSingleTGS="ExpertGraphConvolverDeeper", graphConvHybrid="ExpertGraphConvolverDeeper",
+                            meta="MetaCombinerDeeper")
 
 
 def run_case(case: str) -> None:
@@ -58,7 +64,8 @@ def run_case(case: str) -> None:
     import MixtureOfExpertsAdvanced as M          # the reference
     from hello_b200 import arch, weights, synth
 
-    name = case.replace("_uniform", "").replace("legacy_", "").replace("_batchnorm", "")
+    name = case.replace("_uniform", "").replace("_batchnorm", "")
+    name = {"legacy_single_tech": "single_tech"}.get(name, name)
     n_sites, cov, seed, uniform = CASES[case]
     cfg = arch.CONFIGS[name]
     legacy = case.startswith("legacy_")
@@ -72,7 +79,7 @@ def run_case(case: str) -> None:
             m.gen_config()
         moe = M.create_moe_attention_model({"read_conv0": rc_.config, "compressor0": cc_.config, "xattn0": xa_.config}).eval()
     elif legacy:
-        moe = M.createMoEFullMergedAdvancedModel(dict(LEGACY_CONFIG)).eval()
+        moe = M.createMoEFullMergedAdvancedModel(dict(LEGACY_HYBRID_CONFIG if cfg.hybrid else LEGACY_CONFIG)).eval()
     elif name in arch.REFERENCE_ADDENDUM_MODULE:
         # transfer-learning model: the reference's build_on_top stacks the addendum networks on a trained base model
         # (MixtureOfExpertsDNNFastXferLearning.py:494-502 does this on a DataParallel(WrapperForDataParallel(moe)))
@@ -99,12 +106,14 @@ def run_case(case: str) -> None:
         params = weights.batchnorm_state_to_weight_norm(moe.state_dict())
         assert list(params.keys()) == list(shapes.keys())
     elif legacy:
-        # same parameters in the same registration order under the legacy names: hello_b200's mapping must invert this
-        assert [tuple(v.shape) for v in sd.values()] == list(shapes.values())
-        legacy_sd = {k: params[k2] for k, k2 in zip(sd.keys(), shapes.keys())}
+        # the parameters of the live sub-networks in the same registration order under the legacy names (a BatchNorm-built
+        # `meta` gets deterministic batch-norm state): hello_b200's mapping must invert this
+        legacy_sd = weights.init_legacy_state([(k, tuple(v.shape)) for k, v in sd.items()], cfg, seed=13)
         moe.load_state_dict(legacy_sd)
-        back = weights.legacy_state_to_attention(moe.state_dict())
-        assert list(back.keys()) == list(shapes.keys()) and all(torch.equal(back[k], params[k]) for k in shapes)
+        moe = moe.eval()
+        params = weights.supported_state(moe.state_dict())
+        assert list(params.keys()) == list(shapes.keys()), [(a, b) for a, b in zip(params, shapes) if a != b][:4]
+        bn_keys = [(k, tuple(v.shape)) for k, v in sd.items()]
     else:
         assert list(sd.keys()) == list(shapes.keys()), "arch.py does not describe the reference model"
         for k in sd:

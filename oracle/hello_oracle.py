@@ -121,8 +121,12 @@ class OracleModel:
         e1, s1, c1 = self._compress_and_predict(red1, aps, 1)
         e2, site_for_meta = None, None
         if cfg.xattn_present[2]:
-            c2 = self.nets["combiner0"](torch.cat((c0, c1), dim=1))
-            s2 = self.nets["combiner1"](torch.cat((s0, s1), dim=1))
+            if cfg.legacy_sum:      # MoEMergedAdvanced.forward, useAdditive without ConvCombiners (MixtureOfExpertsAdvanced.py:408-436)
+                c2 = c0 + c1
+                s2 = reduce_slots(c2, aps)
+            else:
+                c2 = self.nets["combiner0"](torch.cat((c0, c1), dim=1))
+                s2 = self.nets["combiner1"](torch.cat((s0, s1), dim=1))
             e2 = self.nets["xattn2"](0 + 2 * c2 + (-1) * torch.repeat_interleave(s2, aps, dim=0))
             site_for_meta = s2
         meta = None

@@ -81,8 +81,9 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
-    # outside tests/ the oracle is imported only by smoke() and by the CPU-baseline legs of the two benchmarks
-    allowed = {"__graft_entry__.py", "bench.py", os.path.join("tools", "bench_encoder.py")}
+    # outside tests/ the oracle is imported only by smoke() and by the CPU-baseline / checker legs of the benchmarks
+    allowed = {"__graft_entry__.py", "bench.py", os.path.join("tools", "bench_encoder.py"),
+               os.path.join("tools", "bench_serving.py")}        # its reference-latency leg times oracle/_ref/python
     for rel in ["__graft_entry__.py", "bench.py"] + [os.path.join("tools", f) for f in os.listdir(os.path.join(ROOT, "tools"))]:
         if rel.endswith(".py") and rel not in allowed:
             text = open(os.path.join(ROOT, rel)).read()

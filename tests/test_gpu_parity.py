@@ -376,6 +376,35 @@ def test_batchnorm_built_model_matches_reference_golden(gpu, precision):
     check_log_probs(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], precision, "batchnorm")
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_legacy_hybrid_wiring_matches_reference_golden(gpu, precision):
+    """The legacy MoEMergedAdvanced wiring with two technologies (additive hybrid features, BatchNorm-built meta): the state
+    dict of the reference's own model is renamed / folded at load and the CUDA forward (HELLO_COMBINE_SUM) reproduces the
+    reference's logits, meta weights, pair probabilities and calls (tests/golden/legacy_hybrid_additive.npz)."""
+    from helpers import legacy_params
+    cfg, pl, g = load_golden("legacy_hybrid_additive")
+    state, params = legacy_params()
+    net = gpu.MoEAttentionB200.from_state_dict(state, device=DEV, precision=precision)
+    assert net.cfg.name == "legacy_hybrid_additive"
+    res = net.forward(*pl.forward_args())
+    logits, meta = flat_result(cfg, res)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=TOL_LOGIT[precision])
+    np.testing.assert_allclose(meta.numpy(), g["meta"], rtol=0, atol=TOL_PROB[precision])
+    r = net.last_result
+    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], rtol=0, atol=TOL_PROB[precision])
+    np.testing.assert_allclose(r.pair_prob[1:].cpu().numpy(), g["pair_experts"], rtol=0, atol=TOL_PROB[precision])
+    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB[precision], "legacy_hybrid_additive/" + precision)
+    check_log_probs(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], precision, "legacy hybrid")
+    # more sites than the fixture holds, against the oracle
+    pl2 = synth.make_pileups(40, coverage=12, channels=cfg.read_cin, seed=99)
+    from oracle import hello_oracle as O
+    want = O.OracleModel(cfg, params).forward(*pl2.forward_args())
+    got = net.forward(*pl2.forward_args())
+    lg, mg = flat_result(cfg, got)
+    lr, mr = flat_result(cfg, want)
+    assert (lg - lr).abs().max().item() < TOL_LOGIT[precision] and (mg - mr).abs().max().item() < TOL_PROB[precision]
+
+
 def check_calls(result, ref_mixed, ref_best, tol, what="", max_tight_share=MAX_TIGHT_SHARE):
     """Genotype calls bit-exact wherever the reference's own top-2 margin exceeds 2*tol; the number of tight-margin
     sites (compared only through their probabilities) is printed and bounded."""

@@ -86,6 +86,37 @@ def test_batchnorm_model_is_folded_like_the_reference_evaluates_it():
     np.testing.assert_allclose(np.array(mixed, np.float32), g["pair_mixed"], rtol=0, atol=TOL)
 
 
+def test_legacy_hybrid_wiring_matches_the_reference():
+    """tests/golden/legacy_hybrid_additive.npz: MoEMergedAdvanced (python/MixtureOfExpertsAdvanced.py:255-484) with two
+    technologies built by createMoEFullMergedAdvancedModel (:614-654): three experts on 2a - s, the hybrid allele feature the
+    SUM of the two technologies' (:408-412), its site frame the per-site sum of that (:425-436), meta (BatchNorm-built by the
+    factory) on it.  The state dict is renamed / folded by weights.supported_state; the oracle reproduces logits, meta weights
+    and the per-site wrapper outputs of the reference."""
+    from helpers import legacy_params
+    cfg, pl, g = load_golden("legacy_hybrid_additive")
+    assert cfg.legacy_sum and cfg.returns_meta
+    state, params = legacy_params()
+    assert any(k.startswith("readConv1.") for k in state) and weights.is_batchnorm_state(state)
+    assert weights.cfg_from_state_dict(params).name == "legacy_hybrid_additive"
+    assert weights.params_digest(params) == str(g["digest"])
+    torch.set_num_threads(1)
+    model = O.OracleModel(cfg, params)
+    res = model.forward(*pl.forward_args())
+    logits, meta = flat_result(cfg, res)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=TOL)
+    np.testing.assert_allclose(meta.numpy(), g["meta"], rtol=0, atol=TOL)
+    mixed, best = [], []
+    for s in range(pl.n_sites):
+        fd, seg = pl.site_feature_dict(s)
+        r = O.wrapper_forward(model, fd, seg, provide_predictions=True)
+        mixed += [float(v) for v in r[0].values()]
+        key, _, _ = O.call_genotype(r[0])
+        names = list(fd.keys())
+        best.append([names.index(key[0]), names.index(key[1])])
+    np.testing.assert_allclose(np.array(mixed, np.float32), g["pair_mixed"], rtol=0, atol=TOL)
+    assert np.array_equal(np.array(best, np.int32), g["best_pair"])
+
+
 def test_batched_equals_per_site_tail():
     cfg, pl, g = load_golden("hybrid_full")
     res = O.OracleModel(cfg, params_for(cfg)).forward(*pl.forward_args())

@@ -105,10 +105,14 @@ def test_legacy_wiring_state_dict_maps_onto_single_tech():
     assert all(torch.equal(back[k], params[k]) for k in params)
     assert weights.cfg_from_state_dict(back).name == "single_tech"
     assert weights.legacy_state_to_attention(params) == dict(params)               # non-legacy dicts pass through
-    hybrid = dict(legacy)
-    hybrid["readConv1.network.0.conv1d.bias"] = torch.zeros(16)
-    with pytest.raises(ValueError, match="hybrid wiring"):
-        weights.legacy_state_to_attention(hybrid)
+    combined = dict(legacy)
+    combined["alleleConvCombiner.network.0.conv1d.bias"] = torch.zeros(16)      # ConvCombiner'ed legacy hybrids are refused
+    with pytest.raises(ValueError, match="ConvCombiner"):
+        weights.legacy_state_to_attention(combined)
+    broken = dict(legacy)
+    broken["readConv1.network.0.conv1d.bias"] = torch.zeros(16)                # an incomplete second technology
+    with pytest.raises(ValueError, match="does not match"):
+        weights.legacy_state_to_attention(broken)
 
 
 CHILD_BN = r"""
