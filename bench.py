@@ -211,7 +211,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "wiring": cfg_name, "sites_per_step": n_sites, "coverage": cov},
-        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": workers, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": workers, "kind": kind, "sample": sample,
+                         "per_core": value / max(workers, 1)},
         "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
