@@ -590,31 +590,46 @@ def run_ours(args):
         from hello_b200 import synth as _synth
         batch = reads = results = result = hb = out = None
         torch.cuda.empty_cache()
-        gen_sites = 32768
-        times = max(1, min(args.e2e_packed_sites, S) // gen_sites)
-        packed, rr, rs = _synth.make_packed_reads(gen_sites, coverage=cov, seed=13 + rank, hp=cfg.read_cin[0] == 7)
-        aro_p, sao_p = _synth.packed_allele_csr(np.diff(packed.read_base), seed=13 + rank)
-        packed, rr, rs = _synth.tile_packed_reads(packed, rr, rs, times)
-        rep = lambda off: torch.cat([off[:-1].long() + k * int(off[-1]) for k in range(times)] +
-                                    [torch.tensor([times * int(off[-1])])]).to(torch.int32)
-        hpb = model.HostPackedBatch(packed, (rr,), (rs,), (rep(aro_p),), rep(sao_p), pin=True)
-        S_p = hpb.n_sites
-        chunk_p = max(8192, min(65536, S_p // 8))
-        engine.forward_host_packed(hpb, chunk_p)                           # warm-up (allocations, pinned outputs)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            out_p = engine.forward_host_packed(hpb, chunk_p)
+        # an extra figure must never cost the headline line: set-up failures are reported in the record, and the ranks agree
+        # on whether to enter the timed region (a rank waiting alone in a barrier would hang the job)
+        prep_err, hpb = None, None
+        try:
+            gen_sites = 32768
+            times = max(1, min(args.e2e_packed_sites, S) // gen_sites)
+            packed, rr, rs = _synth.make_packed_reads(gen_sites, coverage=cov, seed=13 + rank, hp=cfg.read_cin[0] == 7)
+            aro_p, sao_p = _synth.packed_allele_csr(np.diff(packed.read_base), seed=13 + rank)
+            packed, rr, rs = _synth.tile_packed_reads(packed, rr, rs, times)
+            rep = lambda off: torch.cat([off[:-1].long() + k * int(off[-1]) for k in range(times)] +
+                                        [torch.tensor([times * int(off[-1])])]).to(torch.int32)
+            hpb = model.HostPackedBatch(packed, (rr,), (rs,), (rep(aro_p),), rep(sao_p), pin=True)
+            S_p = hpb.n_sites
+            chunk_p = max(8192, min(65536, S_p // 8))
+            engine.forward_host_packed(hpb, chunk_p)                       # warm-up (allocations, pinned outputs)
             torch.cuda.synchronize(dev)
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
-        e2e_packed = {"value": world * S_p * args.steps / dt, "unit": "sites/s", "h2d_bytes_per_step": hpb.input_nbytes(),
-                      "d2h_bytes_per_step": out_p.nbytes(), "sites_per_gpu": S_p, "rows_per_gpu": int(rr.size),
-                      "h2d_bytes_per_row": hpb.input_nbytes() / max(int(rr.size), 1),
-                      "api": "MoEEngine.forward_host_packed (pinned host buffers of aligned reads -- bases, qualities, CIGARs, "
-                             "reference windows -- streamed in %d-site ranges; hello_encode_reads builds the [R,150,C] rows "
-                             "on the GPU; then hello_moe_forward_range)" % chunk_p,
-                      "data": "%d generated sites (synth.make_packed_reads) tiled %d times" % (gen_sites, times)}
+        except Exception as exc:
+            prep_err = repr(exc)[:300]
+        all_ok = prep_err is None
+        if world > 1:
+            t = torch.tensor([1 if all_ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            all_ok = bool(t.item())
+        if not all_ok:
+            e2e_packed = {"error": prep_err or "set-up failed on another rank"}
+        else:
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                out_p = engine.forward_host_packed(hpb, chunk_p)
+                torch.cuda.synchronize(dev)
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            e2e_packed = {"value": world * S_p * args.steps / dt, "unit": "sites/s", "h2d_bytes_per_step": hpb.input_nbytes(),
+                          "d2h_bytes_per_step": out_p.nbytes(), "sites_per_gpu": S_p, "rows_per_gpu": int(rr.size),
+                          "h2d_bytes_per_row": hpb.input_nbytes() / max(int(rr.size), 1),
+                          "api": "MoEEngine.forward_host_packed (pinned host buffers of aligned reads -- bases, qualities, CIGARs, "
+                                 "reference windows -- streamed in %d-site ranges; hello_encode_reads builds the [R,150,C] rows "
+                                 "on the GPU; then hello_moe_forward_range)" % chunk_p,
+                          "data": "%d generated sites (synth.make_packed_reads) tiled %d times" % (gen_sites, times)}
         hpb = out_p = None
 
     if rank != 0:
