@@ -136,7 +136,11 @@ def weight_norm_state(state_dict) -> Dict[str, torch.Tensor]:
     return out
 
 
-LEGACY_PREFIXES = ("readConv", "alleleConv", "expert", "siteConvCombiner.")     # (`meta.` exists in both wirings)
+LEGACY_PREFIXES = ("readConv", "alleleConv", "expert", "siteConvCombiner.")     # (`meta.` exists in both wirings;
+                                                                                 # "alleleConv" also covers alleleConvCombiner)
+LEGACY_RENAME = {"readConv0": "read_convolver0", "readConv1": "read_convolver1", "alleleConv0": "compressor0",
+                 "alleleConv1": "compressor1", "expert0": "xattn0", "expert1": "xattn1", "expert2": "xattn2", "meta": "meta",
+                 "alleleConvCombiner": "combiner0", "siteConvCombiner": "combiner1"}
 
 
 def legacy_state_to_attention(state_dict) -> Dict[str, torch.Tensor]:
@@ -149,26 +153,34 @@ def legacy_state_to_attention(state_dict) -> Dict[str, torch.Tensor]:
     xattn<e> / meta`` (only the Sequential slot numbers differ: the live xattn / meta have parameter-free front-end modules).
     One technology: the legacy model computes exactly MoEAttention's function (expert input ``a - (s - a)``, :374-379) and maps
     onto ``single_tech`` / ``single_tech_hp``.  Two technologies (three experts + meta): the hybrid allele feature is the SUM of
-    the two technologies' and the hybrid site frame its per-site sum (:408-436) -- ``legacy_hybrid_additive``.  The factory
-    builds ``meta`` without weight-norm (``make_network(configDict, "meta")``, :622), i.e. with BatchNorm1d even in a
-    weight-norm model: such a sub-network is folded (``_fold_batchnorm_net``).  ConvCombiner'ed legacy hybrids and separate
-    meta read convolvers (``alleleConvCombiner``, ``siteConvCombiner``, ``readConv*Meta``) are refused.
+    the two technologies' and the hybrid site frame its per-site sum (:408-436) -- ``legacy_hybrid_additive``.  With BOTH
+    ``alleleConvCombiner`` and ``siteConvCombiner`` (``ConvCombiner`` = concatenate channels, then a network, :37-44; the
+    reference's ``ConvCombinerResNetDeeper`` has the layers of ``architectures/conv_combiner.py``) the hybrid allele feature is
+    ``alleleConvCombiner(a0, a1)``, the hybrid site frame ``siteConvCombiner(s0, s1)`` and meta reads that frame (:408-459):
+    exactly MoEAttention's three-expert wiring -- ``hybrid_full``.  The factory builds ``meta`` without weight-norm
+    (``make_network(configDict, "meta")``, :622), i.e. with BatchNorm1d even in a weight-norm model, and the legacy combiner
+    modules have no weight-norm switch at all: such sub-networks are folded (``_fold_batchnorm_net``).  A legacy hybrid with
+    only ONE of the two combiners, the concatenating form (``useAdditive=False``: experts twice as wide, no layer table here)
+    and separate meta read convolvers (``readConv*Meta``) are refused.
     A state dict that is not legacy is returned unchanged."""
     keys = list(state_dict.keys())
     if not keys or not any(k.startswith(LEGACY_PREFIXES) for k in keys):
         return dict(state_dict)
-    rename = {"readConv0": "read_convolver0", "readConv1": "read_convolver1", "alleleConv0": "compressor0",
-              "alleleConv1": "compressor1", "expert0": "xattn0", "expert1": "xattn1", "expert2": "xattn2", "meta": "meta"}
+    rename = LEGACY_RENAME
     groups = {}
     for k in keys:
         groups.setdefault(k.split(".", 1)[0], []).append(k)
     extra = sorted(set(groups) - set(rename))
-    if extra:
-        raise ValueError("legacy MoEMergedAdvanced wiring with %s is not supported (ConvCombiner'ed hybrid features / separate "
-                         "meta read convolvers); supported: one technology, or two technologies with additive features" % extra)
+    n_comb = ("alleleConvCombiner" in groups) + ("siteConvCombiner" in groups)
+    if extra or n_comb == 1:
+        raise ValueError("legacy MoEMergedAdvanced wiring with %s is not supported (separate meta read convolvers, or only one "
+                         "of alleleConvCombiner / siteConvCombiner); supported: one technology, or two technologies with "
+                         "additive features, summed or combined by both ConvCombiners"
+                         % (extra or sorted(g for g in groups if g.endswith("Combiner"))))
     want = {rename[g] for g in groups}
     for cfg in arch.CONFIGS.values():
-        if set(cfg.networks()) != want or cfg.addendum or (cfg.hybrid and not cfg.legacy_sum):
+        # two technologies: summed hybrid features (legacy_sum) without combiners, MoEAttention's own wiring with them
+        if set(cfg.networks()) != want or cfg.addendum or cfg.width != 1 or (cfg.hybrid and cfg.legacy_sum != (n_comb == 0)):
             continue
         out, ok = {}, True
         shapes = param_shapes(cfg)
@@ -323,8 +335,7 @@ def init_legacy_state(keys_and_shapes, cfg: arch.ModelConfig, seed: int = 13) ->
     """Deterministic values for a legacy-wiring reference model (``MoEMergedAdvanced``), in its own state-dict order: the
     weight-normed sub-networks get ``init_params(cfg, seed)`` tensor by tensor (same registration order as the live
     sub-network), a sub-network built with BatchNorm1d (the legacy factory's ``meta``) gets ``init_batchnorm_state``."""
-    rename = {"readConv0": "read_convolver0", "readConv1": "read_convolver1", "alleleConv0": "compressor0",
-              "alleleConv1": "compressor1", "expert0": "xattn0", "expert1": "xattn1", "expert2": "xattn2", "meta": "meta"}
+    rename = LEGACY_RENAME
     params = init_params(cfg, seed)
     shapes = param_shapes(cfg)
     groups = {}

@@ -44,6 +44,9 @@ CASES = {
     # the same legacy wiring with two technologies (three experts + meta, additive hybrid features, no ConvCombiners); the
     # factory builds `meta` without weight-norm, i.e. with BatchNorm1d (make_network(configDict, "meta"), :622)
     "legacy_hybrid_additive": (6, 8, 112, False),
+    # ... and with both ConvCombiners (alleleConvCombiner / siteConvCombiner = ConvCombinerResNetDeeper, built with BatchNorm1d:
+    # the module has no weight-norm switch): the three-expert wiring of MoEAttention, i.e. hello_b200's `hybrid_full`
+    "legacy_hybrid_combiners": (6, 8, 113, False),
     # built WITHOUT weight-norm: plain Conv1d / Linear + BatchNorm1d (the architecture modules' default, weight_norm = False),
     # eval mode, deterministic non-trivial running statistics; hello_b200 folds the batch-norms at load
     "single_tech_batchnorm": (6, 9, 111, False),
@@ -53,6 +56,10 @@ LEGACY_CONFIG = {"readConvNGS": "MoEReadConvolverDeeper", "alleleConvSingleNGS":
 LEGACY_HYBRID_CONFIG = dict(LEGACY_CONFIG, readConvTGS="MoEReadConvolverDeeper", alleleConvSingleTGS="ExpertAlleleConvolverDeeper",
                             graphConvSingleTGS="ExpertGraphConvolverDeeper", graphConvHybrid="ExpertGraphConvolverDeeper",
                             meta="MetaCombinerDeeper")
+LEGACY_COMBINERS_CONFIG = dict(LEGACY_HYBRID_CONFIG, alleleConvCombiner="ConvCombinerResNetDeeper",
+                               siteConvCombiner="ConvCombinerResNetDeeper")
+LEGACY_CASES = {"legacy_single_tech": ("single_tech", LEGACY_CONFIG), "legacy_hybrid_additive": ("legacy_hybrid_additive", LEGACY_HYBRID_CONFIG),
+                "legacy_hybrid_combiners": ("hybrid_full", LEGACY_COMBINERS_CONFIG)}
 
 
 def run_case(case: str) -> None:
@@ -65,7 +72,7 @@ def run_case(case: str) -> None:
     from hello_b200 import arch, weights, synth
 
     name = case.replace("_uniform", "").replace("_batchnorm", "")
-    name = {"legacy_single_tech": "single_tech"}.get(name, name)
+    name = LEGACY_CASES[name][0] if name in LEGACY_CASES else name
     n_sites, cov, seed, uniform = CASES[case]
     cfg = arch.CONFIGS[name]
     legacy = case.startswith("legacy_")
@@ -79,7 +86,7 @@ def run_case(case: str) -> None:
             m.gen_config()
         moe = M.create_moe_attention_model({"read_conv0": rc_.config, "compressor0": cc_.config, "xattn0": xa_.config}).eval()
     elif legacy:
-        moe = M.createMoEFullMergedAdvancedModel(dict(LEGACY_HYBRID_CONFIG if cfg.hybrid else LEGACY_CONFIG)).eval()
+        moe = M.createMoEFullMergedAdvancedModel(dict(LEGACY_CASES[case][1])).eval()
     elif name in arch.REFERENCE_ADDENDUM_MODULE:
         # transfer-learning model: the reference's build_on_top stacks the addendum networks on a trained base model
         # (MixtureOfExpertsDNNFastXferLearning.py:494-502 does this on a DataParallel(WrapperForDataParallel(moe)))

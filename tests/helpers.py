@@ -22,19 +22,22 @@ def batchnorm_params(case="single_tech_batchnorm"):
     return state, weights.supported_state(state)
 
 
+LEGACY_CASE_CFG = {"legacy_single_tech": "single_tech", "legacy_hybrid_combiners": "hybrid_full"}
+
+
 def legacy_params(case="legacy_hybrid_additive"):
     """(legacy state dict, folded / renamed parameters) of a legacy-wiring golden model: the reference model's state dict is
     re-created from the key / shape list stored in the fixture (weights.init_legacy_state is deterministic) and goes through
     weights.supported_state -- what from_state_dict does with a user's legacy model."""
     g = np.load(os.path.join(GOLDEN, case + ".npz"))
     keys = [(str(k), tuple(int(x) for x in str(s).split(",") if x)) for k, s in zip(g["bn_keys"], g["bn_shapes"])]
-    state = weights.init_legacy_state(keys, arch.CONFIGS[case], seed=13)
+    state = weights.init_legacy_state(keys, arch.CONFIGS[LEGACY_CASE_CFG.get(case, case)], seed=13)
     return state, weights.supported_state(state)
 
 
 def load_golden(case):
     g = dict(np.load(os.path.join(GOLDEN, case + ".npz")))
-    cfg = arch.CONFIGS[{"legacy_single_tech": "single_tech"}.get(case, case).replace("_uniform", "").replace("_batchnorm", "")]
+    cfg = arch.CONFIGS[LEGACY_CASE_CFG.get(case, case).replace("_uniform", "").replace("_batchnorm", "")]
     reads, offs = [], []
     for t in range(len(cfg.read_cin)):
         reads.append(torch.from_numpy(g["reads%d" % t]))

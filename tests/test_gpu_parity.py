@@ -376,16 +376,18 @@ def test_batchnorm_built_model_matches_reference_golden(gpu, precision):
     check_log_probs(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], precision, "batchnorm")
 
 
+@pytest.mark.parametrize("case", ["legacy_hybrid_additive", "legacy_hybrid_combiners"])
 @pytest.mark.parametrize("precision", PRECISIONS)
-def test_legacy_hybrid_wiring_matches_reference_golden(gpu, precision):
+def test_legacy_hybrid_wiring_matches_reference_golden(gpu, precision, case):
     """The legacy MoEMergedAdvanced wiring with two technologies (additive hybrid features, BatchNorm-built meta): the state
     dict of the reference's own model is renamed / folded at load and the CUDA forward (HELLO_COMBINE_SUM) reproduces the
-    reference's logits, meta weights, pair probabilities and calls (tests/golden/legacy_hybrid_additive.npz)."""
+    reference's logits, meta weights, pair probabilities and calls (tests/golden/legacy_hybrid_additive.npz); with both
+    ConvCombiners (BatchNorm-built, folded) it is the three-expert wiring `hybrid_full` (legacy_hybrid_combiners.npz)."""
     from helpers import legacy_params
-    cfg, pl, g = load_golden("legacy_hybrid_additive")
-    state, params = legacy_params()
+    cfg, pl, g = load_golden(case)
+    state, params = legacy_params(case)
     net = gpu.MoEAttentionB200.from_state_dict(state, device=DEV, precision=precision)
-    assert net.cfg.name == "legacy_hybrid_additive"
+    assert net.cfg.name == cfg.name
     res = net.forward(*pl.forward_args())
     logits, meta = flat_result(cfg, res)
     np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=0, atol=TOL_LOGIT[precision])
@@ -393,7 +395,7 @@ def test_legacy_hybrid_wiring_matches_reference_golden(gpu, precision):
     r = net.last_result
     np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], rtol=0, atol=TOL_PROB[precision])
     np.testing.assert_allclose(r.pair_prob[1:].cpu().numpy(), g["pair_experts"], rtol=0, atol=TOL_PROB[precision])
-    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB[precision], "legacy_hybrid_additive/" + precision)
+    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB[precision], case + "/" + precision)
     check_log_probs(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], precision, "legacy hybrid")
     # more sites than the fixture holds, against the oracle
     pl2 = synth.make_pileups(40, coverage=12, channels=cfg.read_cin, seed=99)

@@ -86,18 +86,23 @@ def test_batchnorm_model_is_folded_like_the_reference_evaluates_it():
     np.testing.assert_allclose(np.array(mixed, np.float32), g["pair_mixed"], rtol=0, atol=TOL)
 
 
-def test_legacy_hybrid_wiring_matches_the_reference():
+@pytest.mark.parametrize("case", ["legacy_hybrid_additive", "legacy_hybrid_combiners"])
+def test_legacy_hybrid_wiring_matches_the_reference(case):
     """tests/golden/legacy_hybrid_additive.npz: MoEMergedAdvanced (python/MixtureOfExpertsAdvanced.py:255-484) with two
     technologies built by createMoEFullMergedAdvancedModel (:614-654): three experts on 2a - s, the hybrid allele feature the
     SUM of the two technologies' (:408-412), its site frame the per-site sum of that (:425-436), meta (BatchNorm-built by the
     factory) on it.  The state dict is renamed / folded by weights.supported_state; the oracle reproduces logits, meta weights
-    and the per-site wrapper outputs of the reference."""
+    and the per-site wrapper outputs of the reference.
+    tests/golden/legacy_hybrid_combiners.npz: the same factory with alleleConvCombiner / siteConvCombiner =
+    ConvCombinerResNetDeeper (BatchNorm-built, folded): the hybrid allele feature and site frame come from the combiners
+    (:408-436) -- MoEAttention's three-expert wiring, `hybrid_full`."""
     from helpers import legacy_params
-    cfg, pl, g = load_golden("legacy_hybrid_additive")
-    assert cfg.legacy_sum and cfg.returns_meta
-    state, params = legacy_params()
+    cfg, pl, g = load_golden(case)
+    assert cfg.legacy_sum == (case == "legacy_hybrid_additive") and cfg.combiners != cfg.legacy_sum and cfg.returns_meta
+    state, params = legacy_params(case)
     assert any(k.startswith("readConv1.") for k in state) and weights.is_batchnorm_state(state)
-    assert weights.cfg_from_state_dict(params).name == "legacy_hybrid_additive"
+    assert any(k.startswith("siteConvCombiner.") for k in state) == cfg.combiners
+    assert weights.cfg_from_state_dict(params).name == cfg.name
     assert weights.params_digest(params) == str(g["digest"])
     torch.set_num_threads(1)
     model = O.OracleModel(cfg, params)

@@ -89,7 +89,8 @@ def test_legacy_wiring_state_dict_maps_onto_single_tech():
     """MoEMergedAdvanced (legacy wiring, python/MixtureOfExpertsAdvanced.py:255-484) in its single-technology form has the
     parameters of MoEAttention in the same order under other names; tests/golden/legacy_single_tech.npz was produced by the
     reference's createMoEFullMergedAdvancedModel with these very parameters, and the oracle / CUDA forward of `single_tech`
-    reproduce it (test_oracle_golden, test_forward_matches_reference_golden).  The hybrid legacy wiring is refused."""
+    reproduce it (test_oracle_golden, test_forward_matches_reference_golden).  (The hybrid legacy wirings have reference-made
+    golden files of their own: legacy_hybrid_additive, legacy_hybrid_combiners.)"""
     cfg = arch.CONFIGS["single_tech"]
     params = params_for(cfg)
     legacy = {}
@@ -106,7 +107,7 @@ def test_legacy_wiring_state_dict_maps_onto_single_tech():
     assert weights.cfg_from_state_dict(back).name == "single_tech"
     assert weights.legacy_state_to_attention(params) == dict(params)               # non-legacy dicts pass through
     combined = dict(legacy)
-    combined["alleleConvCombiner.network.0.conv1d.bias"] = torch.zeros(16)      # ConvCombiner'ed legacy hybrids are refused
+    combined["alleleConvCombiner.network.0.conv1d.bias"] = torch.zeros(16)      # one ConvCombiner without the other is refused
     with pytest.raises(ValueError, match="ConvCombiner"):
         weights.legacy_state_to_attention(combined)
     broken = dict(legacy)
