@@ -947,7 +947,8 @@ int hello_encode_reads(const hello_encode_batch* b, uint8_t* d_out, void* stream
         g_encode_error = "missing buffer"; return HELLO_ERR_ARG;
     }
     static const enc::Luts luts = enc::make_luts();
-    const long long blocks = (b->n_rows + enc::WARPS - 1) / enc::WARPS;
+    const long long rows_per_block = (long long)enc::WARPS * enc::ROWS_PER_WARP;
+    const long long blocks = (b->n_rows + rows_per_block - 1) / rows_per_block;
     if (blocks > 0x7fffffffLL) { g_encode_error = "too many rows for one launch"; return HELLO_ERR_ARG; }
     enc::encode_reads_kernel<<<(unsigned)blocks, enc::WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(*b, luts, d_out);
     cudaError_t e = cudaGetLastError();

@@ -246,8 +246,9 @@ def tile_packed_reads(packed, row_read, row_site, times: int):
 
 def make_packed_reads(n_sites: int, coverage: int = 30, read_len: int = 150, seed: int = 13, hp: bool = False):
     """Aligned reads for the GPU feature encoder, generated vectorised (numpy) straight in the packed layout of
-    include/hello_encode.h: every read is `M a, I b, M c, D d, M e` (b or d may be 0 -> the operation is dropped to a
-    0-length one, which the CIGAR walk skips) starting 0..119 bases before the 150-wide window centre.
+    include/hello_encode.h: every read is `M a, I b, M c, D d, M e` with an insertion and / or a deletion in 15 % of the reads
+    each; an absent operation is left out and the matches around it are merged, as in a BAM record (72 % of the reads are
+    one match, 26 % have three operations, 2 % five), starting 0..119 bases before the 150-wide window centre.
     Returns (hello_b200.encoder.PackedReads, row_read int32, row_site int32) with one row per read in site order."""
     import numpy as np
     from .encoder import PackedReads
@@ -273,8 +274,16 @@ def make_packed_reads(n_sites: int, coverage: int = 30, read_len: int = 150, see
     total = int(read_off[-1])
     bases = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, total)]
     quals = rng.integers(2, 42, total).astype(np.uint8)
-    cig = np.stack([m1 << 4, ins << 4 | 1, m2 << 4, dele << 4 | 2, m3 << 4], axis=1).astype(np.uint32).reshape(-1)
-    cigar_off = np.arange(R + 1, dtype=np.int64) * 5
+    has_i, has_d = ins > 0, dele > 0
+    # operation slots of a read, in order; a slot is kept when its operation exists (matches merged into the slot after a gap)
+    ma = np.where(has_i, m1, 0)                                   # M before the insertion
+    mc = np.where(has_d, np.where(has_i, m2, m1 + m2), 0)         # M between insertion and deletion
+    me = np.where(has_d, m3, np.where(has_i, m2 + m3, m1 + m2 + m3))
+    slots = np.stack([ma << 4, ins << 4 | 1, mc << 4, dele << 4 | 2, me << 4], axis=1).astype(np.uint32)
+    keep = np.stack([has_i, has_i, has_d, has_d, np.ones(R, bool)], axis=1)
+    cig = slots[keep]
+    cigar_off = np.zeros(R + 1, np.int64)
+    np.cumsum(keep.sum(axis=1), out=cigar_off[1:])
     read_base = np.zeros(n_sites + 1, np.int64)
     np.cumsum(per_site, out=read_base[1:])
     packed = PackedReads(read_off, bases, quals, cigar_off, cig, ref_start.astype(np.int64),
