@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t base_color(uint8_t b) {            // :971-9
 // All window arithmetic is 32-bit and relative to the window start.  A warp encodes ROWS_PER_WARP consecutive rows: rows
 // come in site order, so the per-site part (three 64-bit records, the clamps, five reference bases) is paid once per
 // site and warp instead of once per row.
-constexpr int ROWS_PER_WARP = 4;
+constexpr int ROWS_PER_WARP = 16;
 
 __global__ void __launch_bounds__(WARPS * 32, 8) encode_reads_kernel(const hello_encode_batch b, const Luts lut,
                                                                    uint8_t* __restrict__ out) {
