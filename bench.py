@@ -578,8 +578,9 @@ def run_ours(args):
             S_e_all = int(t.item())
         e2e = {"value": (S_e_all if args.partition == "balanced" else world * S_e) * args.steps / dt, "unit": "sites/s", "h2d_bytes_per_step": hb.input_nbytes(),
                "d2h_bytes_per_step": out.nbytes(), "sites_per_gpu": S_e,
-               "api": "MoEEngine.forward_host (pinned host buffers, read rows streamed in %d-site ranges on a copy "
-                      "stream while the previous range computes)" % args.e2e_chunk_sites}
+               "api": "MoEEngine.forward_host (pinned host buffers, read rows streamed in ranges of up to %d sites -- the "
+                      "first ones an eighth, a quarter, half of that -- on a copy stream while the previous range "
+                      "computes)" % args.e2e_chunk_sites}
         if numa_cpus is not None:
             e2e["host_binding"] = "rank 0 runs on %d cores local to its GPU (pinned buffers first-touched there)" % len(numa_cpus)
 
@@ -627,7 +628,7 @@ def run_ours(args):
                           "d2h_bytes_per_step": out_p.nbytes(), "sites_per_gpu": S_p, "rows_per_gpu": int(rr.size),
                           "h2d_bytes_per_row": hpb.input_nbytes() / max(int(rr.size), 1),
                           "api": "MoEEngine.forward_host_packed (pinned host buffers of aligned reads -- bases, qualities, CIGARs, "
-                                 "reference windows -- streamed in %d-site ranges; hello_encode_reads builds the [R,150,C] rows "
+                                 "reference windows -- streamed in ranges of up to %d sites; hello_encode_reads builds the [R,150,C] rows "
                                  "on the GPU; then hello_moe_forward_range)" % chunk_p,
                           "data": "%d generated sites (synth.make_packed_reads) tiled %d times" % (gen_sites, times)}
         hpb = out_p = None

@@ -283,6 +283,16 @@ class MoEEngine:
                                                   workspace.data_ptr(), workspace.numel(), C.c_void_p(stream))
         self._check(rc, "hello_moe_forward_range")
 
+    @staticmethod
+    def _ranges(n_sites: int, chunk_sites: int):
+        """Site ranges of a streamed call: the first ones are short (chunk/8, chunk/4, chunk/2, ...) because the first
+        range's host -> device copy is the one transfer no computation hides."""
+        size, s0 = max(1024, chunk_sites // 8), 0
+        while s0 < n_sites:
+            s1 = min(n_sites, s0 + min(size, chunk_sites))
+            yield s0, s1
+            s0, size = s1, size * 2
+
     def forward_host(self, hb: "HostBatch", chunk_sites: int = 65536, sync: bool = True,
                      fresh_result: bool = False) -> "HostResult":
         """End-to-end call on HOST buffers.  The device-side batch (read rows, CSR, results) is allocated once per
@@ -308,8 +318,7 @@ class MoEEngine:
             small_done.record(copy_s)
         comp_s.wait_event(small_done)
         sao = hb.site_allele_off
-        for s0 in range(0, S, chunk_sites):
-            s1 = min(S, s0 + chunk_sites)
+        for s0, s1 in self._ranges(S, chunk_sites):
             a0, a1 = int(sao[s0]), int(sao[s1])
             ev = torch.cuda.Event()
             with torch.cuda.stream(copy_s):
@@ -362,8 +371,7 @@ class MoEEngine:
         sao = hp.site_allele_off
         lib = E._load()
         L = arch.FEATURE_LENGTH
-        for s0 in range(0, S, chunk_sites):
-            s1 = min(S, s0 + chunk_sites)
+        for s0, s1 in self._ranges(S, chunk_sites):
             a0, a1 = int(sao[s0]), int(sao[s1])
             rb0, rb1 = int(hp.read_base[s0]), int(hp.read_base[s1])
             spans = {"bases": (int(hp.read_off[rb0]), int(hp.read_off[rb1])), "quals": (int(hp.read_off[rb0]), int(hp.read_off[rb1])),
