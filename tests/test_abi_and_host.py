@@ -241,3 +241,16 @@ def test_bench_reference_arm_prints_one_json_line():
     port = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
                            "--cpu-sites", "32", "--cpu-workers", "2", "--cpu-port"], capture_output=True, text=True, timeout=300)
     assert port.returncode == 0 and json.loads(port.stdout.splitlines()[-1])["cpu_baseline"]["kind"] == "port"
+
+
+def test_streamed_ranges_cover_the_batch_and_start_small():
+    """forward_host / forward_host_packed stream the batch in site ranges: contiguous, complete, never larger than the
+    requested size, and the first one an eighth of it (its copy is the one transfer no computation hides)."""
+    from hello_b200.model import MoEEngine
+    for n_sites, chunk in ((1_000_000, 65536), (5000, 65536), (70_000, 8192), (1, 64), (8192, 8192)):
+        r = list(MoEEngine._ranges(n_sites, chunk))
+        assert r[0][0] == 0 and r[-1][1] == n_sites
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(0 < s1 - s0 <= max(chunk, 1024) for s0, s1 in r)
+        assert r[0][1] - r[0][0] == min(n_sites, max(1024, chunk // 8))
+    assert list(MoEEngine._ranges(0, 4096)) == []
