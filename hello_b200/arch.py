@@ -186,6 +186,15 @@ class ModelConfig:
     addendum_blocks: int = 2             # the shipped addenda have two; other depths run too (fused kernels cover <= 2)
     legacy_sum: bool = False             # legacy MoEMergedAdvanced hybrid wiring (useAdditive, no ConvCombiners): the hybrid
                                          # allele feature is compressor0 + compressor1, the hybrid site frame its per-site sum
+    softplus_nets: Tuple[str, ...] = ()  # kinds of sub-network ("read_convolver", "compressor", "xattn", ...) whose
+                                         # convolutions are followed by torch.nn.Softplus() instead of ReLU: the architecture
+                                         # modules' `activation` switch (NNTools.py:72-115) as set by
+                                         # moe_attention_config_single_tech_old_equivalent_layer_norm.py -- read convolver and
+                                         # expert head honour it, the compressor's generator does not
+
+    def activation(self, net: str) -> str:
+        """"relu" or "softplus" for sub-network `net` ("read_convolver0", "xattn2", ...)."""
+        return "softplus" if net.rstrip("0123456789") in self.softplus_nets else "relu"
 
     @property
     def hybrid(self) -> bool:
@@ -258,7 +267,14 @@ CONFIGS = {
     # ..._full_hybrid_old_equivalent_weight_norm_no_ensemble_addendum.py stacked on the shipped hybrid model
     "hybrid_no_ensemble_addendum": ModelConfig("hybrid_no_ensemble_addendum", (6, 6), (False, False, True), True, None, 1,
                                                True),
+    # moe_attention_config_single_tech_old_equivalent_layer_norm.py: the single-technology networks built with
+    # `norm_type = "Noop"` and `activation = "Softplus"`: plain Conv1d / Linear without normalisation layers (one
+    # BatchNorm1d survives in the expert's pooled head and is folded), Softplus in the read convolver and the expert head
+    "single_tech_softplus": ModelConfig("single_tech_softplus", (6,), (True, False, False), False, None,
+                                        softplus_nets=("read_convolver", "xattn")),
 }
+
+ACTIVATION_CODES = {"relu": 1, "softplus": 2}      # the `relu` field of a convolution record in the weight blob (0 = none)
 
 # configs whose model is <base model> + build_on_top(<addendum config module>)
 REFERENCE_ADDENDUM_MODULE = {
@@ -274,6 +290,7 @@ REFERENCE_CONFIG_MODULE = {
     "hybrid_ensemble2": "moe_attention_config_full_hybrid_old_equivalent_weight_norm_ensemble2",
     "hybrid_full": "moe_attention_config_full_hybrid_old_equivalent_weight_norm",
     "hybrid_no_ensemble_wide": "moe_attention_config_full_hybrid_old_equivalent_weight_norm_no_ensemble_wide",
+    "single_tech_softplus": "moe_attention_config_single_tech_old_equivalent_layer_norm",
 }
 
 

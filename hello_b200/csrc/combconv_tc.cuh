@@ -311,7 +311,7 @@ static CombConvTC* combconv_tc_create(const std::vector<LayerDesc>& net, const f
     using namespace cc;
     if (precision != HELLO_PREC_BF16X3 && precision != HELLO_PREC_BF16) { err = "unknown tensor-core precision"; return nullptr; }
     auto is_conv = [&](const LayerDesc& Ld, int cin, int cout, int k, int pad) {
-        return Ld.kind == KIND_CONV && Ld.a.cin == cin && Ld.a.cout == cout && Ld.a.k == k && Ld.a.stride == 1 && Ld.a.pad == pad && Ld.a.relu;
+        return Ld.kind == KIND_CONV && Ld.a.cin == cin && Ld.a.cout == cout && Ld.a.k == k && Ld.a.stride == 1 && Ld.a.pad == pad && Ld.a.relu == ACT_RELU;
     };
     if (net.size() != 2 || !is_conv(net[0], 2 * C_HALF, C_MID, 3, 1) || !is_conv(net[1], C_MID, C_OUT, 1, 0)) {
         err = "layer table is not the 256 -> 512 (k3) -> 128 (k1) combiner"; return nullptr;

@@ -9,9 +9,21 @@
 
 namespace hello {
 
+// Activation after a convolution: the `relu` field of a layer record (the architecture modules' `activation` switch,
+// python/NNTools.py:72-115).  Softplus = torch.nn.Softplus() with its defaults (beta 1, threshold 20).
+enum Activation { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS = 2 };
+
+__host__ __device__ __forceinline__ float apply_activation(float v, int act) {
+#ifdef __CUDA_ARCH__
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_SOFTPLUS) return v > 20.f ? v : log1pf(expf(v));
+#endif
+    return v;
+}
+
 // One convolution (or linear) layer, weights already weight-norm folded.
 struct ConvDesc {
-    int cin, cout, k, stride, pad, relu;
+    int cin, cout, k, stride, pad, relu;   // relu: an Activation code
     const float* w;     // device: conv [k*cin][cout] (row = tap*cin + ci); linear [cout][cin]
     const float* b;     // device: [cout]
     int out_len(int lin) const { return (lin + 2 * pad - k) / stride + 1; }

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256) conv1d_fp32_kernel(const ConvArgs a) {
         for (int j = 0; j < TN; ++j) {
             const int c = col_of(j);
             float v = acc[i][j] + __ldg(a.bias + n0 + c);
-            if (a.relu) v = fmaxf(v, 0.f);
+            v = apply_activation(v, a.relu);
             if (rrow) v += __ldg(rrow + c);
             acc[i][j] = v;
         }

@@ -178,7 +178,9 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
                         for (int q = 0; q < 4; ++q) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c0) + q);
                             float4 o = make_float4(acc[4 * q] + b.x, acc[4 * q + 1] + b.y, acc[4 * q + 2] + b.z, acc[4 * q + 3] + b.w);
-                            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            if (a.relu == ACT_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                            else if (a.relu) { o.x = apply_activation(o.x, a.relu); o.y = apply_activation(o.y, a.relu);
+                                               o.z = apply_activation(o.z, a.relu); o.w = apply_activation(o.w, a.relu); }
                             if (a.resid) {
                                 const float4 t = *reinterpret_cast<const float4*>(my_res + (cc + 4 * q) * 4);
                                 o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;

@@ -521,10 +521,10 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_
     }
     auto is_res = [&](const LayerDesc& L, int cin, int cout, int s, bool sc) {
         return L.kind == KIND_RES && L.a.cin == cin && L.a.cout == cout && L.a.k == 3 && L.a.stride == s && L.a.pad == 1 &&
-               L.a.relu && L.b.relu && L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&
+               L.a.relu == ACT_RELU && L.b.relu == ACT_RELU && L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&
                (L.has_shortcut != 0) == sc && (!sc || (L.s.cin == cin && L.s.cout == cout && L.s.k == 1 && L.s.stride == s && L.s.pad == 0));
     };
-    bool ok = net[0].a.cout == C && net[0].a.k == 1 && net[0].a.stride == 1 && net[0].a.pad == 0 && net[0].a.relu &&
+    bool ok = net[0].a.cout == C && net[0].a.k == 1 && net[0].a.stride == 1 && net[0].a.pad == 0 && net[0].a.relu == ACT_RELU &&
               is_res(net[1], C, 2 * C, 2, true) && is_res(net[2], 2 * C, 2 * C, 1, false) && is_res(net[3], 2 * C, 2 * C, 1, false);
     int extra = 0;
     while (ok && extra < MAX_EXTRA_BLOCKS && (size_t)(4 + extra) < net.size() && is_res(net[4 + extra], 2 * C, 2 * C, 1, false)) ++extra;

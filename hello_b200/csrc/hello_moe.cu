@@ -519,7 +519,7 @@ bool parse_blob(hello_moe* h, const void* blob, size_t nbytes, std::string& err)
         c->cin = r[0]; c->cout = r[1]; c->k = r[2]; c->stride = r[3]; c->pad = r[4]; c->relu = r[5];
         if (r[6] < 0 || r[7] < 0 || (uint64_t)r[6] > n_floats || (uint64_t)r[7] > n_floats) return false;
         if (used) {
-            if (r[0] <= 0 || r[1] <= 0 || r[2] <= 0 || r[3] <= 0 || r[4] < 0) return false;
+            if (r[0] <= 0 || r[1] <= 0 || r[2] <= 0 || r[3] <= 0 || r[4] < 0 || r[5] < ACT_NONE || r[5] > ACT_SOFTPLUS) return false;
             const uint64_t wn = (uint64_t)r[2] * (uint64_t)r[0] * (uint64_t)r[1];
             if ((uint64_t)r[6] + wn > n_floats || (uint64_t)r[7] + (uint64_t)r[1] > n_floats) return false;
         }
@@ -540,7 +540,7 @@ bool parse_blob(hello_moe* h, const void* blob, size_t nbytes, std::string& err)
             }
             if (!conv_from(r + 2, &L.a, L.kind != KIND_MAXPOOL) || !conv_from(r + 10, &L.b, res) ||
                 !conv_from(r + 18, &L.s, res && L.has_shortcut != 0)) {
-                err = "layer record out of range (cin / cout / k / stride must be positive, pad non-negative, weights and "
+                err = "layer record out of range (cin / cout / k / stride must be positive, pad non-negative, activation 0..2, weights and "
                       "bias inside the data section)";
                 return false;
             }

@@ -955,10 +955,11 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     if (precision != HELLO_PREC_BF16X3 && precision != HELLO_PREC_BF16) { err = "unknown tensor-core precision"; return nullptr; }
     if (feature_length != LIN || channels < 1 || channels > 8) { err = "tensor-core read convolver needs L=150, C<=8"; return nullptr; }
     auto is_conv = [&](const LayerDesc& L, int cin, int cout, int k, int s, int p) {
-        return L.kind == KIND_CONV && L.a.cin == cin && L.a.cout == cout && L.a.k == k && L.a.stride == s && L.a.pad == p && L.a.relu;
+        return L.kind == KIND_CONV && L.a.cin == cin && L.a.cout == cout && L.a.k == k && L.a.stride == s && L.a.pad == p && L.a.relu == ACT_RELU;
     };
     auto is_res = [&](const LayerDesc& L, int cin, int cout, int s, bool sc) {
-        return L.kind == KIND_RES && L.a.cin == cin && L.a.cout == cout && L.a.k == 3 && L.a.stride == s && L.a.pad == 1 &&
+        return L.kind == KIND_RES && L.a.relu == ACT_RELU && L.b.relu == ACT_RELU &&
+               L.a.cin == cin && L.a.cout == cout && L.a.k == 3 && L.a.stride == s && L.a.pad == 1 &&
                L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&
                (L.has_shortcut != 0) == sc && (!sc || (L.s.cin == cin && L.s.cout == cout && L.s.k == 1 && L.s.stride == s && L.s.pad == 0));
     };

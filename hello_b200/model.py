@@ -688,9 +688,11 @@ class MoEAttentionB200:
         self.last_result: Optional[BatchResult] = None
 
     @classmethod
-    def from_state_dict(cls, state_dict, **kw) -> "MoEAttentionB200":
-        sd = weights.supported_state(state_dict)
-        return cls(weights.cfg_from_state_dict(sd), sd, **kw)
+    def from_state_dict(cls, state_dict, softplus_nets=(), **kw) -> "MoEAttentionB200":
+        """``softplus_nets``: the kinds of sub-network built with Softplus instead of ReLU, e.g. ("read_convolver", "xattn")
+        -- a state dict does not say; ``load_wrapper`` reads it off the pickled modules.  Empty for every shipped model."""
+        sd = weights.supported_state(state_dict, softplus_nets=softplus_nets)
+        return cls(weights.cfg_from_state_dict(sd, softplus_nets=softplus_nets), sd, **kw)
 
     @classmethod
     def from_reference_module(cls, moe_attention, **kw) -> "MoEAttentionB200":
@@ -823,13 +825,25 @@ def read_wrapper(path: str, reference_python: Optional[str] = None):
     if not hasattr(moe, "state_dict"):
         raise _lib.HelloMoEError("load_wrapper: %s does not hold a torch module" % path)
     # the activation and the kind of normalisation are not in a state dict: look at the modules
-    odd = sorted({type(m).__name__ for m in moe.modules()} & {"Softplus", "LayerNorm", "LayerNormModule", "GroupNorm", "ELU",
-                                                               "LeakyReLU", "Tanh", "Sigmoid", "Dropout"})
+    kinds = {type(m).__name__ for m in moe.modules()}
+    odd = sorted(kinds & {"LayerNorm", "LayerNormModule", "GroupNorm", "ELU", "LeakyReLU", "Tanh", "Sigmoid", "Dropout"})
+    softplus_nets = set()
+    for name, sub in moe.named_children():                   # the activation is chosen per sub-network (architecture module)
+        acts = {type(m).__name__ for m in sub.modules()} & {"ReLU", "Softplus"}
+        if acts == {"Softplus"}:
+            if any(getattr(m, "beta", 1) != 1 or getattr(m, "threshold", 20) != 20 for m in sub.modules()
+                   if type(m).__name__ == "Softplus"):
+                odd.append("Softplus with non-default beta / threshold")
+            softplus_nets.add(name.rstrip("0123456789"))
+        elif len(acts) > 1:
+            odd.append("ReLU and Softplus mixed inside " + name)
     if odd:
-        raise _lib.HelloMoEError("load_wrapper: the model uses %s; this build covers the ReLU networks with weight-norm or "
-                                 "BatchNorm1d that the reference's shipped configurations use" % ", ".join(odd))
-    sd = weights.supported_state(moe.state_dict())
-    return weights.cfg_from_state_dict(sd), sd, bool(getattr(net, "providePredictions", False))
+        raise _lib.HelloMoEError("load_wrapper: the model uses %s; this build covers the ReLU networks (weight-norm or "
+                                 "BatchNorm1d) and the Softplus networks without normalisation layers that the reference's "
+                                 "configurations build" % ", ".join(odd))
+    sd = weights.supported_state(moe.state_dict(), softplus_nets=tuple(sorted(softplus_nets)))
+    cfg = weights.cfg_from_state_dict(sd, softplus_nets=tuple(sorted(softplus_nets)))
+    return cfg, sd, bool(getattr(net, "providePredictions", False))
 
 
 def load_wrapper(path: str, device="cuda:0", precision: str = "bf16x3", reference_python: Optional[str] = None,

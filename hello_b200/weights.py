@@ -180,7 +180,8 @@ def legacy_state_to_attention(state_dict) -> Dict[str, torch.Tensor]:
     want = {rename[g] for g in groups}
     for cfg in arch.CONFIGS.values():
         # two technologies: summed hybrid features (legacy_sum) without combiners, MoEAttention's own wiring with them
-        if set(cfg.networks()) != want or cfg.addendum or cfg.width != 1 or (cfg.hybrid and cfg.legacy_sum != (n_comb == 0)):
+        if set(cfg.networks()) != want or cfg.addendum or cfg.width != 1 or cfg.softplus_nets or \
+                (cfg.hybrid and cfg.legacy_sum != (n_comb == 0)):
             continue
         out, ok = {}, True
         shapes = param_shapes(cfg)
@@ -272,7 +273,13 @@ def _emit_folded(out, layers, ours) -> bool:
     return True
 
 
-def batchnorm_state_to_weight_norm(state_dict, eps: float = BN_EPS) -> Dict[str, torch.Tensor]:
+def is_plain_state(state_dict) -> bool:
+    """True when some layer holds a plain ``weight`` (no ``weight_g`` / ``weight_v``): a model built without weight-norm."""
+    return any(k.endswith(".weight") and state_dict[k].dim() >= 2 and k[:-len(".weight")] + ".weight_v" not in state_dict
+               for k in state_dict)
+
+
+def batchnorm_state_to_weight_norm(state_dict, eps: float = BN_EPS, softplus_nets=()) -> Dict[str, torch.Tensor]:
     """State dict of a model built WITHOUT weight-norm -- plain Conv1d / Linear followed (or, in the pooled head, preceded)
     by ``BatchNorm1d`` (``norm_type="BatchNorm1d"``, the default of python/NNTools.py:27-45,72-115,118-294,517-566 when an
     architecture module has ``weight_norm = False``) -- folded for inference (``_fold_batchnorm_net``) and renamed to this
@@ -286,12 +293,13 @@ def batchnorm_state_to_weight_norm(state_dict, eps: float = BN_EPS) -> Dict[str,
         nets.setdefault(k.split(".", 1)[0], []).append(k)
     folded_nets = {net: _fold_batchnorm_net(keys, state_dict, eps) for net, keys in nets.items()}
     for cfg in arch.CONFIGS.values():
-        if set(cfg.networks()) != set(folded_nets):
+        if set(cfg.networks()) != set(folded_nets) or set(cfg.softplus_nets) != set(softplus_nets):
             continue
         out = {}
         if all(_emit_folded(out, folded_nets[net], conv_keys(cfg, net)) for net in cfg.networks()):
             return out
-    raise ValueError("BatchNorm state dict does not match any supported HELLO MoE configuration")
+    raise ValueError("state dict of a model built without weight-norm does not match any supported HELLO MoE configuration "
+                     "(sub-networks with Softplus: %s)" % (sorted(softplus_nets) or "none"))
 
 
 def init_batchnorm_state(keys_and_shapes, seed: int = 13) -> Dict[str, torch.Tensor]:
@@ -322,12 +330,17 @@ def init_batchnorm_state(keys_and_shapes, seed: int = 13) -> Dict[str, torch.Ten
     return out
 
 
-def supported_state(state_dict) -> Dict[str, torch.Tensor]:
+def supported_state(state_dict, softplus_nets=()) -> Dict[str, torch.Tensor]:
     """Any state dict this package can run -> its weight-norm form under MoEAttention names: the live wiring with weight-norm
-    (as it is), the legacy single-technology wiring (renamed), a BatchNorm1d-built model (folded).  Anything else raises."""
+    (as it is), the legacy wirings (renamed), a model built without weight-norm -- BatchNorm1d layers folded, or no
+    normalisation layer at all (``norm_type = "Noop"``, the Softplus configuration).  Anything else raises.  The activation
+    is not part of a state dict: the caller names the kinds of sub-network that use Softplus (load_wrapper reads them off
+    the modules)."""
     sd = legacy_state_to_attention(state_dict)
-    if is_batchnorm_state(sd):
-        return batchnorm_state_to_weight_norm(sd)
+    if is_batchnorm_state(sd) or is_plain_state(sd):
+        return batchnorm_state_to_weight_norm(sd, softplus_nets=softplus_nets)
+    if softplus_nets:
+        raise ValueError("no weight-norm configuration with Softplus sub-networks")
     return weight_norm_state(sd)
 
 
@@ -354,9 +367,11 @@ def init_legacy_state(keys_and_shapes, cfg: arch.ModelConfig, seed: int = 13) ->
     return {k: out[k] for k, _ in keys_and_shapes}
 
 
-def cfg_from_state_dict(params: Dict[str, torch.Tensor]) -> arch.ModelConfig:
-    """Recognise which reference config a MoEAttention state dict belongs to."""
+def cfg_from_state_dict(params: Dict[str, torch.Tensor], softplus_nets=()) -> arch.ModelConfig:
+    """Recognise which reference config a MoEAttention state dict belongs to (the activations are the caller's knowledge)."""
     for cfg in arch.CONFIGS.values():
+        if set(cfg.softplus_nets) != set(softplus_nets):
+            continue
         shapes = param_shapes(cfg)
         if set(shapes) == {k for k in params if not k.endswith(".weight")} or set(shapes) == set(params):
             if all(tuple(params[k].shape) == s for k, s in shapes.items()):
@@ -380,10 +395,10 @@ class _BlobWriter:
         return off
 
 
-def _conv_rec(conv: arch.Conv, params, prefix, bw: _BlobWriter) -> List[int]:
+def _conv_rec(conv: arch.Conv, params, prefix, bw: _BlobWriter, act: int = 1) -> List[int]:
     w, b = folded(params, prefix)                      # [cout, cin, k]
     wt = w.permute(2, 1, 0).reshape(conv.k * conv.cin, conv.cout)   # row kk = tap*cin + ci, cout contiguous
-    return [conv.cin, conv.cout, conv.k, conv.stride, conv.pad, int(conv.relu), bw.add(wt), bw.add(b)]
+    return [conv.cin, conv.cout, conv.k, conv.stride, conv.pad, act if conv.relu else 0, bw.add(wt), bw.add(b)]
 
 
 def pack_blob(cfg: arch.ModelConfig, params: Dict[str, torch.Tensor]) -> bytes:
@@ -405,18 +420,19 @@ def pack_blob(cfg: arch.ModelConfig, params: Dict[str, torch.Tensor]) -> bytes:
     zero8 = [0] * 8
     for net in cfg.networks():
         nid = NET_IDS[net]
+        act = arch.ACTIVATION_CODES[cfg.activation(net)]
         first[nid] = len(recs)
         for base, layer in cfg.keyed(net):
             if isinstance(layer, arch.Front):
                 continue
             if isinstance(layer, arch.Conv):
-                recs.append([KIND_CONV, 0] + _conv_rec(layer, params, base + ".conv1d", bw) + zero8 + zero8)
+                recs.append([KIND_CONV, 0] + _conv_rec(layer, params, base + ".conv1d", bw, act) + zero8 + zero8)
             elif isinstance(layer, arch.MaxPool):
                 recs.append([KIND_MAXPOOL, 0] + [0, 0, layer.k, layer.stride, 0, 0, 0, 0] + zero8 + zero8)
             elif isinstance(layer, arch.Res):
-                a = _conv_rec(layer.conv_a, params, base + ".ffNetwork.network.0.conv1d", bw)
-                b = _conv_rec(layer.conv_b, params, base + ".ffNetwork.network.3.conv1d", bw)
-                s = _conv_rec(layer.conv_s, params, base + ".shNetwork.network.0.conv1d", bw) \
+                a = _conv_rec(layer.conv_a, params, base + ".ffNetwork.network.0.conv1d", bw, act)
+                b = _conv_rec(layer.conv_b, params, base + ".ffNetwork.network.3.conv1d", bw, act)
+                s = _conv_rec(layer.conv_s, params, base + ".shNetwork.network.0.conv1d", bw, act) \
                     if layer.conv_shortcut else zero8
                 recs.append([KIND_RES, int(layer.conv_shortcut)] + a + b + s)
             elif isinstance(layer, arch.GapLinear):

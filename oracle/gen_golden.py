@@ -50,6 +50,9 @@ CASES = {
     # built WITHOUT weight-norm: plain Conv1d / Linear + BatchNorm1d (the architecture modules' default, weight_norm = False),
     # eval mode, deterministic non-trivial running statistics; hello_b200 folds the batch-norms at load
     "single_tech_batchnorm": (6, 9, 111, False),
+    # moe_attention_config_single_tech_old_equivalent_layer_norm.py as shipped: norm_type = "Noop", activation = "Softplus"
+    # (plain Conv1d / Linear, no normalisation layer, torch.nn.Softplus() after every convolution)
+    "single_tech_softplus": (6, 9, 114, False),
 }
 LEGACY_CONFIG = {"readConvNGS": "MoEReadConvolverDeeper", "alleleConvSingleNGS": "ExpertAlleleConvolverDeeper",
                  "graphConvSingleNGS": "ExpertGraphConvolverDeeper", "weight_norm": True, "kwargs": {"useAdditive": True}}
@@ -79,7 +82,13 @@ def run_case(case: str) -> None:
     batchnorm = case.endswith("_batchnorm")
     name = name.replace("_batchnorm", "")
     cfg = arch.CONFIGS[name]
-    if batchnorm:
+    plain = bool(cfg.softplus_nets)                       # built without weight-norm and without normalisation layers
+    if plain:
+        moe = M.create_moe_attention_model(importlib.import_module(arch.REFERENCE_CONFIG_MODULE[name]).configDict).eval()
+        for sub_name, sub in moe.named_children():        # arch.py names the sub-networks that got Softplus
+            acts = {type(m).__name__ for m in sub.modules()} & {"ReLU", "Softplus"}
+            assert acts == ({"Softplus"} if cfg.activation(sub_name) == "softplus" else {"ReLU"}), (sub_name, acts)
+    elif batchnorm:
         import architectures.read_convolver as rc_, architectures.compressor_conv_small as cc_, architectures.xattn_subtract as xa_
         for m in (rc_, cc_, xa_):
             m.weight_norm = False
@@ -105,13 +114,14 @@ def run_case(case: str) -> None:
     sd = moe.state_dict()
     params = weights.init_params(cfg, seed=13)
     bn_keys = None
-    if batchnorm:
+    if batchnorm or plain:
         bn_keys = [(k, tuple(v.shape)) for k, v in sd.items()]
         bn_state = weights.init_batchnorm_state(bn_keys, seed=13)
         moe.load_state_dict(bn_state)
         moe = moe.eval()                                  # running statistics, not batch statistics
-        params = weights.batchnorm_state_to_weight_norm(moe.state_dict())
+        params = weights.supported_state(moe.state_dict(), softplus_nets=cfg.softplus_nets)
         assert list(params.keys()) == list(shapes.keys())
+        assert weights.cfg_from_state_dict(params, softplus_nets=cfg.softplus_nets).name == cfg.name
     elif legacy:
         # the parameters of the live sub-networks in the same registration order under the legacy names (a BatchNorm-built
         # `meta` gets deterministic batch-norm state): hello_b200's mapping must invert this

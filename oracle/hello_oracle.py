@@ -52,6 +52,9 @@ class FoldedNet:
 
     def __init__(self, cfg: arch.ModelConfig, net: str, params):
         self.layers = []
+        # the architecture modules' `activation` switch (NNTools.SingleConvLayer, python/NNTools.py:72-115): ReLU, or
+        # torch.nn.Softplus() with its defaults for moe_attention_config_single_tech_old_equivalent_layer_norm.py
+        self.act = {"relu": F.relu, "softplus": F.softplus}[cfg.activation(net)]
         for base, layer in cfg.keyed(net):          # addendum layers (XferLearning.py:131-160) simply follow
             if isinstance(layer, arch.Conv):
                 self.layers.append(("conv", layer, folded(params, base + ".conv1d")))
@@ -65,10 +68,9 @@ class FoldedNet:
             elif isinstance(layer, arch.GapLinear):
                 self.layers.append(("gap", layer, folded(params, arch.linear_key(base))))
 
-    @staticmethod
-    def _conv(x, c: arch.Conv, wb):
+    def _conv(self, x, c: arch.Conv, wb):
         y = F.conv1d(x, wb[0], wb[1], stride=c.stride, padding=c.pad)
-        return F.relu(y) if c.relu else y
+        return self.act(y) if c.relu else y
 
     def __call__(self, x: torch.Tensor, trace: Optional[list] = None) -> torch.Tensor:
         """x: [n, C, L] fp32 (channel-major, as in the reference)."""

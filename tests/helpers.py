@@ -19,7 +19,8 @@ def batchnorm_params(case="single_tech_batchnorm"):
     g = np.load(os.path.join(GOLDEN, case + ".npz"))
     keys = [(str(k), tuple(int(x) for x in str(s).split(",") if x)) for k, s in zip(g["bn_keys"], g["bn_shapes"])]
     state = weights.init_batchnorm_state(keys, seed=13)
-    return state, weights.supported_state(state)
+    cfg = arch.CONFIGS.get(case)                       # the Softplus configuration names its Softplus sub-networks
+    return state, weights.supported_state(state, softplus_nets=cfg.softplus_nets if cfg else ())
 
 
 LEGACY_CASE_CFG = {"legacy_single_tech": "single_tech", "legacy_hybrid_combiners": "hybrid_full"}

@@ -120,7 +120,7 @@ def test_blob_roundtrip(name):
 
 def test_cfg_from_state_dict_recognises_every_wiring():
     for name, cfg in arch.CONFIGS.items():
-        assert weights.cfg_from_state_dict(params_for(cfg)).name == name
+        assert weights.cfg_from_state_dict(params_for(cfg), softplus_nets=cfg.softplus_nets).name == name
 
 
 def test_synthetic_pileups_follow_the_codebook():

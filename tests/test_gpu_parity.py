@@ -376,6 +376,31 @@ def test_batchnorm_built_model_matches_reference_golden(gpu, precision):
     check_log_probs(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], precision, "batchnorm")
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_softplus_configuration_matches_reference_golden(gpu, precision):
+    """moe_attention_config_single_tech_old_equivalent_layer_norm.py (Softplus in the read convolver and the expert head, no
+    normalisation layers): the fused kernels are ReLU kernels, so this model runs layer by layer (conv1d_fp32 /
+    convlayer_tc with the Softplus epilogue) and reproduces the reference's outputs (tests/golden/single_tech_softplus.npz)."""
+    from helpers import batchnorm_params
+    cfg, pl, g = load_golden("single_tech_softplus")
+    state, params = batchnorm_params("single_tech_softplus")
+    net = gpu.MoEAttentionB200.from_state_dict(state, softplus_nets=cfg.softplus_nets, device=DEV, precision=precision)
+    assert net.cfg.name == "single_tech_softplus"
+    before = net.engine.launch_count()
+    res = net.forward(*pl.forward_args())
+    assert net.engine.launch_count() - before > 20                      # un-fused: one launch per layer
+    np.testing.assert_allclose(res.reshape(1, -1).cpu().numpy(), g["logits"], rtol=0, atol=TOL_LOGIT[precision])
+    r = net.last_result
+    np.testing.assert_allclose(r.pair_prob[0].cpu().numpy(), g["pair_mixed"], rtol=0, atol=TOL_PROB[precision])
+    check_calls(r, g["pair_mixed"], g["best_pair"], TOL_PROB[precision], "single_tech_softplus/" + precision)
+    # more sites than the fixture holds, against the oracle
+    pl2 = synth.make_pileups(60, coverage=14, channels=cfg.read_cin, seed=77)
+    from oracle import hello_oracle as O
+    want = O.OracleModel(cfg, params).forward(*pl2.forward_args())
+    got = net.forward(*pl2.forward_args())
+    assert (got.cpu().reshape(-1) - want.reshape(-1)).abs().max().item() < TOL_LOGIT[precision]
+
+
 @pytest.mark.parametrize("case", ["legacy_hybrid_additive", "legacy_hybrid_combiners"])
 @pytest.mark.parametrize("precision", PRECISIONS)
 def test_legacy_hybrid_wiring_matches_reference_golden(gpu, precision, case):

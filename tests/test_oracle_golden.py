@@ -86,6 +86,33 @@ def test_batchnorm_model_is_folded_like_the_reference_evaluates_it():
     np.testing.assert_allclose(np.array(mixed, np.float32), g["pair_mixed"], rtol=0, atol=TOL)
 
 
+def test_softplus_configuration_matches_the_reference():
+    """tests/golden/single_tech_softplus.npz: moe_attention_config_single_tech_old_equivalent_layer_norm.py as shipped
+    (norm_type "Noop", activation "Softplus": plain Conv1d / Linear, torch.nn.Softplus() in the read convolver and the expert
+    head, ReLU in the compressor, one BatchNorm1d left in the pooled head).  The state dict says nothing about activations:
+    the caller names the Softplus sub-networks; the oracle then reproduces the reference's logits and probabilities."""
+    from helpers import batchnorm_params
+    cfg, pl, g = load_golden("single_tech_softplus")
+    assert cfg.activation("read_convolver0") == "softplus" and cfg.activation("compressor0") == "relu" and cfg.activation("xattn0") == "softplus"
+    state, params = batchnorm_params("single_tech_softplus")
+    assert weights.is_plain_state(state) and not weights.is_plain_state(params)
+    assert weights.cfg_from_state_dict(params, softplus_nets=cfg.softplus_nets).name == "single_tech_softplus"
+    assert weights.cfg_from_state_dict(params).name == "single_tech"        # same tensors: only the caller knows the activation
+    assert weights.params_digest(params) == str(g["digest"])
+    torch.set_num_threads(1)
+    model = O.OracleModel(cfg, params)
+    res = model.forward(*pl.forward_args())
+    np.testing.assert_allclose(res.reshape(1, -1).numpy(), g["logits"], rtol=0, atol=TOL)
+    relu_res = O.OracleModel(arch.CONFIGS["single_tech"], params).forward(*pl.forward_args())
+    assert (relu_res.reshape(1, -1).numpy() - g["logits"]).__abs__().max() > 0.05           # the activation matters
+    mixed = []
+    for s in range(pl.n_sites):
+        fd, seg = pl.site_feature_dict(s)
+        r = O.wrapper_forward(model, fd, seg, provide_predictions=True)
+        mixed += [float(v) for v in r[0].values()]
+    np.testing.assert_allclose(np.array(mixed, np.float32), g["pair_mixed"], rtol=0, atol=TOL)
+
+
 @pytest.mark.parametrize("case", ["legacy_hybrid_additive", "legacy_hybrid_combiners"])
 def test_legacy_hybrid_wiring_matches_the_reference(case):
     """tests/golden/legacy_hybrid_additive.npz: MoEMergedAdvanced (python/MixtureOfExpertsAdvanced.py:255-484) with two

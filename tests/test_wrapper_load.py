@@ -133,9 +133,11 @@ if kind == "batchnorm":
     moe = M.create_moe_attention_model({"read_conv0": rc.config, "compressor0": cc.config, "xattn0": xa.config}).eval()
     state = weights.init_batchnorm_state([(k, tuple(v.shape)) for k, v in moe.state_dict().items()], seed=13)
     moe.load_state_dict(state)
-else:                                                   # the Softplus / no-normalisation experiment configuration
+else:                                                   # the Softplus / no-normalisation configuration
     cfgd = importlib.import_module("moe_attention_config_single_tech_old_equivalent_layer_norm").configDict
     moe = M.create_moe_attention_model(cfgd).eval()
+    state = weights.init_batchnorm_state([(k, tuple(v.shape)) for k, v in moe.state_dict().items()], seed=13)
+    moe.load_state_dict(state)
 torch.save(M.createMoEFullMergedAdvancedModelWrapper(moe.eval()).eval(), path)
 from hello_b200 import model
 try:
@@ -147,10 +149,10 @@ except _lib.HelloMoEError as e:
 
 
 @pytest.mark.skipif(not ref_model.available(), reason="the reference's python modules are not available")
-def test_batchnorm_wrapper_is_folded_and_softplus_model_is_refused(tmp_path):
+def test_batchnorm_wrapper_is_folded_and_softplus_model_is_recognised(tmp_path):
     """A .wrapper.dnn of a model built without weight-norm loads (BatchNorm1d folded, same blob as folding the state dict
-    directly); the reference's Softplus experiment (moe_attention_config_single_tech_old_equivalent_layer_norm.py) is
-    refused by name instead of being run with the wrong activation."""
+    directly); the reference's Softplus configuration (moe_attention_config_single_tech_old_equivalent_layer_norm.py) is
+    recognised by its modules -- the state dict alone would read as the ReLU model -- and packs Softplus layer records."""
     from helpers import batchnorm_params
     run = lambda kind: subprocess.run([sys.executable, "-c", CHILD_BN % {"root": ROOT}, kind, str(tmp_path / (kind + ".dnn"))],
                                       capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
@@ -162,5 +164,9 @@ def test_batchnorm_wrapper_is_folded_and_softplus_model_is_refused(tmp_path):
     assert line[2] == hashlib.sha256(weights.pack_blob(arch.CONFIGS["single_tech"], params)).hexdigest()
     out = run("softplus")
     assert out.returncode == 0, out.stderr[-2000:]
-    refused = [l for l in out.stdout.splitlines() if l.startswith("REFUSED")]
-    assert refused and "Softplus" in refused[-1], out.stdout
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()
+    assert line[1] == "single_tech_softplus"
+    cfg_sp = arch.CONFIGS["single_tech_softplus"]
+    _, params_sp = batchnorm_params("single_tech_softplus")          # same deterministic state as the child built
+    assert line[2] == hashlib.sha256(weights.pack_blob(cfg_sp, params_sp)).hexdigest()
+    assert line[2] != hashlib.sha256(weights.pack_blob(arch.CONFIGS["single_tech"], params_sp)).hexdigest()
