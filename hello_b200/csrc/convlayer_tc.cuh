@@ -382,7 +382,8 @@ struct PackedConv {
 inline bool eligible(const ConvDesc& c) {
     Geometry g;
     return c.cin % 16 == 0 && c.cout % 16 == 0 && c.cin >= 16 && c.cout >= 16 && (c.k == 1 || c.k == 3) &&
-           (c.cout <= 256 || c.cout % 256 == 0) && geometry(c, 3, &g);
+           (c.cout <= 256 || c.cout % 256 == 0) && (c.cout <= EPI_COLS || c.cout % EPI_COLS == 0) &&   // whole epilogue blocks
+           geometry(c, 3, &g);
 }
 
 }  // namespace cl
