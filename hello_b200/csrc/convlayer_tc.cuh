@@ -466,7 +466,8 @@ static bool convlayer_tc_launch(ConvLayerTC* t, const ActView& x, const ConvDesc
                                 const float* resid, cudaStream_t st, cudaError_t* e) {
     *e = cudaSuccess;
     if (!t || x.is_u8 || x.sc != 1 || x.ch != c.cin || (x.sl % 4) || (x.sn % 4) ||
-        (reinterpret_cast<uintptr_t>(x.base) & 15)) return false;
+        ((reinterpret_cast<uintptr_t>(x.base) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(resid)) & 15))
+        return false;                                  // 128-bit loads and the rows' bulk copies need 16-byte aligned bases
     auto it = t->layers.find(c.w);
     if (it == t->layers.end()) return false;
     if (n_items <= 0) return true;
