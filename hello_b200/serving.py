@@ -135,10 +135,17 @@ class BatchPlanner:
 
 
 def serve_loop(run_batch: Callable, n_tech: int, requests, responses: Sequence, max_sites: int = 4096,
-               max_wait_s: float = 0.002, stats: Optional[dict] = None, heartbeat=None, idle_tick_s: float = 0.5):
+               max_wait_s: float = 0.0003, stats: Optional[dict] = None, heartbeat=None, idle_tick_s: float = 0.5):
     """Drain `requests` (SiteRequest objects; the string _STOP ends the loop), score up to `max_sites` pending sites
     per call of `run_batch(reads, allele_read_off, site_allele_off, allele_rank, ref_onehot)` -> dict of numpy arrays
     (pair_prob, meta, best_pair, call_pair, call_qual, best_expert) and answer on responses[client].
+
+    Batching policy: everything already queued is taken at once; the loop then waits at most `max_wait_s` for stragglers
+    and never longer than it takes every client to have a request in the batch -- the workers call synchronously (one
+    request in flight each, like the reference's pool workers), so once all of them are waiting nothing more can arrive.
+    A forward of a few dozen sites costs the same as one of a single site (launch-bound), so requests that arrive while a
+    batch is on the GPU simply form the next one; a long collection window only adds latency, and with synchronous
+    callers latency IS throughput (sites/s = workers / round trip).
 
     A request that fails validation is answered with its exception on its own; if a whole batch fails, its sites are
     re-scored one by one so that only the offending client sees the exception.  `heartbeat` (a shared double) is stamped
@@ -174,11 +181,18 @@ def serve_loop(run_batch: Callable, n_tech: int, requests, responses: Sequence, 
         if not admit(plan, first):
             break
         deadline = time.perf_counter() + max_wait_s
+        full = min(max_sites, max(1, len(responses)))        # one outstanding request per client at most
         while len(plan) < max_sites:
             try:
-                nxt = requests.get(timeout=max(0.0, deadline - time.perf_counter()))
+                nxt = requests.get_nowait()                  # whatever queued up during the previous batch
             except queue.Empty:
-                break
+                left = deadline - time.perf_counter()
+                if left <= 0 or len(plan) >= full:
+                    break
+                try:
+                    nxt = requests.get(timeout=left)
+                except queue.Empty:
+                    break
             if not admit(plan, nxt):
                 stop = True
                 break
@@ -293,7 +307,7 @@ class ScoringServer:
     """Owns one GPU engine in its own (spawned) process.  ``client(i)`` gives worker i its ``RemoteNetwork``."""
 
     def __init__(self, cfg_name: str, params: Dict[str, torch.Tensor], n_clients: int, device="cuda:0",
-                 precision: str = "bf16x3", max_sites: int = 4096, max_wait_s: float = 0.002,
+                 precision: str = "bf16x3", max_sites: int = 4096, max_wait_s: float = 0.0003,
                  startup_timeout_s: float = 300.0):
         if not torch.cuda.is_available():
             from . import _lib

@@ -87,8 +87,7 @@ def main():
     out["scoring_server"] = []
     ctx = mp.get_context("fork")
     for n_prod in args.producers:
-        with serving.ScoringServer(args.config, params, n_clients=n_prod, device="cuda:0", precision="bf16x3", max_sites=4096,
-                                   max_wait_s=0.002) as server:
+        with serving.ScoringServer(args.config, params, n_clients=n_prod, device="cuda:0", precision="bf16x3", max_sites=4096) as server:
             barrier, out_q = ctx.Barrier(n_prod), ctx.Queue()
             procs = []
             for c in range(n_prod):
