@@ -855,6 +855,24 @@ def load_wrapper(path: str, device="cuda:0", precision: str = "bf16x3", referenc
     return MoEMergedWrapperB200(moe, providePredictions=provide)
 
 
+class _SiteResult:
+    """The results of one site scored through the wrapper: a host copy of the packed result image; the BatchResult fields
+    (host tensors) are made on first access."""
+
+    def __init__(self, raw: np.ndarray, fields, n_pairs: int):
+        self._raw, self._fields = raw, fields
+        self.pair_off = torch.tensor([0, n_pairs], dtype=torch.int64)
+
+    def __getattr__(self, name):
+        fields = self.__dict__.get("_fields", {})
+        if name not in fields:
+            raise AttributeError(name)
+        o, nb, dt, shape = fields[name]
+        t = torch.from_numpy(self._raw[o:o + nb].view(dt).reshape(shape))
+        setattr(self, name, t)
+        return t
+
+
 class MoEMergedWrapperB200:
     """Drop-in for ``MoEMergedWrapperAdvanced``: ``network(featureDict, segment)`` for one site."""
 
@@ -865,34 +883,119 @@ class MoEMergedWrapperB200:
     def eval(self):
         return self
 
+    def _scratch(self, in_bytes: int, out_bytes: int):
+        """One pinned host + one device buffer for a site's inputs, and the same for its results: a call is ONE host ->
+        device copy, the kernels, ONE device -> host copy, and no tensor is created for anything that only needs an address
+        (a dozen small copies, allocations and views cost more than the site's kernels).  Grown on demand, reused by every
+        call of this wrapper."""
+        sc = getattr(self, "_sc", None)
+        if sc is None or sc["h_in"].numel() < in_bytes or sc["h_out"].numel() < out_bytes:
+            dev = self.moeMerged.engine.device
+            cap_in, cap_out = max(1 << 16, 2 * in_bytes), max(1 << 12, 2 * out_bytes)
+            sc = {"h_in": torch.empty(cap_in, dtype=torch.uint8).pin_memory(), "d_in": torch.empty(cap_in, dtype=torch.uint8, device=dev),
+                  "h_out": torch.empty(cap_out, dtype=torch.uint8).pin_memory(), "d_out": torch.empty(cap_out, dtype=torch.uint8, device=dev)}
+            sc["np_in"], sc["np_out"] = sc["h_in"].numpy(), sc["h_out"].numpy()
+            self._sc = sc
+        return sc
+
     def forward(self, featureDict, segment):
         cfg = self.moeMerged.cfg
         eng = self.moeMerged.engine
         alleles = list(featureDict.keys())
-        n_tech = len(cfg.read_cin)
-        reads, offs = [], []
+        n, n_tech = len(alleles), len(cfg.read_cin)
+        L = arch.FEATURE_LENGTH
+        reads, counts = [], []
         for t in range(n_tech):
             parts = [featureDict[a][t] for a in alleles]
             if any(p is None for p in parts):
                 raise ValueError("hybrid model called without technology %d tensors" % t)
-            offs.append(_csr([p.shape[0] for p in parts]))
-            reads.append(_as_uint8(torch.cat(parts, dim=0)))          # stays [r, L, C]: no transpose needed
-        sao = _csr([len(alleles)])
+            counts.append([int(p.shape[0]) for p in parts])
+            if min(counts[-1]) < 1:
+                raise ValueError("every CSR slot must hold at least one row (reduceSlots requires it)")
+            r = _as_uint8(torch.cat(parts, dim=0)).contiguous()           # stays [r, L, C]: no transpose needed
+            if tuple(r.shape[1:]) != (L, cfg.read_cin[t]):
+                raise ValueError("technology %d reads have shape %s, expected [R, %d, %d]" % (t, tuple(r.shape), L, cfg.read_cin[t]))
+            reads.append(r)
         # tie-break of the reference's sort is on the allele strings (caller_calling.py:702-705)
-        order = sorted(range(len(alleles)), key=lambda i: alleles[i])
-        rank = torch.empty(len(alleles), dtype=torch.int32)
+        order = sorted(range(n), key=lambda i: alleles[i])
+        rank = [0] * n
         for r, i in enumerate(order):
             rank[i] = r
-        ref = segment if cfg.meta == "meta_convolver_ref" else None
-        batch = DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, offs, sao, ref, eng.device, allele_rank=rank)
-        res = eng.run(batch)
-        self.moeMerged.last_result = res
-        pp = res.pair_prob.cpu()
-        meta = res.meta[0].cpu()
-        n = len(alleles)
+        need_ref = cfg.meta == "meta_convolver_ref"
+        P = n * (n + 1) // 2
+        # ---- input image, every piece 16-byte aligned: [reads_t ...][allele_read_off_t int32 [n+1] ...]
+        #      [site_allele_off int32 [2]][rank int32 [n]][pair_off int64 [2]][reference one-hot fp32 [L*5]]
+        al = lambda x: (x + 15) & ~15
+        off, o_reads, o_aro = 0, [], []
+        for t in range(n_tech):
+            o_reads.append(off); off = al(off + reads[t].numel())
+        for t in range(n_tech):
+            o_aro.append(off); off = al(off + 4 * (n + 1))
+        o_sao = off; off = al(off + 8)
+        o_rank = off; off = al(off + 4 * n)
+        o_po = off; off = al(off + 16)
+        o_ref = off
+        if need_ref:
+            off = al(off + 4 * L * 5)
+        in_bytes = off
+        # ---- result image (include/hello_moe.h hello_result), same alignment
+        fields, o = {}, 0
+        for name, dt, shape in (("logits", np.float32, (3, n)), ("meta", np.float32, (1, 3)), ("pair_prob", np.float32, (4, P)),
+                                ("pair_mix64", np.float64, (P,)), ("best_pair", np.int32, (1, 2)), ("best_prob", np.float32, (1,)),
+                                ("call_pair", np.int32, (1, 5, 2)), ("call_qual", np.float64, (1, 5)), ("best_expert", np.int32, (1,))):
+            nb = int(np.dtype(dt).itemsize)
+            for d in shape:
+                nb *= d
+            fields[name] = (o, nb, dt, shape)
+            o = al(o + nb)
+        out_bytes = o
+        sc = self._scratch(in_bytes, out_bytes)
+        np_in = sc["np_in"]
+        for t in range(n_tech):
+            np_in[o_reads[t]:o_reads[t] + reads[t].numel()] = reads[t].numpy().reshape(-1)
+            aro = np_in[o_aro[t]:o_aro[t] + 4 * (n + 1)].view(np.int32)
+            aro[0] = 0
+            np.cumsum(counts[t], out=aro[1:])
+        np_in[o_sao:o_sao + 8].view(np.int32)[:] = (0, n)
+        np_in[o_rank:o_rank + 4 * n].view(np.int32)[:] = rank
+        np_in[o_po:o_po + 16].view(np.int64)[:] = (0, P)
+        if need_ref:
+            np_in[o_ref:o_ref + 4 * L * 5].view(np.float32)[:] = segment.reshape(-1).float().numpy()
+        sc["d_in"][:in_bytes].copy_(sc["h_in"][:in_bytes], non_blocking=True)
+        base_d, base_h, base_o = sc["d_in"].data_ptr(), sc["h_in"].data_ptr(), sc["d_out"].data_ptr()
+        hb = _lib.HelloBatch()
+        hb.n_sites, hb.n_alleles, hb.input_layout = 1, n, _lib.LAYOUT_RLC
+        for t in range(n_tech):
+            hb.n_reads[t] = reads[t].shape[0]
+            hb.d_reads[t] = base_d + o_reads[t]
+            hb.d_allele_read_off[t], hb.h_allele_read_off[t] = base_d + o_aro[t], base_h + o_aro[t]
+        hb.d_site_allele_off, hb.h_site_allele_off = base_d + o_sao, base_h + o_sao
+        hb.d_ref_onehot = base_d + o_ref if need_ref else None
+        hb.d_allele_rank, hb.d_pair_off = base_d + o_rank, base_d + o_po
+        hr = _lib.HelloResult()
+        hr.d_logits, hr.d_meta = base_o + fields["logits"][0], base_o + fields["meta"][0]
+        hr.d_pair_prob, hr.d_pair_mix64 = base_o + fields["pair_prob"][0], base_o + fields["pair_mix64"][0]
+        hr.d_best_pair, hr.d_best_prob = base_o + fields["best_pair"][0], base_o + fields["best_prob"][0]
+        hr.d_call_pair, hr.d_call_qual = base_o + fields["call_pair"][0], base_o + fields["call_qual"][0]
+        hr.d_best_expert = base_o + fields["best_expert"][0]
+        nr = [int(reads[t].shape[0]) if t < n_tech else 0 for t in range(2)]
+        ws = eng._workspace(eng.workspace_bytes(nr[0], nr[1], n, 1))
+        stream = torch.cuda.current_stream(eng.device)
+        with torch.cuda.device(eng.device):
+            rc = eng.lib.hello_moe_forward(eng.handle, C.byref(hb), C.byref(hr), ws.data_ptr(), ws.numel(),
+                                           C.c_void_p(stream.cuda_stream))
+        eng._check(rc, "hello_moe_forward")
+        sc["h_out"][:out_bytes].copy_(sc["d_out"][:out_bytes], non_blocking=True)
+        stream.synchronize()
+        raw = sc["np_out"][:out_bytes].copy()                              # the caller keeps the results; the scratch is reused
+        self.moeMerged.last_result = _SiteResult(raw, fields, P)
+        pp = torch.from_numpy(raw[fields["pair_prob"][0]:fields["pair_prob"][0] + 16 * P].view(np.float32).reshape(4, P))
+        meta = torch.from_numpy(raw[fields["meta"][0]:fields["meta"][0] + 12].view(np.float32))
         keys = [(alleles[i], alleles[j]) for i in range(n) for j in range(i, n)]
         dicts = [{k: pp[row, q] for q, k in enumerate(keys)} for row in range(4)]
-        self.last_call = (keys[self._pair_index(n, res.best_pair[0].tolist())], float(res.best_prob[0]))
+        bp = raw[fields["best_pair"][0]:fields["best_pair"][0] + 8].view(np.int32)
+        self.last_call = (keys[self._pair_index(n, (int(bp[0]), int(bp[1])))],
+                          float(raw[fields["best_prob"][0]:fields["best_prob"][0] + 4].view(np.float32)[0]))
         self.last_alleles = alleles
         if self.providePredictions:
             return tuple(dicts) + (meta,)
