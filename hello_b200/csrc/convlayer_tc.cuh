@@ -64,7 +64,15 @@ struct ConvTcArgs {
     int lin, lout, cin, cout, ksz, stride, relu, nt, stacked;
     int pitch, sigma_min, n_arr, kc, n_chunks, max_delta;
     int tap_arr[MAX_TAPS], tap_delta[MAX_TAPS];
+    long long* trace;        // developer timeline (tools/convlayer_trace.cu): CTA 0 stamps clock64() per tile and role; else nullptr
 };
+
+// Timeline slots of one tile: producer {slot free, loads issued, operand stored}, issuer {accumulator free, operand
+// seen, last MMA issued}, epilogue {accumulator seen, rows written}.
+constexpr int TRACE_TILES = 48, TRACE_SLOTS = 8;
+__device__ __forceinline__ void trace_stamp(const ConvTcArgs& a, uint32_t tile_seq, int slot) {
+    if (a.trace && blockIdx.x == 0 && tile_seq < (uint32_t)TRACE_TILES) a.trace[tile_seq * TRACE_SLOTS + slot] = clock64();
+}
 
 // shared -> global bulk copy of the issuing thread's own bulk group (TMA unit); the source must stay untouched until
 // bulk_wait_read
@@ -155,6 +163,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
             const uint32_t ab = it & 1u;
             ptx::mbar_wait(bar(BAR_ACCFULL + ab), (it >> 1) & 1u);
             ptx::tc_fence_after();
+            if (r == 0) trace_stamp(a, it, 6);
             const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16) + ab * 256u;
             for (int cb = 0; cb < n_cb; ++cb) {
                 if (row_ok) bulk_wait_read();                                // the previous piece has left the output line
@@ -197,6 +206,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar(BAR_ACCEMPTY + ab));                        // the accumulator may be overwritten
+            if (r == 0) trace_stamp(a, it, 7);
         }
         bulk_wait_all();
     } else if (warp < E_WARPS + P_WARPS) {
@@ -229,6 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
                 }
                 const uint32_t slot = chunk_n % A_SLOTS;
                 ptx::mbar_wait(bar(BAR_AEMPTY + slot), ((chunk_n / A_SLOTS) & 1u) ^ 1u);
+                if (r == 0 && ch == 0) trace_stamp(a, chunk_n / (uint32_t)a.n_chunks, 0);
                 uint8_t* buf = s_a + slot * a_slot;
                 const float* xc = a.x + ch * a.kc;
                 for (int base = 0; base < n_f4; base += P_GROUP * 16) {
@@ -242,6 +253,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
                             if (off >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(xc + off) + (i & ((1 << f4_shift) - 1)));
                         }
                     }
+                    if (r == 0 && ch == 0 && base == 0) trace_stamp(a, chunk_n / (uint32_t)a.n_chunks, 1);
 #pragma unroll
                     for (int u = 0; u < 16; ++u) {
                         const int i = base + u * P_GROUP + r;
@@ -262,6 +274,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
                 }
                 ptx::fence_proxy_async();
                 ptx::mbar_arrive(bar(BAR_AFULL + slot));
+                if (r == 0 && ch == a.n_chunks - 1) trace_stamp(a, chunk_n / (uint32_t)a.n_chunks, 2);
             }
         }
     } else if (warp == E_WARPS + P_WARPS) {
@@ -273,12 +286,14 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
             const uint32_t ab = it & 1u;
             ptx::mbar_wait(bar(BAR_ACCEMPTY + ab), ((it >> 1) & 1u) ^ 1u);   // the epilogue has read this accumulator
             ptx::tc_fence_after();
+            if (lane == 0) trace_stamp(a, it, 3);
             const uint32_t d = tmem + ab * 256u;
             uint32_t first = 1u;
             for (int ch = 0; ch < a.n_chunks; ++ch, ++chunk_n) {
                 const uint32_t slot = chunk_n % A_SLOTS;
                 ptx::mbar_wait(bar(BAR_AFULL + slot), (chunk_n / A_SLOTS) & 1u);
                 ptx::tc_fence_after();
+                if (lane == 0 && ch == 0) trace_stamp(a, it, 4);
                 const uint32_t abase = ptx::smem_u32(s_a + slot * a_slot);
                 for (int tp = 0; tp < a.ksz; ++tp) {
                     for (int j = 0; j < k16c; ++j, ++unit_n) {
@@ -308,6 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
             }
             ptx::tc_commit(bar(BAR_ACCFULL + ab));
             __syncwarp();
+            if (lane == 0) trace_stamp(a, it, 5);
         }
     } else {
         // ------------------------------------------------------------------ weight loader
@@ -393,6 +409,7 @@ struct ConvLayerTC {
     std::map<const float*, cl::PackedConv> layers;
     int mode = 3;
     int sm_count = 148;
+    long long* d_trace = nullptr;          // developer timeline buffer (tools/convlayer_trace.cu), nullptr in the library
 };
 
 static bool convlayer_tc_add(ConvLayerTC* t, const ConvDesc& c, const float* d_base, const float* h_base, std::string& err) {
@@ -481,6 +498,7 @@ static bool convlayer_tc_launch(ConvLayerTC* t, const ActView& x, const ConvDesc
     a.sigma_min = g.sigma_min; a.max_delta = g.max_delta;
     for (int k = 0; k < cl::MAX_TAPS; ++k) { a.tap_arr[k] = g.tap_arr[k]; a.tap_delta[k] = g.tap_delta[k]; }
     a.pitch = g.pitch(a.lin, a.lout);
+    a.trace = t->d_trace;
     const long long total = n_items * a.pitch;
     if (a.lout <= 0 || total + 128 + cl::ROWS_TAB >= 0x7fffffffLL) return false;      // 32-bit row arithmetic in the kernel
     a.n_items = (uint32_t)n_items; a.total_rows = (uint32_t)total;
