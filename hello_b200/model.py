@@ -283,6 +283,108 @@ class MoEEngine:
                                                   workspace.data_ptr(), workspace.numel(), C.c_void_p(stream))
         self._check(rc, "hello_moe_forward_range")
 
+    def _scratch(self, in_bytes: int, out_bytes: int):
+        """One pinned host + one device buffer for a small batch's inputs, and the same for its results.  Grown on demand,
+        reused by every run_host call of this engine."""
+        sc = getattr(self, "_sc", None)
+        if sc is None or sc["h_in"].numel() < in_bytes or sc["h_out"].numel() < out_bytes:
+            cap_in, cap_out = max(1 << 16, 2 * in_bytes), max(1 << 12, 2 * out_bytes)
+            sc = {"h_in": torch.empty(cap_in, dtype=torch.uint8).pin_memory(),
+                  "d_in": torch.empty(cap_in, dtype=torch.uint8, device=self.device),
+                  "h_out": torch.empty(cap_out, dtype=torch.uint8).pin_memory(),
+                  "d_out": torch.empty(cap_out, dtype=torch.uint8, device=self.device)}
+            sc["np_in"], sc["np_out"] = sc["h_in"].numpy(), sc["h_out"].numpy()
+            self._sc = sc
+        return sc
+
+    def run_host(self, reads: Sequence[np.ndarray], allele_read_off: Sequence[np.ndarray], site_allele_off: np.ndarray,
+                 allele_rank: np.ndarray, ref_onehot: Optional[np.ndarray] = None):
+        """Score a SMALL batch that lives in host memory (one site of the strict drop-in call, a few dozen sites of the
+        scoring server) and return its results on the host: -> (raw result image uint8, {field: (offset, bytes, dtype, shape)}).
+
+        The whole input travels as ONE image (reads, CSR arrays, allele ranks, pair offsets, reference one-hot; every piece
+        16-byte aligned) in one host -> device copy from a pinned buffer, the results come back as one image in one device ->
+        host copy, and the C ABI gets raw addresses into the two device images: no tensor is created for anything that only
+        needs an address.  (A dozen small copies, allocations and views cost more than a site's kernels.)  Synchronous.
+        reads[t]: uint8 [R_t, L, C_t]; allele_read_off[t]: int32 [A+1]; site_allele_off: int32 [S+1]; allele_rank: int32 [A]
+        (tie-break order of the allele strings inside each site); ref_onehot: fp32 [S, L, 5] for the reference-gated model."""
+        cfg, L = self.cfg, arch.FEATURE_LENGTH
+        n_tech = len(cfg.read_cin)
+        sao = np.asarray(site_allele_off, np.int64)
+        S, A = sao.size - 1, int(sao[-1])
+        napS = np.diff(sao)
+        pair_off = np.zeros(S + 1, np.int64)
+        np.cumsum(napS * (napS + 1) // 2, out=pair_off[1:])
+        P = int(pair_off[-1])
+        need_ref = cfg.meta == "meta_convolver_ref"
+        if need_ref and ref_onehot is None:
+            raise ValueError("this model gates on the reference segment; reference_segments is required")
+        al = lambda x: (x + 15) & ~15
+        off, o_reads, o_aro = 0, [], []
+        for t in range(n_tech):
+            r = reads[t]
+            if r.dtype != np.uint8 or r.ndim != 3 or tuple(r.shape[1:]) != (L, cfg.read_cin[t]):
+                raise ValueError("technology %d reads have shape %s %s, expected uint8 [R, %d, %d]" % (t, r.shape, r.dtype, L, cfg.read_cin[t]))
+            o_reads.append(off); off = al(off + r.size)
+        for t in range(n_tech):
+            if np.asarray(allele_read_off[t]).size != A + 1:
+                raise ValueError("allele_read_off has the wrong length")
+            o_aro.append(off); off = al(off + 4 * (A + 1))
+        o_sao = off; off = al(off + 4 * (S + 1))
+        o_rank = off; off = al(off + 4 * A)
+        o_po = off; off = al(off + 8 * (S + 1))
+        o_ref = off
+        if need_ref:
+            off = al(off + 4 * S * L * 5)
+        in_bytes = off
+        fields, o = {}, 0
+        for name, dt, shape in (("logits", np.float32, (3, A)), ("meta", np.float32, (S, 3)), ("pair_prob", np.float32, (4, P)),
+                                ("pair_mix64", np.float64, (P,)), ("best_pair", np.int32, (S, 2)), ("best_prob", np.float32, (S,)),
+                                ("call_pair", np.int32, (S, 5, 2)), ("call_qual", np.float64, (S, 5)), ("best_expert", np.int32, (S,))):
+            nb = int(np.dtype(dt).itemsize)
+            for d in shape:
+                nb *= d
+            fields[name] = (o, nb, dt, shape)
+            o = al(o + nb)
+        out_bytes = max(o, 16)
+        sc = self._scratch(in_bytes, out_bytes)
+        np_in = sc["np_in"]
+        for t in range(n_tech):
+            np_in[o_reads[t]:o_reads[t] + reads[t].size] = reads[t].reshape(-1)
+            np_in[o_aro[t]:o_aro[t] + 4 * (A + 1)].view(np.int32)[:] = allele_read_off[t]
+        np_in[o_sao:o_sao + 4 * (S + 1)].view(np.int32)[:] = sao
+        np_in[o_rank:o_rank + 4 * A].view(np.int32)[:] = allele_rank
+        np_in[o_po:o_po + 8 * (S + 1)].view(np.int64)[:] = pair_off
+        if need_ref:
+            np_in[o_ref:o_ref + 4 * S * L * 5].view(np.float32)[:] = np.asarray(ref_onehot, np.float32).reshape(-1)
+        sc["d_in"][:in_bytes].copy_(sc["h_in"][:in_bytes], non_blocking=True)
+        base_d, base_h, base_o = sc["d_in"].data_ptr(), sc["h_in"].data_ptr(), sc["d_out"].data_ptr()
+        hb = _lib.HelloBatch()
+        hb.n_sites, hb.n_alleles, hb.input_layout = S, A, _lib.LAYOUT_RLC
+        for t in range(n_tech):
+            hb.n_reads[t] = reads[t].shape[0]
+            hb.d_reads[t] = base_d + o_reads[t]
+            hb.d_allele_read_off[t], hb.h_allele_read_off[t] = base_d + o_aro[t], base_h + o_aro[t]
+        hb.d_site_allele_off, hb.h_site_allele_off = base_d + o_sao, base_h + o_sao
+        hb.d_ref_onehot = base_d + o_ref if need_ref else None
+        hb.d_allele_rank, hb.d_pair_off = base_d + o_rank, base_d + o_po
+        hr = _lib.HelloResult()
+        hr.d_logits, hr.d_meta = base_o + fields["logits"][0], base_o + fields["meta"][0]
+        hr.d_pair_prob, hr.d_pair_mix64 = base_o + fields["pair_prob"][0], base_o + fields["pair_mix64"][0]
+        hr.d_best_pair, hr.d_best_prob = base_o + fields["best_pair"][0], base_o + fields["best_prob"][0]
+        hr.d_call_pair, hr.d_call_qual = base_o + fields["call_pair"][0], base_o + fields["call_qual"][0]
+        hr.d_best_expert = base_o + fields["best_expert"][0]
+        nr = [int(reads[t].shape[0]) if t < n_tech else 0 for t in range(2)]
+        ws = self._workspace(self.workspace_bytes(nr[0], nr[1], A, S))
+        stream = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.hello_moe_forward(self.handle, C.byref(hb), C.byref(hr), ws.data_ptr(), ws.numel(),
+                                            C.c_void_p(stream.cuda_stream))
+        self._check(rc, "hello_moe_forward")
+        sc["h_out"][:out_bytes].copy_(sc["d_out"][:out_bytes], non_blocking=True)
+        stream.synchronize()
+        return sc["np_out"][:out_bytes].copy(), fields, pair_off         # the caller keeps the results; the scratch is reused
+
     @staticmethod
     def _ranges(n_sites: int, chunk_sites: int):
         """Site ranges of a streamed call: the first ones are short (chunk/8, chunk/4, chunk/2, ...) because the first
@@ -883,111 +985,31 @@ class MoEMergedWrapperB200:
     def eval(self):
         return self
 
-    def _scratch(self, in_bytes: int, out_bytes: int):
-        """One pinned host + one device buffer for a site's inputs, and the same for its results: a call is ONE host ->
-        device copy, the kernels, ONE device -> host copy, and no tensor is created for anything that only needs an address
-        (a dozen small copies, allocations and views cost more than the site's kernels).  Grown on demand, reused by every
-        call of this wrapper."""
-        sc = getattr(self, "_sc", None)
-        if sc is None or sc["h_in"].numel() < in_bytes or sc["h_out"].numel() < out_bytes:
-            dev = self.moeMerged.engine.device
-            cap_in, cap_out = max(1 << 16, 2 * in_bytes), max(1 << 12, 2 * out_bytes)
-            sc = {"h_in": torch.empty(cap_in, dtype=torch.uint8).pin_memory(), "d_in": torch.empty(cap_in, dtype=torch.uint8, device=dev),
-                  "h_out": torch.empty(cap_out, dtype=torch.uint8).pin_memory(), "d_out": torch.empty(cap_out, dtype=torch.uint8, device=dev)}
-            sc["np_in"], sc["np_out"] = sc["h_in"].numpy(), sc["h_out"].numpy()
-            self._sc = sc
-        return sc
-
     def forward(self, featureDict, segment):
         cfg = self.moeMerged.cfg
         eng = self.moeMerged.engine
         alleles = list(featureDict.keys())
         n, n_tech = len(alleles), len(cfg.read_cin)
-        L = arch.FEATURE_LENGTH
-        reads, counts = [], []
+        reads, aro = [], []
         for t in range(n_tech):
             parts = [featureDict[a][t] for a in alleles]
             if any(p is None for p in parts):
                 raise ValueError("hybrid model called without technology %d tensors" % t)
-            counts.append([int(p.shape[0]) for p in parts])
-            if min(counts[-1]) < 1:
+            counts = [int(p.shape[0]) for p in parts]
+            if min(counts) < 1:
                 raise ValueError("every CSR slot must hold at least one row (reduceSlots requires it)")
-            r = _as_uint8(torch.cat(parts, dim=0)).contiguous()           # stays [r, L, C]: no transpose needed
-            if tuple(r.shape[1:]) != (L, cfg.read_cin[t]):
-                raise ValueError("technology %d reads have shape %s, expected [R, %d, %d]" % (t, tuple(r.shape), L, cfg.read_cin[t]))
-            reads.append(r)
+            reads.append(_as_uint8(torch.cat(parts, dim=0)).contiguous().numpy())      # stays [r, L, C]: no transpose needed
+            off = np.zeros(n + 1, np.int32)
+            np.cumsum(counts, out=off[1:])
+            aro.append(off)
         # tie-break of the reference's sort is on the allele strings (caller_calling.py:702-705)
         order = sorted(range(n), key=lambda i: alleles[i])
-        rank = [0] * n
+        rank = np.zeros(n, np.int32)
         for r, i in enumerate(order):
             rank[i] = r
-        need_ref = cfg.meta == "meta_convolver_ref"
-        P = n * (n + 1) // 2
-        # ---- input image, every piece 16-byte aligned: [reads_t ...][allele_read_off_t int32 [n+1] ...]
-        #      [site_allele_off int32 [2]][rank int32 [n]][pair_off int64 [2]][reference one-hot fp32 [L*5]]
-        al = lambda x: (x + 15) & ~15
-        off, o_reads, o_aro = 0, [], []
-        for t in range(n_tech):
-            o_reads.append(off); off = al(off + reads[t].numel())
-        for t in range(n_tech):
-            o_aro.append(off); off = al(off + 4 * (n + 1))
-        o_sao = off; off = al(off + 8)
-        o_rank = off; off = al(off + 4 * n)
-        o_po = off; off = al(off + 16)
-        o_ref = off
-        if need_ref:
-            off = al(off + 4 * L * 5)
-        in_bytes = off
-        # ---- result image (include/hello_moe.h hello_result), same alignment
-        fields, o = {}, 0
-        for name, dt, shape in (("logits", np.float32, (3, n)), ("meta", np.float32, (1, 3)), ("pair_prob", np.float32, (4, P)),
-                                ("pair_mix64", np.float64, (P,)), ("best_pair", np.int32, (1, 2)), ("best_prob", np.float32, (1,)),
-                                ("call_pair", np.int32, (1, 5, 2)), ("call_qual", np.float64, (1, 5)), ("best_expert", np.int32, (1,))):
-            nb = int(np.dtype(dt).itemsize)
-            for d in shape:
-                nb *= d
-            fields[name] = (o, nb, dt, shape)
-            o = al(o + nb)
-        out_bytes = o
-        sc = self._scratch(in_bytes, out_bytes)
-        np_in = sc["np_in"]
-        for t in range(n_tech):
-            np_in[o_reads[t]:o_reads[t] + reads[t].numel()] = reads[t].numpy().reshape(-1)
-            aro = np_in[o_aro[t]:o_aro[t] + 4 * (n + 1)].view(np.int32)
-            aro[0] = 0
-            np.cumsum(counts[t], out=aro[1:])
-        np_in[o_sao:o_sao + 8].view(np.int32)[:] = (0, n)
-        np_in[o_rank:o_rank + 4 * n].view(np.int32)[:] = rank
-        np_in[o_po:o_po + 16].view(np.int64)[:] = (0, P)
-        if need_ref:
-            np_in[o_ref:o_ref + 4 * L * 5].view(np.float32)[:] = segment.reshape(-1).float().numpy()
-        sc["d_in"][:in_bytes].copy_(sc["h_in"][:in_bytes], non_blocking=True)
-        base_d, base_h, base_o = sc["d_in"].data_ptr(), sc["h_in"].data_ptr(), sc["d_out"].data_ptr()
-        hb = _lib.HelloBatch()
-        hb.n_sites, hb.n_alleles, hb.input_layout = 1, n, _lib.LAYOUT_RLC
-        for t in range(n_tech):
-            hb.n_reads[t] = reads[t].shape[0]
-            hb.d_reads[t] = base_d + o_reads[t]
-            hb.d_allele_read_off[t], hb.h_allele_read_off[t] = base_d + o_aro[t], base_h + o_aro[t]
-        hb.d_site_allele_off, hb.h_site_allele_off = base_d + o_sao, base_h + o_sao
-        hb.d_ref_onehot = base_d + o_ref if need_ref else None
-        hb.d_allele_rank, hb.d_pair_off = base_d + o_rank, base_d + o_po
-        hr = _lib.HelloResult()
-        hr.d_logits, hr.d_meta = base_o + fields["logits"][0], base_o + fields["meta"][0]
-        hr.d_pair_prob, hr.d_pair_mix64 = base_o + fields["pair_prob"][0], base_o + fields["pair_mix64"][0]
-        hr.d_best_pair, hr.d_best_prob = base_o + fields["best_pair"][0], base_o + fields["best_prob"][0]
-        hr.d_call_pair, hr.d_call_qual = base_o + fields["call_pair"][0], base_o + fields["call_qual"][0]
-        hr.d_best_expert = base_o + fields["best_expert"][0]
-        nr = [int(reads[t].shape[0]) if t < n_tech else 0 for t in range(2)]
-        ws = eng._workspace(eng.workspace_bytes(nr[0], nr[1], n, 1))
-        stream = torch.cuda.current_stream(eng.device)
-        with torch.cuda.device(eng.device):
-            rc = eng.lib.hello_moe_forward(eng.handle, C.byref(hb), C.byref(hr), ws.data_ptr(), ws.numel(),
-                                           C.c_void_p(stream.cuda_stream))
-        eng._check(rc, "hello_moe_forward")
-        sc["h_out"][:out_bytes].copy_(sc["d_out"][:out_bytes], non_blocking=True)
-        stream.synchronize()
-        raw = sc["np_out"][:out_bytes].copy()                              # the caller keeps the results; the scratch is reused
+        ref = segment.reshape(1, -1, 5).float().numpy() if cfg.meta == "meta_convolver_ref" else None
+        raw, fields, pair_off = eng.run_host(reads, aro, np.array([0, n], np.int32), rank, ref)      # one H2D, one D2H
+        P = int(pair_off[-1])
         self.moeMerged.last_result = _SiteResult(raw, fields, P)
         pp = torch.from_numpy(raw[fields["pair_prob"][0]:fields["pair_prob"][0] + 16 * P].view(np.float32).reshape(4, P))
         meta = torch.from_numpy(raw[fields["meta"][0]:fields["meta"][0] + 12].view(np.float32))

@@ -155,10 +155,18 @@ def serve_loop(run_batch: Callable, n_tech: int, requests, responses: Sequence, 
             heartbeat.value = time.time()
 
     def score(plan):
-        res = run_batch(*plan.build())
+        t0 = time.perf_counter()
+        built = plan.build()
+        t1 = time.perf_counter()
+        res = run_batch(*built)
+        t2 = time.perf_counter()
         for req, site in plan.split(res["pair_prob"], res["meta"], res["best_pair"], res["call_pair"], res["call_qual"],
                                     res["best_expert"]):
             responses[req.client].put((req.seq, site))
+        if stats is not None:                      # where a batch's time goes (seconds, summed over batches)
+            t3 = time.perf_counter()
+            for k, v in (("t_build", t1 - t0), ("t_forward", t2 - t1), ("t_respond", t3 - t2)):
+                stats[k] = stats.get(k, 0.0) + v
 
     def admit(plan, item) -> bool:
         """item -> plan, or straight back to its client when it is malformed.  False on _STOP."""
@@ -177,6 +185,7 @@ def serve_loop(run_batch: Callable, n_tech: int, requests, responses: Sequence, 
             first = requests.get(timeout=idle_tick_s)
         except queue.Empty:
             continue
+        t_first = time.perf_counter()
         plan = BatchPlanner(n_tech)
         if not admit(plan, first):
             break
@@ -198,6 +207,8 @@ def serve_loop(run_batch: Callable, n_tech: int, requests, responses: Sequence, 
                 break
         if len(plan) == 0:
             continue
+        if stats is not None:
+            stats["t_collect"] = stats.get("t_collect", 0.0) + time.perf_counter() - t_first
         tick()
         try:
             score(plan)
@@ -290,17 +301,21 @@ def _gpu_server_main(cfg_name, params, device, precision, requests, responses, m
         raise
 
     def run_batch(reads, offs, sao, rank, ref):
-        batch = model.DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, offs, sao, ref if cfg.meta == "meta_convolver_ref" else None,
-                                            net.engine.device, allele_rank=rank)
-        r = net.engine.run(batch)
-        torch.cuda.synchronize(net.engine.device)
-        return {"pair_prob": r.pair_prob.cpu().numpy(), "meta": r.meta.cpu().numpy(), "best_pair": r.best_pair.cpu().numpy(),
-                "call_pair": r.call_pair.cpu().numpy(), "call_qual": r.call_qual.cpu().numpy(),
-                "best_expert": r.best_expert.cpu().numpy()}
+        # one staging image per direction (MoEEngine.run_host): a batch of a few dozen sites costs one host -> device copy,
+        # the kernels and one device -> host copy
+        raw, fields, _ = net.engine.run_host([r.numpy() for r in reads], [o.numpy() for o in offs], sao.numpy(), rank.numpy(),
+                                             ref.numpy() if (ref is not None and cfg.meta == "meta_convolver_ref") else None)
+        view = lambda k: raw[fields[k][0]:fields[k][0] + fields[k][1]].view(fields[k][2]).reshape(fields[k][3])
+        return {k: view(k) for k in ("pair_prob", "meta", "best_pair", "call_pair", "call_qual", "best_expert")}
 
     heartbeat.value = time.time()
     ready.set()
-    serve_loop(run_batch, len(cfg.read_cin), requests, responses, max_sites, max_wait_s, heartbeat=heartbeat)
+    stats = {} if os.environ.get("HELLO_SERVE_STATS") else None
+    serve_loop(run_batch, len(cfg.read_cin), requests, responses, max_sites, max_wait_s, stats=stats, heartbeat=heartbeat)
+    if stats:                                          # developer aid: where the server's time went, as JSON
+        import json
+        with open(os.environ["HELLO_SERVE_STATS"], "a") as f:
+            f.write(json.dumps(stats) + "\n")
 
 
 class ScoringServer:
