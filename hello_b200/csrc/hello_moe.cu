@@ -50,6 +50,7 @@ struct Arena {
 }  // namespace
 
 constexpr size_t MAX_PROFILE_REGIONS = 4096;   // regions bracketed between two hello_moe_profile_collect calls
+constexpr long long SMALL_BATCH_READS = 4 * 148 * 9;   // up to four work items per SM: see the read-convolver stage
 
 struct hello_moe {
     hello_cfg cfg;
@@ -71,6 +72,7 @@ struct hello_moe {
     std::vector<LayerDesc> tail[N_NETS];
     bool profile = false;
     std::vector<cudaEvent_t> ev_pool;            // pairs (start, stop), created lazily, at most MAX_PROFILE_REGIONS pairs
+    bool small_call[2] = {false, false};         // this call scores at most SMALL_BATCH_READS reads of the technology
     size_t ev_used = 0;
 };
 
@@ -339,7 +341,13 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
         const size_t m2 = ar.mark();
         // the fused kernel sums the reads of every allele itself (no per-read maps in HBM); the per-layer path needs them
         const bool rc_tail = h->tc[t] && !h->tail[NET_RC0 + t].empty();
-        float* r_feat = (h->tc[t] && !rc_tail) ? nullptr : ar.allocf(nr * read_e);
+        // A handful of sites (the strict per-site call, a scoring-server batch): the fused allele sum makes a CTA own whole
+        // alleles, so a 30-read allele is four work items in a row on ONE SM while the others idle.  Below this many reads
+        // the kernel writes per-read maps instead (every CTA gets one item) and segsum_kernel adds them: the same additions
+        // in the same order (test_huge_allele_and_partition_invariance), a quarter of the latency.
+        const bool rc_small = h->tc[t] && !rc_tail && h->small_call[t];   // (per call, not per chunk: the chunk planner
+                                                                          // relies on bigger chunks needing more workspace)
+        float* r_feat = (h->tc[t] && !rc_tail && !rc_small) ? nullptr : ar.allocf(nr * read_e);
         float* r_pre = rc_tail ? ar.allocf(nr * read_e) : nullptr;      // fused original layers -> added layers
         if (ar.overflow) return run.fail(HELLO_ERR_WORKSPACE, "workspace overflow");
         // read convolver (architectures/read_convolver.py) on uint8 rows
@@ -366,6 +374,16 @@ bool forward_chunk(Runner& run, const Chunk& ck, const hello_batch* in, const he
                 if (!run.check(e, "readconv_tc")) return false;
             }
             if (!run.run_net(h->tail[NET_RC0 + t], view_cl(r_pre, h->read_len, h->read_ch), nr, r_feat, nullptr)) return false;
+            if (ev_stop && !run.check(cudaEventRecord(ev_stop, run.st), "cudaEventRecord")) return false;
+            if (!run.segsum(r_feat, a_feat, dry ? nullptr : in->d_allele_read_off[t] + ck.a0, na, (int)ck.r0[t], read_e))
+                return false;
+        } else if (rc_small) {
+            if (!dry && nr > 0) {
+                cudaError_t e = readconv_tc_launch(h->tc[t], reads, nr, in->input_layout, r_feat, run.st, nullptr, -1, nullptr,
+                                                   nullptr, 0, 0);
+                h->launches++;
+                if (!run.check(e, "readconv_tc")) return false;
+            }
             if (ev_stop && !run.check(cudaEventRecord(ev_stop, run.st), "cudaEventRecord")) return false;
             if (!run.segsum(r_feat, a_feat, dry ? nullptr : in->d_allele_read_off[t] + ck.a0, na, (int)ck.r0[t], read_e))
                 return false;
@@ -696,7 +714,10 @@ const char* hello_moe_last_error(const hello_moe* h) { return h ? h->err.c_str()
 size_t hello_moe_workspace_bytes(const hello_moe* h, int64_t n_reads0, int64_t n_reads1, int64_t n_alleles,
                                  int64_t n_sites) {
     if (!h) return 0;
-    return dry_bytes(const_cast<hello_moe*>(h), n_reads0, n_reads1, n_alleles, n_sites);
+    hello_moe* hm = const_cast<hello_moe*>(h);
+    hm->small_call[0] = n_reads0 <= SMALL_BATCH_READS;
+    hm->small_call[1] = n_reads1 <= SMALL_BATCH_READS;
+    return dry_bytes(hm, n_reads0, n_reads1, n_alleles, n_sites);
 }
 
 int hello_moe_profile_enable(hello_moe* h, int on) {
@@ -765,6 +786,9 @@ static int forward_impl(hello_moe* h, const hello_batch* in, const hello_result*
         for (long long al = in->h_site_allele_off[sb]; al < in->h_site_allele_off[se]; ++al)
             if (off[al + 1] <= off[al]) { h->err = "every allele needs at least one read row per technology"; return HELLO_ERR_ARG; }
     }
+    for (int t = 0; t < 2; ++t)
+        h->small_call[t] = t < cfg.n_tech && (long long)in->h_allele_read_off[t][in->h_site_allele_off[se]] -
+                                                 in->h_allele_read_off[t][in->h_site_allele_off[sb]] <= SMALL_BATCH_READS;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) { h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return HELLO_ERR_CUDA; }

@@ -117,12 +117,32 @@ def test_standard_models_run_on_the_fused_kernels(gpu):
               "hybrid_no_ensemble_addendum": 11}
     for name, n_launch in expect.items():
         cfg = arch.CONFIGS[name]
-        pl = synth.make_pileups(6, coverage=6, channels=cfg.read_cin, seed=2)
         eng = net_for(gpu, cfg, "bf16x3").engine
-        batch = gpu.DeviceBatch.from_pileups(pl, DEV)
-        before = eng.launch_count()
-        eng.run(batch)
-        assert eng.launch_count() - before == n_launch + 1, name     # + fill_meta_default (no meta network)
+        # a batch that fills the GPU: the read convolver sums the alleles itself; a handful of sites (fewer than four work
+        # items per SM): per-read maps + segsum_kernel, one more launch per technology (every SM gets an item instead of
+        # one SM walking a whole allele)
+        for n_sites, cov, extra in ((400, 20, 0), (6, 6, len(cfg.read_cin))):
+            pl = synth.make_pileups(n_sites, coverage=cov, channels=cfg.read_cin, seed=2)
+            assert (pl.reads[0].shape[0] > 4 * 148 * 9) == (extra == 0)
+            batch = gpu.DeviceBatch.from_pileups(pl, DEV)
+            before = eng.launch_count()
+            eng.run(batch)
+            assert eng.launch_count() - before == n_launch + 1 + extra, (name, n_sites)   # + fill_meta_default (no meta network)
+
+
+def test_small_and_large_batches_agree_bit_for_bit(gpu):
+    """The same sites scored alone (small-batch path: per-read maps + segsum) and inside a batch that fills the GPU (allele
+    sum fused into the read convolver) give bit-identical logits: both add an allele's reads in read order."""
+    cfg = arch.CONFIGS["single_tech"]
+    net = net_for(gpu, cfg, "bf16x3")
+    pl = synth.make_pileups(400, coverage=20, channels=cfg.read_cin, seed=8)
+    whole = net.forward(*pl.forward_args()).cpu().reshape(-1)
+    sao = pl.site_allele_off
+    a1 = int(sao[5])
+    r1 = int(pl.allele_read_off[0][a1])
+    sub = synth.Pileups((pl.reads[0][:r1],), (pl.allele_read_off[0][:a1 + 1],), sao[:6], pl.ref_onehot[:5])
+    part = net.forward(*sub.forward_args()).cpu().reshape(-1)
+    assert torch.equal(part, whole[:part.numel()])
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
