@@ -408,7 +408,8 @@ def pack_blob(cfg: arch.ModelConfig, params: Dict[str, torch.Tensor]) -> bytes:
       header: magic[8] u32 version u32 n_net_slots u64 rec_off u64 n_rec u64 data_off u64 n_floats
               u32 first_rec[10] u32 n_rec[10]
       record: kind, has_shortcut, conv_a[8], conv_b[8], conv_s[8], pad   with
-              conv = cin, cout, k, stride, pad, relu, w_off, b_off   (offsets in floats into the data section)
+              conv = cin, cout, k, stride, pad, activation, w_off, b_off   (activation: 0 none, 1 ReLU, 2 Softplus --
+                     arch.ACTIVATION_CODES; offsets in floats into the data section)
       conv weights are stored transposed [k*cin, cout] (row = tap*cin + ci) for channel-last activations;
       linear weights as [cout, cin].
     """
