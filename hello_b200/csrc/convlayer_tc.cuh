@@ -4,7 +4,8 @@
 // (architectures/*_wide.py), which do not fit the fused kernels' shared-memory layouts.  Replaces torch.nn.Conv1d called
 // through NNTools.WeightNormedConv1d (python/NNTools.py:791-799).
 //
-// Implicit GEMM without im2col, persistent (one CTA per SM walks (row tile, column tile) work items):
+// Implicit GEMM without im2col, persistent (two CTAs per SM -- one where a layer's accumulator needs more than half of
+// tensor memory -- walk (row tile, column tile) work items):
 //   * Rows.  The items (reads / alleles / sites) are laid back to back along M with a fixed PITCH of output rows; the
 //     pitch - lout surplus rows of an item are garbage outputs that are never stored.  A 128-row tile of that padded
 //     sequence needs the input rows of the same range (+ k - 1), so the tile's input is STAGED ONCE in shared memory in
@@ -26,6 +27,7 @@
 // Layer by layer through HBM (fp32 activations): these layers are bound by that traffic, not by the tensor pipe.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -65,6 +67,7 @@ struct ConvTcArgs {
     int pitch, sigma_min, n_arr, kc, n_chunks, max_delta;
     int tap_arr[MAX_TAPS], tap_delta[MAX_TAPS];
     long long* trace;        // developer timeline (tools/convlayer_trace.cu): CTA 0 stamps clock64() per tile and role; else nullptr
+    int acc_shift;           // log2 of the accumulators in tensor memory (1: two, tile i+1 fills one while tile i is read; 0: one)
 };
 
 // Timeline slots of one tile: producer {slot free, loads issued, operand stored}, issuer {accumulator free, operand
@@ -83,8 +86,15 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-template <int MODE>
-__global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_constant__ ConvTcArgs a) {
+// CPS = CTAs per SM.  2: half of tensor memory (256 columns, accumulators 128 columns apart), at most half of the shared
+// memory (the residual is read straight from HBM instead of through a staging tile) and 72 registers, so that two CTAs
+// share an SM: every warp role here is a few warps running dependent chains, and a second independent pipeline on the SM
+// fills the issue slots, the tensor pipe and the memory pipes the first one leaves idle.
+template <int MODE, int CPS>
+__global__ void __launch_bounds__(THREADS, CPS) convlayer_tc_kernel(const __grid_constant__ ConvTcArgs a) {
+    constexpr uint32_t TMEM_COLS = CPS == 2 ? 256u : 512u, ACC_STRIDE = CPS == 2 ? 128u : 256u;
+    constexpr int LOAD_BATCH = CPS == 2 ? 9 : 16;         // 128-bit loads a producer thread keeps in flight
+    constexpr bool RES_STAGED = CPS == 1;
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
@@ -96,8 +106,8 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
     uint8_t* s_a = smem;
     uint8_t* s_b = s_a + A_SLOTS * a_slot;
     uint8_t* s_out = s_b + B_STAGES * unit;                                   // epilogue staging: output rows, residual rows
-    uint8_t* s_res = s_out + 128 * STG_PITCH;
-    long long* s_tab = reinterpret_cast<long long*>(s_res + 128 * STG_PITCH);  // [2 groups][n_arr][ROWS_TAB] source offsets
+    uint8_t* s_res = s_out + 128 * STG_PITCH;                                // (absent with two CTAs per SM)
+    long long* s_tab = reinterpret_cast<long long*>(s_res + (RES_STAGED ? 128 * STG_PITCH : 0));  // [2 groups][n_arr][ROWS_TAB]
     const uint32_t bar0 = ptx::smem_u32(s_tab + 2 * 2 * ROWS_TAB);
     auto bar = [&](int k) { return bar0 + 8u * k; };
     constexpr int BAR_AFULL = 0, BAR_AEMPTY = A_SLOTS, BAR_BFULL = 2 * A_SLOTS, BAR_BEMPTY = BAR_BFULL + B_STAGES,
@@ -113,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
         ptx::fence_mbar_init();
     }
     if (warp == E_WARPS + P_WARPS) {
-        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(s_tmem)), 512);
+        ptx::tmem_alloc(ptx::smem_u32(const_cast<uint32_t*>(s_tmem)), TMEM_COLS);
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
             *n0 = (int)ntile * a.nt;
         };
         auto request_res = [&](uint32_t wk, int cb) {
-            if (!a.resid || wk >= n_work) return;
+            if (!RES_STAGED || !a.resid || wk >= n_work) return;
             bool ok; long long orow; int n0;
             row_of(wk, &ok, &orow, &n0);
             if (!ok) return;
@@ -160,14 +170,15 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
             bool row_ok; long long orow; int n0;
             row_of(wk, &row_ok, &orow, &n0);
             float* yrow = a.y + orow * a.cout + n0;
-            const uint32_t ab = it & 1u;
-            ptx::mbar_wait(bar(BAR_ACCFULL + ab), (it >> 1) & 1u);
+            const float* rrow = a.resid ? a.resid + orow * a.cout + n0 : nullptr;
+            const uint32_t ab = it & (uint32_t)a.acc_shift;
+            ptx::mbar_wait(bar(BAR_ACCFULL + ab), (it >> a.acc_shift) & 1u);
             ptx::tc_fence_after();
             if (r == 0) trace_stamp(a, it, 6);
-            const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16) + ab * 256u;
+            const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16) + ab * ACC_STRIDE;
             for (int cb = 0; cb < n_cb; ++cb) {
                 if (row_ok) bulk_wait_read();                                // the previous piece has left the output line
-                if (a.resid && row_ok) { ptx::mbar_wait(my_bar, res_n & 1u); ++res_n; }
+                if (RES_STAGED && a.resid && row_ok) { ptx::mbar_wait(my_bar, res_n & 1u); ++res_n; }
                 __syncwarp();
                 for (int cc = 0; cc < cb_cols; cc += 16) {
                     const int c0 = cb * EPI_COLS + cc;
@@ -191,7 +202,8 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
                             else if (a.relu) { o.x = apply_activation(o.x, a.relu); o.y = apply_activation(o.y, a.relu);
                                                o.z = apply_activation(o.z, a.relu); o.w = apply_activation(o.w, a.relu); }
                             if (a.resid) {
-                                const float4 t = *reinterpret_cast<const float4*>(my_res + (cc + 4 * q) * 4);
+                                const float4 t = RES_STAGED ? *reinterpret_cast<const float4*>(my_res + (cc + 4 * q) * 4)
+                                                            : __ldg(reinterpret_cast<const float4*>(rrow + c0) + q);
                                 o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
                             }
                             *reinterpret_cast<float4*>(my_out + (cc + 4 * q) * 4) = o;
@@ -226,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
                 if (tab_mt != mt) {
                     // where every staged row of this row tile comes from (element offset into x, -1 = a row of zeros)
                     tab_mt = mt;
-                    ptx::named_bar_sync(1 + pg, P_GROUP);                    // the previous tile's table is no longer read
+                    if (pg == 0) ptx::named_bar_sync(1, P_GROUP); else ptx::named_bar_sync(2, P_GROUP);                    // the previous tile's table is no longer read
                     for (int i = r; i < a.n_arr * ROWS_TAB; i += P_GROUP) {
                         const int arr = i >= ROWS_TAB ? 1 : 0, rr = i - arr * ROWS_TAB;
                         const uint32_t g = mt * 128u + (uint32_t)rr;
@@ -235,17 +247,17 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
                         const bool ok = rr < 128 + a.max_delta && item < a.n_items && q >= 0 && q < a.lin;
                         tab[i] = ok ? (long long)item * a.sn + (long long)q * a.sl : -1ll;
                     }
-                    ptx::named_bar_sync(1 + pg, P_GROUP);
+                    if (pg == 0) ptx::named_bar_sync(1, P_GROUP); else ptx::named_bar_sync(2, P_GROUP);
                 }
                 const uint32_t slot = chunk_n % A_SLOTS;
                 ptx::mbar_wait(bar(BAR_AEMPTY + slot), ((chunk_n / A_SLOTS) & 1u) ^ 1u);
                 if (r == 0 && ch == 0) trace_stamp(a, chunk_n / (uint32_t)a.n_chunks, 0);
                 uint8_t* buf = s_a + slot * a_slot;
                 const float* xc = a.x + ch * a.kc;
-                for (int base = 0; base < n_f4; base += P_GROUP * 16) {
-                    float4 v[16];
+                for (int base = 0; base < n_f4; base += P_GROUP * LOAD_BATCH) {
+                    float4 v[LOAD_BATCH];
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {                           // all loads in flight before the first conversion
+                    for (int u = 0; u < LOAD_BATCH; ++u) {                   // all loads in flight before the first conversion
                         const int i = base + u * P_GROUP + r;
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (i < n_f4) {
@@ -255,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
                     }
                     if (r == 0 && ch == 0 && base == 0) trace_stamp(a, chunk_n / (uint32_t)a.n_chunks, 1);
 #pragma unroll
-                    for (int u = 0; u < 16; ++u) {
+                    for (int u = 0; u < LOAD_BATCH; ++u) {
                         const int i = base + u * P_GROUP + r;
                         if (i < n_f4) {
                             const int row = i >> f4_shift, c4 = i & ((1 << f4_shift) - 1);
@@ -283,11 +295,11 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
         const uint32_t b_lbo = (MODE == 3 && a.stacked ? 2u : 1u) * (uint32_t)a.nt * 16u;
         uint32_t chunk_n = 0, unit_n = 0, it = 0;
         for (uint32_t wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it) {
-            const uint32_t ab = it & 1u;
-            ptx::mbar_wait(bar(BAR_ACCEMPTY + ab), ((it >> 1) & 1u) ^ 1u);   // the epilogue has read this accumulator
+            const uint32_t ab = it & (uint32_t)a.acc_shift;
+            ptx::mbar_wait(bar(BAR_ACCEMPTY + ab), ((it >> a.acc_shift) & 1u) ^ 1u);   // the epilogue has read this accumulator
             ptx::tc_fence_after();
             if (lane == 0) trace_stamp(a, it, 3);
-            const uint32_t d = tmem + ab * 256u;
+            const uint32_t d = tmem + ab * ACC_STRIDE;
             uint32_t first = 1u;
             for (int ch = 0; ch < a.n_chunks; ++ch, ++chunk_n) {
                 const uint32_t slot = chunk_n % A_SLOTS;
@@ -346,12 +358,13 @@ __global__ void __launch_bounds__(THREADS, 1) convlayer_tc_kernel(const __grid_c
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == E_WARPS + P_WARPS) ptx::tmem_dealloc(tmem, 512);
+    if (warp == E_WARPS + P_WARPS) ptx::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // How a layer maps onto the kernel: chunking of K, tap -> (input array, row shift), pitch of an item's output rows.
 struct Geometry {
     int nt, stacked, kc, n_arr, stride, sigma_min, max_delta;
+    int cps, acc_shift;                                  // CTAs per SM the layer runs with; log2(accumulators in tensor memory)
     int tap_arr[MAX_TAPS], tap_delta[MAX_TAPS];
     int pitch(int lin, int lout) const {
         // rows [0, pitch) of an item are its own; a tap reaching row `pitch + j` reads row j of the next item, which is
@@ -367,10 +380,22 @@ struct Geometry {
     }
 };
 
-inline bool geometry(const ConvDesc& c, int mode, Geometry* g) {
+inline size_t smem_bytes(int mode, const Geometry& g) {
+    const size_t parts = mode == 3 ? 2 : 1;
+    const size_t a_slot = parts * g.n_arr * (g.kc / 8) * ARR, unit = parts * 32u * g.nt;
+    return A_SLOTS * a_slot + B_STAGES * unit + (g.cps == 2 ? 1 : 2) * 128 * STG_PITCH + 2 * 2 * ROWS_TAB * 8 +
+           (2 * A_SLOTS + 2 * B_STAGES + 4 + E_WARPS * 32) * 8 + 16;
+}
+
+// cps = 2: the layer as two CTAs per SM (half the tensor memory, K chunks of 32 channels, no residual staging), when its
+// accumulator fits 256 columns and the CTA fits half an SM's shared memory
+inline bool geometry(const ConvDesc& c, int mode, Geometry* g, int cps = 1) {
     if (c.k > MAX_TAPS || c.stride < 1 || c.stride > 2 || c.pad < 0) return false;
+    g->cps = cps;
     g->nt = c.cout <= 256 ? c.cout : 256;
-    g->stacked = mode == 3 && g->nt <= 128;
+    g->stacked = mode == 3 && g->nt <= (cps == 2 ? 64 : 128);
+    const int acc_cols = g->stacked ? 2 * g->nt : g->nt, acc_stride = cps == 2 ? 128 : 256;
+    g->acc_shift = acc_cols <= acc_stride ? 1 : 0;
     g->stride = c.stride;
     auto fdiv = [](int x, int s) { return x >= 0 ? x / s : -((-x + s - 1) / s); };
     int smin = 1 << 30, smax = -(1 << 30);
@@ -386,8 +411,9 @@ inline bool geometry(const ConvDesc& c, int mode, Geometry* g) {
         g->tap_delta[t] = s - smin;
         g->n_arr = std::max(g->n_arr, g->tap_arr[t] + 1);
     }
-    g->kc = std::min(c.cin, 64 / g->n_arr);
-    return c.cin % g->kc == 0 && g->kc % 16 == 0;
+    g->kc = std::min(c.cin, (cps == 2 ? 32 : 64) / g->n_arr);
+    if (c.cin % g->kc || g->kc % 16) return false;
+    return cps == 1 || smem_bytes(mode, *g) <= 113 * 1024;
 }
 
 struct PackedConv {
@@ -410,12 +436,13 @@ struct ConvLayerTC {
     int mode = 3;
     int sm_count = 148;
     long long* d_trace = nullptr;          // developer timeline buffer (tools/convlayer_trace.cu), nullptr in the library
+    int cps = 2;                           // CTAs per SM asked for (2 wherever a layer's geometry allows it)
 };
 
 static bool convlayer_tc_add(ConvLayerTC* t, const ConvDesc& c, const float* d_base, const float* h_base, std::string& err) {
     if (!cl::eligible(c) || t->layers.count(c.w)) return true;
     cl::PackedConv p;
-    if (!cl::geometry(c, t->mode, &p.g)) return true;
+    if (!(t->cps == 2 && cl::geometry(c, t->mode, &p.g, 2)) && !cl::geometry(c, t->mode, &p.g, 1)) return true;
     const int parts = t->mode == 3 ? 2 : 1;
     const float* w = h_base + (c.w - d_base);                       // [k*cin][cout]
     const int nt = p.g.nt, kc = p.g.kc;
@@ -453,22 +480,19 @@ static bool convlayer_tc_add(ConvLayerTC* t, const ConvDesc& c, const float* d_b
     return true;
 }
 
-static size_t convlayer_tc_smem(int mode, const cl::Geometry& g) {
-    const size_t parts = mode == 3 ? 2 : 1;
-    const size_t a_slot = parts * g.n_arr * (g.kc / 8) * cl::ARR, unit = parts * 32u * g.nt;
-    return cl::A_SLOTS * a_slot + cl::B_STAGES * unit + 2 * 128 * cl::STG_PITCH + 2 * 2 * cl::ROWS_TAB * 8 +
-           (2 * cl::A_SLOTS + 2 * cl::B_STAGES + 4 + cl::E_WARPS * 32) * 8 + 16;
-}
+static size_t convlayer_tc_smem(int mode, const cl::Geometry& g) { return cl::smem_bytes(mode, g); }
 
 static ConvLayerTC* convlayer_tc_create(int precision, std::string& err) {
     ConvLayerTC* t = new ConvLayerTC();
     t->mode = precision == HELLO_PREC_BF16X3 ? 3 : 1;
-    cl::Geometry worst;
-    worst.nt = 256; worst.n_arr = 1; worst.kc = 64;
-    const int smem = (int)std::max(convlayer_tc_smem(t->mode, worst), cl::MIN_SMEM);
-    cudaError_t e = t->mode == 3
-        ? cudaFuncSetAttribute(cl::convlayer_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-        : cudaFuncSetAttribute(cl::convlayer_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = 227 * 1024;             // opt in to everything; a launch asks for what its geometry needs
+    cudaError_t e = cudaSuccess;
+    auto opt_in = [&](const void* fn) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    };
+    if (t->mode == 3) { opt_in((const void*)cl::convlayer_tc_kernel<3, 1>); opt_in((const void*)cl::convlayer_tc_kernel<3, 2>); }
+    else { opt_in((const void*)cl::convlayer_tc_kernel<1, 1>); opt_in((const void*)cl::convlayer_tc_kernel<1, 2>); }
+    if (const char* env = std::getenv("HELLO_CL_CPS")) t->cps = std::atoi(env) == 1 ? 1 : 2;      // developer A/B switch
     cudaDeviceProp prop;
     int dev = 0;
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
@@ -505,10 +529,17 @@ static bool convlayer_tc_launch(ConvLayerTC* t, const ActView& x, const ConvDesc
     a.m_tiles = (uint32_t)((total + 127) / 128); a.n_tiles = (uint32_t)(c.cout / g.nt);
     const long long work = (long long)a.m_tiles * a.n_tiles;
     if (work >= 0x7fffffffLL) return false;
-    const unsigned grid = (unsigned)std::min<long long>(work, t->sm_count);
-    const size_t smem = std::max(convlayer_tc_smem(t->mode, g), cl::MIN_SMEM);
-    if (t->mode == 3) cl::convlayer_tc_kernel<3><<<grid, cl::THREADS, smem, st>>>(a);
-    else cl::convlayer_tc_kernel<1><<<grid, cl::THREADS, smem, st>>>(a);
+    a.acc_shift = g.acc_shift;
+    const unsigned grid = (unsigned)std::min<long long>(work, (long long)t->sm_count * g.cps);
+    // one CTA per SM takes all of tensor memory: ask for more than half an SM's shared memory so that two never share one
+    const size_t smem = g.cps == 2 ? convlayer_tc_smem(t->mode, g) : std::max(convlayer_tc_smem(t->mode, g), cl::MIN_SMEM);
+    if (t->mode == 3) {
+        if (g.cps == 2) cl::convlayer_tc_kernel<3, 2><<<grid, cl::THREADS, smem, st>>>(a);
+        else cl::convlayer_tc_kernel<3, 1><<<grid, cl::THREADS, smem, st>>>(a);
+    } else {
+        if (g.cps == 2) cl::convlayer_tc_kernel<1, 2><<<grid, cl::THREADS, smem, st>>>(a);
+        else cl::convlayer_tc_kernel<1, 1><<<grid, cl::THREADS, smem, st>>>(a);
+    }
     *e = cudaGetLastError();
     return true;
 }
