@@ -68,6 +68,7 @@ struct ConvTcArgs {
     int tap_arr[MAX_TAPS], tap_delta[MAX_TAPS];
     long long* trace;        // developer timeline (tools/convlayer_trace.cu): CTA 0 stamps clock64() per tile and role; else nullptr
     int acc_shift;           // log2 of the accumulators in tensor memory (1: two, tile i+1 fills one while tile i is read; 0: one)
+    int res_ring;            // two CTAs per SM: the residual comes through a two-slot ring of 16-column pieces per row
 };
 
 // Timeline slots of one tile: producer {slot free, loads issued, operand stored}, issuer {accumulator free, operand
@@ -85,6 +86,13 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// 16-byte asynchronous copy global -> shared (LDGSTS, past L1), in the issuing thread's own groups
+__device__ __forceinline__ void ldgsts16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldgsts_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ldgsts_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+constexpr uint32_t RING_PITCH = 2 * 64 + 16;              // residual ring of one row: two 16-column slots, 16-byte skew per row
 
 // CPS = CTAs per SM.  2: half of tensor memory (256 columns, accumulators 128 columns apart), at most half of the shared
 // memory (the residual is read straight from HBM instead of through a staging tile) and 72 registers, so that two CTAs
@@ -107,7 +115,8 @@ __global__ void __launch_bounds__(THREADS, CPS) convlayer_tc_kernel(const __grid
     uint8_t* s_b = s_a + A_SLOTS * a_slot;
     uint8_t* s_out = s_b + B_STAGES * unit;                                   // epilogue staging: output rows, residual rows
     uint8_t* s_res = s_out + 128 * STG_PITCH;                                // (absent with two CTAs per SM)
-    long long* s_tab = reinterpret_cast<long long*>(s_res + (RES_STAGED ? 128 * STG_PITCH : 0));  // [2 groups][n_arr][ROWS_TAB]
+    long long* s_tab = reinterpret_cast<long long*>(                          // [2 groups][n_arr][ROWS_TAB]
+        s_res + (RES_STAGED ? 128 * STG_PITCH : a.res_ring ? 128 * RING_PITCH : 0));
     const uint32_t bar0 = ptx::smem_u32(s_tab + 2 * 2 * ROWS_TAB);
     auto bar = [&](int k) { return bar0 + 8u * k; };
     constexpr int BAR_AFULL = 0, BAR_AEMPTY = A_SLOTS, BAR_BFULL = 2 * A_SLOTS, BAR_BEMPTY = BAR_BFULL + B_STAGES,
@@ -165,6 +174,37 @@ __global__ void __launch_bounds__(THREADS, CPS) convlayer_tc_kernel(const __grid
             ptx::bulk_g2s(ptx::smem_u32(my_res), a.resid + orow * a.cout + n0 + cb * EPI_COLS, cb_bytes, my_bar);
         };
         request_res(blockIdx.x, 0);
+        // Two CTAs per SM have no room for a residual tile.  Where a ring of two 16-column pieces per row fits, the residual
+        // comes through it two pieces ahead of the arithmetic: 16-byte asynchronous copies, four lanes along the 64 bytes of
+        // a row so that a warp instruction fetches whole sectors of eight rows (a thread fetching its own row would touch 32
+        // rows and use half of every sector), one group per piece, empty past the end so that "all but the newest group"
+        // always means "this piece has landed"; a warp barrier either side of the reads, since the lines a thread reads were
+        // filled by other lanes of its warp.  Else the residual is read where it is used.
+        const bool ring = !RES_STAGED && a.res_ring;
+        const uint32_t my_ring = ptx::smem_u32(s_res + (uint32_t)r * RING_PITCH);
+        const uint32_t warp_ring = ptx::smem_u32(s_res + (uint32_t)(warp * 32) * RING_PITCH);
+        const int n_j = a.nt / 16;
+        uint32_t rq_wk = blockIdx.x, rq_n = 0, rd_n = 0;
+        int rq_j = 0;
+        auto ring_request = [&]() {
+            if (rq_wk < n_work) {
+                bool ok; long long orow; int n0;
+                row_of(rq_wk, &ok, &orow, &n0);
+                const float* src = a.resid + n0 + rq_j * 16 + (lane & 3) * 4;
+                const uint32_t dst = warp_ring + (rq_n & 1u) * 64u + (uint32_t)(lane & 3) * 16u;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                                // rows 8q .. 8q+7 of this warp's 32
+                    const int row = 8 * q + (lane >> 2);
+                    const bool rok = __shfl_sync(0xffffffffu, (int)ok, row);
+                    const long long rrow = __shfl_sync(0xffffffffu, orow, row);
+                    if (rok) ldgsts16(dst + (uint32_t)row * RING_PITCH, src + rrow * a.cout);
+                }
+                if (++rq_j == n_j) { rq_j = 0; rq_wk += gridDim.x; }
+            }
+            ldgsts_commit();
+            ++rq_n;
+        };
+        if (ring) { ring_request(); ring_request(); }
         uint32_t it = 0;
         for (uint32_t wk = blockIdx.x; wk < n_work; wk += gridDim.x, ++it) {
             bool row_ok; long long orow; int n0;
@@ -193,6 +233,7 @@ __global__ void __launch_bounds__(THREADS, CPS) convlayer_tc_kernel(const __grid
                     } else {
                         ptx::tmem_wait_ld();
                     }
+                    if (ring) { ldgsts_wait_but_one(); __syncwarp(); }
                     if (row_ok) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -202,13 +243,18 @@ __global__ void __launch_bounds__(THREADS, CPS) convlayer_tc_kernel(const __grid
                             else if (a.relu) { o.x = apply_activation(o.x, a.relu); o.y = apply_activation(o.y, a.relu);
                                                o.z = apply_activation(o.z, a.relu); o.w = apply_activation(o.w, a.relu); }
                             if (a.resid) {
-                                const float4 t = RES_STAGED ? *reinterpret_cast<const float4*>(my_res + (cc + 4 * q) * 4)
-                                                            : __ldg(reinterpret_cast<const float4*>(rrow + c0) + q);
+                                float4 t;
+                                if (RES_STAGED) t = *reinterpret_cast<const float4*>(my_res + (cc + 4 * q) * 4);
+                                else if (ring) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                                            : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                                            : "r"(my_ring + (rd_n & 1u) * 64u + 16u * q) : "memory");
+                                else t = __ldg(reinterpret_cast<const float4*>(rrow + c0) + q);
                                 o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
                             }
                             *reinterpret_cast<float4*>(my_out + (cc + 4 * q) * 4) = o;
                         }
                     }
+                    if (ring) { __syncwarp(); ring_request(); ++rd_n; }      // this piece's slot is free: fetch the piece after next
                 }
                 ptx::fence_proxy_async();        // this thread's staging reads / writes are ordered before the bulk copies below
                 // the residual line is free: fetch the piece of the next (tile, block)
@@ -380,6 +426,9 @@ struct Geometry {
     }
 };
 
+// a two-CTA layer with a residual: room for the ring?
+inline size_t ring_bytes() { return 128 * RING_PITCH; }
+constexpr size_t HALF_SM_SMEM = 113 * 1024;
 inline size_t smem_bytes(int mode, const Geometry& g) {
     const size_t parts = mode == 3 ? 2 : 1;
     const size_t a_slot = parts * g.n_arr * (g.kc / 8) * ARR, unit = parts * 32u * g.nt;
@@ -413,7 +462,7 @@ inline bool geometry(const ConvDesc& c, int mode, Geometry* g, int cps = 1) {
     }
     g->kc = std::min(c.cin, (cps == 2 ? 32 : 64) / g->n_arr);
     if (c.cin % g->kc || g->kc % 16) return false;
-    return cps == 1 || smem_bytes(mode, *g) <= 113 * 1024;
+    return cps == 1 || smem_bytes(mode, *g) <= HALF_SM_SMEM;
 }
 
 struct PackedConv {
@@ -530,9 +579,11 @@ static bool convlayer_tc_launch(ConvLayerTC* t, const ActView& x, const ConvDesc
     const long long work = (long long)a.m_tiles * a.n_tiles;
     if (work >= 0x7fffffffLL) return false;
     a.acc_shift = g.acc_shift;
+    a.res_ring = g.cps == 2 && resid && convlayer_tc_smem(t->mode, g) + cl::ring_bytes() <= cl::HALF_SM_SMEM;
     const unsigned grid = (unsigned)std::min<long long>(work, (long long)t->sm_count * g.cps);
     // one CTA per SM takes all of tensor memory: ask for more than half an SM's shared memory so that two never share one
-    const size_t smem = g.cps == 2 ? convlayer_tc_smem(t->mode, g) : std::max(convlayer_tc_smem(t->mode, g), cl::MIN_SMEM);
+    const size_t smem = g.cps == 2 ? convlayer_tc_smem(t->mode, g) + (a.res_ring ? cl::ring_bytes() : 0)
+                                   : std::max(convlayer_tc_smem(t->mode, g), cl::MIN_SMEM);
     if (t->mode == 3) {
         if (g.cps == 2) cl::convlayer_tc_kernel<3, 2><<<grid, cl::THREADS, smem, st>>>(a);
         else cl::convlayer_tc_kernel<3, 1><<<grid, cl::THREADS, smem, st>>>(a);
