@@ -36,7 +36,7 @@ WORKLOADS = {
     "hybrid_no_ensemble_wide_30x": ("hybrid_no_ensemble_wide", 30, "hybrid no_ensemble model with 2x channels (layer-wise tensor-core kernels)"),
     "hybrid_no_ensemble_addendum_30x": ("hybrid_no_ensemble_addendum", 30, "hybrid transfer-learning model"),
     "illumina_30x_addendum": ("single_tech_addendum", 30, "Illumina 30x transfer-learning model (two more residual blocks per sub-network)"),
-    "illumina_30x_softplus": ("single_tech_softplus", 30, "Illumina 30x model of the Softplus configuration (layer-wise kernels)"),
+    "illumina_30x_softplus": ("single_tech_softplus", 30, "Illumina 30x model of the Softplus configuration (fused kernels with a Softplus epilogue)"),
 }
 
 

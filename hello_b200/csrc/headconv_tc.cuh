@@ -145,7 +145,7 @@ __device__ __forceinline__ void load_input(uint8_t* act, const HeadParams& prm, 
 
 // Epilogue of one convolution for one group.  Thread = TMEM lane = packed row; this warp owns columns
 // [chalf*N/CS, (chalf+1)*N/CS).   y = relu(acc + bias) [+ resid (+ bias2)], invalid rows forced to zero.
-template <int MODE, int C, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID, int OUT>
+template <int MODE, int C, int ACT, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID, int OUT>
 __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, int bias, int bias2, int n,
                                          uint32_t out_stride, uint32_t out_lo, const HeadParams& prm, long long i0,
                                          float* __restrict__ dbg, int wrow, int lane, int chalf, float* part) {
@@ -168,7 +168,8 @@ __device__ __forceinline__ void epi_conv(uint8_t* act, uint32_t tl, int bias, in
             ptx::tmem_wait_ld();
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
-                float x = fmaxf(v[c] + prm.bias_tab[bias + c0 + c], 0.f);
+                float x = v[c] + prm.bias_tab[bias + c0 + c];
+                x = ACT == ACT_RELU ? fmaxf(x, 0.f) : softplus_fast(x);
                 if (RESID) x += RES_BIAS ? (r[c] + prm.bias_tab[bias2 + c0 + c]) : r[c];
                 v[c] = valid ? x : 0.f;
             }
@@ -304,7 +305,7 @@ __device__ __forceinline__ long long* head_trace_slot(const HeadParams& prm, int
     return reinterpret_cast<long long*>(prm.dbg) + ((long long)(li * ngrp + g) * TRACE_SLOTS) * 4;
 }
 
-template <int MODE, int C, bool DBG>
+template <int MODE, int C, bool DBG, int ACT = ACT_RELU>
 __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const __grid_constant__ HeadParams prm) {
     using Gm = Geo<C>;
     constexpr int NGRP = Gm::NGRP, CS = Gm::CS, G = Gm::G;
@@ -367,24 +368,24 @@ __global__ void __launch_bounds__(Geo<C>::THREADS, 1) headconv_tc_kernel(const _
                 float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph)
                                  ? prm.dbg + ((long long)item * NGRP + g) * (DBG_ROWS * DBG_COLS) : nullptr;
                 if (ph == 0) {
-                    epi_conv<MODE, C, C, 2, Gm::P1, Gm::L, false, false, false, OUT_EO>(
+                    epi_conv<MODE, C, ACT, C, 2, Gm::P1, Gm::L, false, false, false, OUT_EO>(
                         act, tl, Gm::B_0, 0, n, Gm::E_ARR, Gm::E_LO, prm, i0, dbg, wrow, lane, chalf, part);
                 } else if (ph == 1) {
-                    epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, false, false, false, OUT_NAT>(
+                    epi_conv<MODE, C, ACT, 2 * C, 1, Gm::P2, Gm::L2, false, false, false, OUT_NAT>(
                         act, tl, Gm::B_1A, 0, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
                 } else if (ph == 2) {
-                    epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, true, true, OUT_NAT>(
+                    epi_conv<MODE, C, ACT, 2 * C, 1, Gm::P2, Gm::L2, true, true, true, OUT_NAT>(
                         act, tl, Gm::B_1B, Gm::B_1S, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
                 } else {
                     const int b = Gm::B_REST + (ph - 3) * 2 * C;
                     if ((ph - 3) % 2 == 0)                  // conv a of a residual block
-                        epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, false, false, false, OUT_NAT>(
+                        epi_conv<MODE, C, ACT, 2 * C, 1, Gm::P2, Gm::L2, false, false, false, OUT_NAT>(
                             act, tl, b, 0, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
                     else if (ph + 1 < n_ph)                 // conv b + residual, feeds the next block
-                        epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, false, true, OUT_NAT>(
+                        epi_conv<MODE, C, ACT, 2 * C, 1, Gm::P2, Gm::L2, true, false, true, OUT_NAT>(
                             act, tl, b, 0, n, Gm::S_ARR, Gm::S_LO, prm, i0, dbg, wrow, lane, chalf, part);
                     else                                    // last block: output / pooled linear head
-                        epi_conv<MODE, C, 2 * C, 1, Gm::P2, Gm::L2, true, false, false, OUT_FINAL>(
+                        epi_conv<MODE, C, ACT, 2 * C, 1, Gm::P2, Gm::L2, true, false, false, OUT_FINAL>(
                             act, tl, b, 0, n, 0, 0, prm, i0, dbg, wrow, lane, chalf, part);
                 }
                 if (tr && tid == 0) tr[ph * 4 + 3] = clock64();
@@ -503,6 +504,7 @@ struct HeadConvTC {
     uint8_t* d_weights = nullptr;
     float* d_bias = nullptr;       // the pooled linear head (weights, bias)
     int mode = 3, C = 0, sm_count = 148;
+    int act = ACT_RELU;            // the one activation of every convolution (Softplus: the [18, 128] expert head only)
     int in_len = 0, out_len = 0, out_ch = 0;
 };
 
@@ -519,12 +521,15 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_
     if (!((C == 64 && in_len == 36) || (C == 128 && in_len == 18))) {
         err = "head network needs [36, 64] or [18, 128] inputs"; return nullptr;
     }
+    // ReLU, or Softplus for the expert head of moe_attention_config_single_tech_old_equivalent_layer_norm.py
+    const int act = net[0].a.relu;
+    if (act != ACT_RELU && !(act == ACT_SOFTPLUS && C == 128)) { err = "head network needs ReLU (or Softplus at 128 channels)"; return nullptr; }
     auto is_res = [&](const LayerDesc& L, int cin, int cout, int s, bool sc) {
         return L.kind == KIND_RES && L.a.cin == cin && L.a.cout == cout && L.a.k == 3 && L.a.stride == s && L.a.pad == 1 &&
-               L.a.relu == ACT_RELU && L.b.relu == ACT_RELU && L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&
+               L.a.relu == act && L.b.relu == act && L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&
                (L.has_shortcut != 0) == sc && (!sc || (L.s.cin == cin && L.s.cout == cout && L.s.k == 1 && L.s.stride == s && L.s.pad == 0));
     };
-    bool ok = net[0].a.cout == C && net[0].a.k == 1 && net[0].a.stride == 1 && net[0].a.pad == 0 && net[0].a.relu == ACT_RELU &&
+    bool ok = net[0].a.cout == C && net[0].a.k == 1 && net[0].a.stride == 1 && net[0].a.pad == 0 &&
               is_res(net[1], C, 2 * C, 2, true) && is_res(net[2], 2 * C, 2 * C, 1, false) && is_res(net[3], 2 * C, 2 * C, 1, false);
     int extra = 0;
     while (ok && extra < MAX_EXTRA_BLOCKS && (size_t)(4 + extra) < net.size() && is_res(net[4 + extra], 2 * C, 2 * C, 1, false)) ++extra;
@@ -542,6 +547,7 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_
     HeadConvTC* t = new HeadConvTC();
     t->mode = parts == 2 ? 3 : 1;
     t->C = C;
+    t->act = act;
     t->in_len = C == 64 ? 36 : 18;
     t->out_len = t->in_len / 2;
     t->out_ch = 2 * C;
@@ -614,6 +620,8 @@ static HeadConvTC* headconv_tc_create(const std::vector<LayerDesc>& net, int in_
     } else {
         if (t->mode == 3) { opt_in((const void*)headconv_tc_kernel<3, 128, false>); opt_in((const void*)headconv_tc_kernel<3, 128, true>); }
         else { opt_in((const void*)headconv_tc_kernel<1, 128, false>); opt_in((const void*)headconv_tc_kernel<1, 128, true>); }
+        if (t->mode == 3) opt_in((const void*)headconv_tc_kernel<3, 128, false, ACT_SOFTPLUS>);
+        else opt_in((const void*)headconv_tc_kernel<1, 128, false, ACT_SOFTPLUS>);
     }
     if (e != cudaSuccess) {
         err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
@@ -647,7 +655,12 @@ static cudaError_t headconv_tc_launch(HeadConvTC* t, const float* in_a, const fl
         if (debug) hc::headconv_tc_kernel<M, CC, true><<<grid, hc::Geo<CC>::THREADS, hc::Geo<CC>::SMEM_BYTES, st>>>(prm); \
         else hc::headconv_tc_kernel<M, CC, false><<<grid, hc::Geo<CC>::THREADS, hc::Geo<CC>::SMEM_BYTES, st>>>(prm); \
     } while (0)
-    if (t->C == 64) {
+    if (t->act == ACT_SOFTPLUS) {                      // 128 channels, no layer dump (the test hook exists for ReLU only)
+        using Gs = hc::Geo<128>;
+        if (debug) return cudaErrorNotSupported;
+        if (t->mode == 3) hc::headconv_tc_kernel<3, 128, false, ACT_SOFTPLUS><<<grid, Gs::THREADS, Gs::SMEM_BYTES, st>>>(prm);
+        else hc::headconv_tc_kernel<1, 128, false, ACT_SOFTPLUS><<<grid, Gs::THREADS, Gs::SMEM_BYTES, st>>>(prm);
+    } else if (t->C == 64) {
         if (t->mode == 3) HELLO_HEAD_LAUNCH(3, 64); else HELLO_HEAD_LAUNCH(1, 64);
     } else {
         if (t->mode == 3) HELLO_HEAD_LAUNCH(3, 128); else HELLO_HEAD_LAUNCH(1, 128);

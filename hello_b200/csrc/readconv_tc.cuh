@@ -239,7 +239,7 @@ __device__ __forceinline__ void store_rows(uint8_t* act, const uint32_t (&raw)[I
 //   accumulator columns are [hl even | hh even | hh odd | hl odd] (bf16x3) or [even | odd] (bf16), see issue_stage2_s2d;
 //   LVALID counts rows of the even positions, the odd ones have one fewer.
 //   OUT_Q4 (stem conv 2): output rows de-interleaved mod 4 into (chunk, position & 3) arrays of pitch P3.
-template <int MODE, bool STACK, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID,
+template <int MODE, int ACT, bool STACK, int N, int TILES, int PITCH, int LVALID, bool RESID, bool RES_BIAS, bool WRITE_RESID,
           bool MOVE_SC, int OUT, int LEAD, bool S2D = false>
 __device__ __forceinline__ void epi_conv(const TcParams& prm, uint8_t* act, uint32_t tl, int bias, int bias2, int n_reads,
                                          uint32_t out_stride, uint32_t out_lo, float* __restrict__ gout,
@@ -279,7 +279,8 @@ __device__ __forceinline__ void epi_conv(const TcParams& prm, uint8_t* act, uint
             float y0 = x[c], y1 = x[c + 1];
             if (TWO) ptx::add2(y0, y1, w[c], w[c + 1]);
             ptx::add2(y0, y1, prm.bias_tab[bias + c0 + c], prm.bias_tab[bias + c0 + c + 1]);
-            y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f);
+            if (ACT == ACT_RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+            else { y0 = softplus_fast(y0); y1 = softplus_fast(y1); }
             if (RESID) {
                 float r0 = REG ? rr[RO + c] : r[c], r1 = REG ? rr[RO + c + 1] : r[c + 1];
                 if (RES_BIAS) ptx::add2(r0, r1, prm.bias_tab[bias2 + c0 + c], prm.bias_tab[bias2 + c0 + c + 1]);
@@ -415,7 +416,7 @@ __device__ __forceinline__ void accumulate_out(uint8_t* smem, const uint8_t* act
 // operand products); pooled[2r] = max(a0, a1, a2), pooled[2r+1] = max(a2, a3, a0 of row r+1) -- the latter comes from the
 // neighbouring lane (shared-memory exchange across warp borders).  Starts the residual stream: the even position's 32
 // channels -> registers, the odd position's -> TMEM (blocks 0,1 / 2,3 of epi_conv<S2D>).
-template <int MODE>
+template <int MODE, int ACT>
 __device__ __forceinline__ void epi_pool(const TcParams& prm, uint8_t* act, uint32_t tl, int bias, int n_reads, int g, int wq,
                                          int lane, float* __restrict__ dbg, float (&rr)[32]) {
     float* xchg = reinterpret_cast<float*>(act + XCHG_OFF);
@@ -460,8 +461,10 @@ __device__ __forceinline__ void epi_pool(const TcParams& prm, uint8_t* act, uint
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
                 const float bb = prm.bias_tab[bias + hb * 16 + c];
-                const float e = fmaxf(fmaxf(ev[c], a2[c]) + bb, 0.f);
-                const float o = fmaxf(fmaxf(fmaxf(a2[c], a3[c]), ov[c]) + bb, 0.f);
+                // the activation is monotone, so it commutes with the max: one evaluation per pooled value
+                const float em = fmaxf(ev[c], a2[c]) + bb, om = fmaxf(fmaxf(a2[c], a3[c]), ov[c]) + bb;
+                const float e = ACT == ACT_RELU ? fmaxf(em, 0.f) : softplus_fast(em);
+                const float o = ACT == ACT_RELU ? fmaxf(om, 0.f) : softplus_fast(om);
                 ev[c] = valid_e ? e : 0.f;
                 ov[c] = valid_o ? o : 0.f;
             }
@@ -637,7 +640,7 @@ __device__ __forceinline__ long long* trace_slot(const TcParams& prm, int item, 
 
 // DBG = false is the production kernel: the layer dump and the timeline stamps are compiled out (the kernel is ~9 k
 // instructions; every KB less helps the instruction cache, whose misses show up as stall_no_inst in the epilogues).
-template <int MODE, bool DBG>
+template <int MODE, bool DBG, int ACT = ACT_RELU>
 __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_constant__ TcParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);     // warp-uniform by construction
@@ -760,42 +763,42 @@ __global__ void __launch_bounds__(THREADS, 1) readconv_tc_kernel(const __grid_co
                 if (tr && tid == 0) tr[ph * 8 + 2] = clock64();
                 float* dbg = (DBG && prm.dbg && prm.dbg_phase == ph) ? prm.dbg + (r0 / G) * (T1 * 128 * 64) : nullptr;
                 if (ph == 0) {
-                    epi_conv<MODE, true, 16, T1, P1, LV1, false, false, false, false, OUT_NAT, 0>(
+                    epi_conv<MODE, ACT, true, 16, T1, P1, LV1, false, false, false, false, OUT_NAT, 0>(
                         prm, act, tl, B_L1, 0, n, A1_CH, 2 * A1_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 1) {
-                    epi_conv<MODE, true, 16, T1, P1, LV2, false, false, false, false, OUT_Q4, 0>(
+                    epi_conv<MODE, ACT, true, 16, T1, P1, LV2, false, false, false, false, OUT_Q4, 0>(
                         prm, act, tl, B_L2, 0, n, Q4_ARR, 8 * Q4_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 2) {
-                    epi_pool<MODE>(prm, act, tl, B_L3, n, g, wq, lane, dbg, rr);
+                    epi_pool<MODE, ACT>(prm, act, tl, B_L3, n, g, wq, lane, dbg, rr);
                 } else if (ph < 9) {
                     const int b = B_S2 + (ph - 3) * 32;
                     // space-to-depth rows (two positions per row): same tile shape and operand layout as the 64-channel stage;
                     // the last layer's output is already the (chunk, parity) layout the stride-2 block reads
                     if ((ph - 3) % 2 == 0)
-                        epi_conv<MODE, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1, true>(
+                        epi_conv<MODE, ACT, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1, true>(
                             prm, act, tl, b, 0, n, D2_ARR, 8 * D2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else if (ph < 8)
-                        epi_conv<MODE, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1, true>(
+                        epi_conv<MODE, ACT, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1, true>(
                             prm, act, tl, b, 0, n, D2_ARR, 8 * D2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else
-                        epi_conv<MODE, true, 64, T3, P3, LV4, true, false, false, false, OUT_NAT, 1, true>(
+                        epi_conv<MODE, ACT, true, 64, T3, P3, LV4, true, false, false, false, OUT_NAT, 1, true>(
                             prm, act, tl, b, 0, n, D2_ARR, 8 * D2_ARR, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 9) {
-                    epi_conv<MODE, false, 64, T3, P3, LV4, false, false, false, true, OUT_NAT, 1>(
+                    epi_conv<MODE, ACT, false, 64, T3, P3, LV4, false, false, false, true, OUT_NAT, 1>(
                         prm, act, tl, B_RCA, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else if (ph == 10) {
-                    epi_conv<MODE, true, 64, T3, P3, LV4, true, true, true, false, OUT_NAT, 1>(
+                    epi_conv<MODE, ACT, true, 64, T3, P3, LV4, true, true, true, false, OUT_NAT, 1>(
                         prm, act, tl, B_RCB, B_RCS, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                 } else {
                     const int b = B_S3 + (ph - 11) * 64;
                     if ((ph - 11) % 2 == 0)
-                        epi_conv<MODE, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1>(
+                        epi_conv<MODE, ACT, true, 64, T3, P3, LV4, false, false, false, false, OUT_NAT, 1>(
                             prm, act, tl, b, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else if (ph + 1 < n_ph)
-                        epi_conv<MODE, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1>(
+                        epi_conv<MODE, ACT, true, 64, T3, P3, LV4, true, false, true, false, OUT_NAT, 1>(
                             prm, act, tl, b, 0, n, S3_CH, 8 * S3_CH, nullptr, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                     else {
-                        epi_conv<MODE, true, 64, T3, P3, LV4, true, false, false, false, OUT_GLOBAL, 1>(
+                        epi_conv<MODE, ACT, true, 64, T3, P3, LV4, true, false, false, false, OUT_GLOBAL, 1>(
                             prm, act, tl, b, 0, n, 0, 0, gout, dbg, wrow, lane, rr, tr ? tr + ph * 8 : nullptr);
                         // the next item's bytes travel to registers while this group waits for its turn in the sum
                         if (item + 1 < n_items_cta) fetch_item(item + 1);
@@ -941,6 +944,7 @@ struct ReadConvTC {
     tc::TcParams prm;
     uint8_t* d_weights = nullptr;
     int mode = 3;
+    int act = ACT_RELU;                // the one activation of every convolution in the stack (ReLU or Softplus)
     int sm_count = 148;
 };
 
@@ -954,11 +958,14 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     using namespace tc;
     if (precision != HELLO_PREC_BF16X3 && precision != HELLO_PREC_BF16) { err = "unknown tensor-core precision"; return nullptr; }
     if (feature_length != LIN || channels < 1 || channels > 8) { err = "tensor-core read convolver needs L=150, C<=8"; return nullptr; }
+    // one activation throughout: ReLU, or Softplus (moe_attention_config_single_tech_old_equivalent_layer_norm.py)
+    const int act = net.empty() ? ACT_RELU : net[0].a.relu;
+    if (act != ACT_RELU && act != ACT_SOFTPLUS) { err = "tensor-core read convolver needs ReLU or Softplus"; return nullptr; }
     auto is_conv = [&](const LayerDesc& L, int cin, int cout, int k, int s, int p) {
-        return L.kind == KIND_CONV && L.a.cin == cin && L.a.cout == cout && L.a.k == k && L.a.stride == s && L.a.pad == p && L.a.relu == ACT_RELU;
+        return L.kind == KIND_CONV && L.a.cin == cin && L.a.cout == cout && L.a.k == k && L.a.stride == s && L.a.pad == p && L.a.relu == act;
     };
     auto is_res = [&](const LayerDesc& L, int cin, int cout, int s, bool sc) {
-        return L.kind == KIND_RES && L.a.relu == ACT_RELU && L.b.relu == ACT_RELU &&
+        return L.kind == KIND_RES && L.a.relu == act && L.b.relu == act &&
                L.a.cin == cin && L.a.cout == cout && L.a.k == 3 && L.a.stride == s && L.a.pad == 1 &&
                L.b.cin == cout && L.b.cout == cout && L.b.k == 3 && L.b.stride == 1 && L.b.pad == 1 &&
                (L.has_shortcut != 0) == sc && (!sc || (L.s.cin == cin && L.s.cout == cout && L.s.k == 1 && L.s.stride == s && L.s.pad == 0));
@@ -981,6 +988,7 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     std::vector<float> bias(N_BIAS, 0.f);
     ReadConvTC* t = new ReadConvTC();
     t->mode = precision == HELLO_PREC_BF16X3 ? 3 : 1;
+    t->act = act;
     std::memset(&t->prm, 0, sizeof(t->prm));
 
     // One B unit covers (tap, k16 step j): [2 chunks][rows][8] bf16, rows = the cout "hi" rows followed (bf16x3) by the
@@ -1111,8 +1119,13 @@ static ReadConvTC* readconv_tc_create(const std::vector<LayerDesc>& net, const f
     auto opt_in = [&](const void* fn) {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     };
-    if (t->mode == 3) { opt_in((const void*)readconv_tc_kernel<3, false>); opt_in((const void*)readconv_tc_kernel<3, true>); }
-    else { opt_in((const void*)readconv_tc_kernel<1, false>); opt_in((const void*)readconv_tc_kernel<1, true>); }
+    if (t->mode == 3) {
+        opt_in((const void*)readconv_tc_kernel<3, false>); opt_in((const void*)readconv_tc_kernel<3, true>);
+        opt_in((const void*)readconv_tc_kernel<3, false, ACT_SOFTPLUS>);
+    } else {
+        opt_in((const void*)readconv_tc_kernel<1, false>); opt_in((const void*)readconv_tc_kernel<1, true>);
+        opt_in((const void*)readconv_tc_kernel<1, false, ACT_SOFTPLUS>);
+    }
     if (e != cudaSuccess) {
         err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         cudaFree(t->d_weights); delete t;
@@ -1147,7 +1160,11 @@ static cudaError_t readconv_tc_launch(ReadConvTC* t, const uint8_t* reads, long 
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
     const int grid = (int)std::min<long long>(items, t->sm_count);
     const bool debug = dbg != nullptr;
-    if (t->mode == 3) {
+    if (t->act == ACT_SOFTPLUS) {
+        if (debug) return cudaErrorNotSupported;       // the layer dump (test hook) exists for the ReLU kernels only
+        if (t->mode == 3) tc::readconv_tc_kernel<3, false, ACT_SOFTPLUS><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
+        else tc::readconv_tc_kernel<1, false, ACT_SOFTPLUS><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
+    } else if (t->mode == 3) {
         if (debug) tc::readconv_tc_kernel<3, true><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
         else tc::readconv_tc_kernel<3, false><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(prm);
     } else {
