@@ -488,10 +488,16 @@ struct ConvLayerTC {
     int cps = 2;                           // CTAs per SM asked for (2 wherever a layer's geometry allows it)
 };
 
-static bool convlayer_tc_add(ConvLayerTC* t, const ConvDesc& c, const float* d_base, const float* h_base, std::string& err) {
+// `with_resid`: the layer's launches add a residual.  Two CTAs per SM then need room for the residual ring; without it the
+// rows would be read where they are used, 16 bytes per thread from 32 different rows per instruction, which costs more than
+// the second CTA brings (128 -> 128 channels, 1.39 M rows: 0.85 ms against 0.80 ms with one CTA per SM and its staged rows).
+static bool convlayer_tc_add(ConvLayerTC* t, const ConvDesc& c, const float* d_base, const float* h_base, std::string& err,
+                             bool with_resid = false) {
     if (!cl::eligible(c) || t->layers.count(c.w)) return true;
     cl::PackedConv p;
-    if (!(t->cps == 2 && cl::geometry(c, t->mode, &p.g, 2)) && !cl::geometry(c, t->mode, &p.g, 1)) return true;
+    const bool two = t->cps == 2 && cl::geometry(c, t->mode, &p.g, 2) &&
+                     (!with_resid || cl::smem_bytes(t->mode, p.g) + cl::ring_bytes() <= cl::HALF_SM_SMEM);
+    if (!two && !cl::geometry(c, t->mode, &p.g, 1)) return true;
     const int parts = t->mode == 3 ? 2 : 1;
     const float* w = h_base + (c.w - d_base);                       // [k*cin][cout]
     const int nt = p.g.nt, kc = p.g.kc;

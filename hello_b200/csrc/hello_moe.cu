@@ -681,7 +681,7 @@ int hello_moe_create(const void* blob, size_t nbytes, const hello_cfg* cfg, int 
                 if (L.kind == KIND_CONV) ok_tc = convlayer_tc_add(h->layer_tc, L.a, h->d_weights, h->h_weights.data(), terr);
                 if (L.kind == KIND_RES) {
                     ok_tc = convlayer_tc_add(h->layer_tc, L.a, h->d_weights, h->h_weights.data(), terr) &&
-                            convlayer_tc_add(h->layer_tc, L.b, h->d_weights, h->h_weights.data(), terr) &&
+                            convlayer_tc_add(h->layer_tc, L.b, h->d_weights, h->h_weights.data(), terr, true) &&
                             (!L.has_shortcut || convlayer_tc_add(h->layer_tc, L.s, h->d_weights, h->h_weights.data(), terr));
                 }
                 if (!ok_tc) break;

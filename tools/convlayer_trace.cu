@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < hw.size(); ++i) hw[i] = (float)((i * 2654435761u >> 8) % 2001) / 20000.f - 0.05f;
     float* dw; cudaMalloc(&dw, hw.size() * 4); cudaMemcpy(dw, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice);
     ConvDesc c{cin, cout, k, stride, pad, 1, dw, dw + nw};
-    if (!convlayer_tc_add(t, c, dw, hw.data(), err) || !t->layers.count(dw)) { printf("add: %s (eligible %d)\n", err.c_str(), (int)cl::eligible(c)); return 1; }
+    if (!convlayer_tc_add(t, c, dw, hw.data(), err, with_resid != 0) || !t->layers.count(dw)) { printf("add: %s (eligible %d)\n", err.c_str(), (int)cl::eligible(c)); return 1; }
     const int lout = c.out_len(lin);
     const size_t nx = (size_t)n_items * lin * cin, ny = (size_t)n_items * lout * cout;
     float *dx, *dy, *dr = nullptr;
