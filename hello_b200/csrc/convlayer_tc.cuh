@@ -438,7 +438,7 @@ inline size_t smem_bytes(int mode, const Geometry& g) {
 
 // cps = 2: the layer as two CTAs per SM (half the tensor memory, K chunks of 32 channels, no residual staging), when its
 // accumulator fits 256 columns and the CTA fits half an SM's shared memory
-inline bool geometry(const ConvDesc& c, int mode, Geometry* g, int cps = 1) {
+inline bool geometry(const ConvDesc& c, int mode, Geometry* g, int cps = 1, int kc_cap = 64) {
     if (c.k > MAX_TAPS || c.stride < 1 || c.stride > 2 || c.pad < 0) return false;
     g->cps = cps;
     g->nt = c.cout <= 256 ? c.cout : 256;
@@ -460,7 +460,7 @@ inline bool geometry(const ConvDesc& c, int mode, Geometry* g, int cps = 1) {
         g->tap_delta[t] = s - smin;
         g->n_arr = std::max(g->n_arr, g->tap_arr[t] + 1);
     }
-    g->kc = std::min(c.cin, (cps == 2 ? 32 : 64) / g->n_arr);
+    g->kc = std::min(std::min(c.cin, kc_cap), (cps == 2 ? 32 : 64) / g->n_arr);
     if (c.cin % g->kc || g->kc % 16) return false;
     return cps == 1 || smem_bytes(mode, *g) <= HALF_SM_SMEM;
 }
@@ -491,12 +491,14 @@ struct ConvLayerTC {
 // `with_resid`: the layer's launches add a residual.  Two CTAs per SM then need room for the residual ring; without it the
 // rows would be read where they are used, 16 bytes per thread from 32 different rows per instruction, which costs more than
 // the second CTA brings (128 -> 128 channels, 1.39 M rows: 0.85 ms against 0.80 ms with one CTA per SM and its staged rows).
+// Where the ring does not fit beside K chunks of 32 channels (column tile 128), chunks of 16 make the room: 0.63 ms.
 static bool convlayer_tc_add(ConvLayerTC* t, const ConvDesc& c, const float* d_base, const float* h_base, std::string& err,
                              bool with_resid = false) {
     if (!cl::eligible(c) || t->layers.count(c.w)) return true;
     cl::PackedConv p;
-    const bool two = t->cps == 2 && cl::geometry(c, t->mode, &p.g, 2) &&
-                     (!with_resid || cl::smem_bytes(t->mode, p.g) + cl::ring_bytes() <= cl::HALF_SM_SMEM);
+    auto fits = [&]() { return !with_resid || cl::smem_bytes(t->mode, p.g) + cl::ring_bytes() <= cl::HALF_SM_SMEM; };
+    const bool two = t->cps == 2 && ((cl::geometry(c, t->mode, &p.g, 2) && fits()) ||
+                                     (cl::geometry(c, t->mode, &p.g, 2, 16) && fits()));
     if (!two && !cl::geometry(c, t->mode, &p.g, 1)) return true;
     const int parts = t->mode == 3 ? 2 : 1;
     const float* w = h_base + (c.w - d_base);                       // [k*cin][cout]
