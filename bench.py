@@ -379,16 +379,20 @@ def run_other_workloads(args, dev, skip):
     import torch
     from hello_b200 import _lib, arch, model, weights
     out = {}
-    for name in ("pacbio_hp_30x", "hybrid_no_ensemble_30x", "hybrid_ensemble2_30x", "wgs_ragged_15_60x"):
+    # after BASELINE's configs: the two reference configurations outside them that differ in kernels --
+    # Softplus epilogues on the fused kernels, and the 2x-wide model on the layer-wise kernel (1/8 of the sites: 16x slower)
+    for name in ("pacbio_hp_30x", "hybrid_no_ensemble_30x", "hybrid_ensemble2_30x", "wgs_ragged_15_60x",
+                 "illumina_30x_softplus", "hybrid_no_ensemble_wide_30x"):
         if name == skip:
             continue
+        n_sites = max(1, args.other_sites // 8) if name == "hybrid_no_ensemble_wide_30x" else args.other_sites
         cfg_name, cov, desc = WORKLOADS[name]
         cfg = arch.CONFIGS[cfg_name]
         try:
             params = weights.init_params(cfg, seed=13)
             eng = model.MoEEngine(cfg, params, device=dev, precision=args.precision,
                                   workspace_bytes=int(args.workspace_gb * (1 << 30)))
-            reads, aro, sao, ref = generate_on_device(cfg, cov, args.other_sites, dev, seed=4242)
+            reads, aro, sao, ref = generate_on_device(cfg, cov, n_sites, dev, seed=4242)
             batch = model.DeviceBatch.from_host(reads, _lib.LAYOUT_RLC, aro, sao, ref, dev)
             res = eng.alloc_result(batch)
             eng.run(batch, res)

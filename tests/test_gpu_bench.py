@@ -36,10 +36,12 @@ def test_bench_line_contract():
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     # BASELINE configs 3-5 ride along without touching the headline fields
     ow = d["other_workloads"]
-    assert set(ow) == {"pacbio_hp_30x", "hybrid_no_ensemble_30x", "hybrid_ensemble2_30x", "wgs_ragged_15_60x"}
+    assert set(ow) == {"pacbio_hp_30x", "hybrid_no_ensemble_30x", "hybrid_ensemble2_30x", "wgs_ragged_15_60x",
+                       "illumina_30x_softplus", "hybrid_no_ensemble_wide_30x"}
     for name, w in ow.items():
         assert "error" not in w, (name, w)
-        assert w["sites"] == 2048 and w["sites_per_sec"] > 0 and 0 < w["read_convolver_stage_share"] < 1
+        assert w["sites"] == (256 if name == "hybrid_no_ensemble_wide_30x" else 2048)       # the wide model: 1/8 of the sites
+        assert w["sites_per_sec"] > 0 and 0 < w["read_convolver_stage_share"] < 1
         assert w["max_abs_dlogit_vs_oracle"] < 1e-3 and w["oracle_sample_sites"] == 32
 
 
