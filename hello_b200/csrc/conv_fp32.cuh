@@ -191,6 +191,56 @@ __global__ void __launch_bounds__(256) conv1d_fp32_kernel(const ConvArgs a) {
     }
 }
 
+// First convolution of a layer-by-layer model: uint8 pileup rows [item][L][CIN] in, k = 3, stride 1, no padding, so the
+// K = 3 * CIN bytes an output needs (18 for six-channel rows) are contiguous in memory.  The implicit-GEMM kernel above pads
+// K to two slabs of 16 and spends its time on shared-memory round trips for 18 products; here a thread owns four output
+// channels of STEM_ROWS rows, reads its bytes at constant offsets straight from L1 (the lanes of a row read the same
+// bytes) and each weight row from shared memory once for all its rows, and a warp store covers whole consecutive output
+// rows.  Products are accumulated with fmaf in the same order as conv1d_fp32_kernel (k = tap * cin + ci ascending from
+// zero), so the two kernels are bit-identical.
+constexpr int STEM_ROWS = 4;
+
+template <int COUT, int CIN>
+__global__ void __launch_bounds__(256) conv_stem_u8_kernel(const ConvArgs a) {
+    constexpr int K = 3 * CIN;
+    constexpr int LPR = COUT / 4;                    // lanes per output row
+    constexpr int RPW = 32 / LPR;                    // rows per warp store
+    __shared__ __align__(16) float w_s[K * COUT];
+    for (int i = threadIdx.x; i < K * COUT; i += 256) w_s[i] = __ldg(a.w + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c4 = (lane % LPR) * 4, rw = lane / LPR;
+    const long long m0 = (long long)blockIdx.x * (8 * STEM_ROWS * RPW) + (long long)warp * (STEM_ROWS * RPW) + rw;
+    float4 acc[STEM_ROWS];
+    const uint8_t* src[STEM_ROWS];
+#pragma unroll
+    for (int r = 0; r < STEM_ROWS; ++r) {
+        const long long m = min(m0 + r * RPW, a.M - 1);                        // rows past the end recompute the last one
+        const long long item = m / a.lout;
+        src[r] = reinterpret_cast<const uint8_t*>(a.x) + item * a.sn + (m - item * a.lout) * CIN;
+        acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float4 w = *reinterpret_cast<const float4*>(&w_s[k * COUT + c4]);
+#pragma unroll
+        for (int r = 0; r < STEM_ROWS; ++r) {
+            const float v = (float)__ldg(src[r] + k);
+            acc[r].x = fmaf(v, w.x, acc[r].x); acc[r].y = fmaf(v, w.y, acc[r].y);
+            acc[r].z = fmaf(v, w.z, acc[r].z); acc[r].w = fmaf(v, w.w, acc[r].w);
+        }
+    }
+    const float4 bias = __ldg(reinterpret_cast<const float4*>(a.bias + c4));
+#pragma unroll
+    for (int r = 0; r < STEM_ROWS; ++r) {
+        const long long m = m0 + r * RPW;
+        if (m >= a.M) continue;
+        float4 o = make_float4(apply_activation(acc[r].x + bias.x, a.relu), apply_activation(acc[r].y + bias.y, a.relu),
+                               apply_activation(acc[r].z + bias.z, a.relu), apply_activation(acc[r].w + bias.w, a.relu));
+        *reinterpret_cast<float4*>(a.y + m * COUT + c4) = o;
+    }
+}
+
 template <int BN, int TM, int TN>
 static cudaError_t launch_conv_bn(const ConvArgs& a, bool is_u8, bool vec, cudaStream_t st) {
     dim3 grid((unsigned)((a.M + 127) / 128), (unsigned)(a.cout / BN));
@@ -214,6 +264,16 @@ static cudaError_t launch_conv(const ActView& x, const ConvDesc& c, long long n_
     a.lout = c.out_len(x.len);
     a.M = n_items * a.lout;
     a.cout = c.cout; a.ksz = c.k; a.stride = c.stride; a.pad = c.pad; a.relu = c.relu; a.K = c.k * c.cin;
+    if (x.is_u8 && !resid && c.k == 3 && c.stride == 1 && c.pad == 0 && x.sc == 1 && x.sl == c.cin && (c.cin == 6 || c.cin == 7) &&
+        (c.cout == 16 || c.cout == 32) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(c.b)) & 15) == 0) {
+        const int rows_per_block = 8 * STEM_ROWS * (c.cout == 16 ? 8 : 4);
+        const unsigned grid = (unsigned)((a.M + rows_per_block - 1) / rows_per_block);
+        if (c.cout == 16 && c.cin == 6) conv_stem_u8_kernel<16, 6><<<grid, 256, 0, st>>>(a);
+        else if (c.cout == 16) conv_stem_u8_kernel<16, 7><<<grid, 256, 0, st>>>(a);
+        else if (c.cin == 6) conv_stem_u8_kernel<32, 6><<<grid, 256, 0, st>>>(a);
+        else conv_stem_u8_kernel<32, 7><<<grid, 256, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     const bool vec = !x.is_u8 && x.sc == 1 && (c.cin % 16 == 0) && (x.sl % 4 == 0) && (x.sn % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(x.base) & 15) == 0);
     if (c.cout % 128 == 0) return launch_conv_bn<128, 8, 8>(a, x.is_u8, vec, st);
