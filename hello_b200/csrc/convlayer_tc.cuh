@@ -95,7 +95,7 @@ __device__ __forceinline__ void ldgsts_wait_but_one() { asm volatile("cp.async.w
 constexpr uint32_t RING_PITCH = 2 * 64 + 16;              // residual ring of one row: two 16-column slots, 16-byte skew per row
 
 // CPS = CTAs per SM.  2: half of tensor memory (256 columns, accumulators 128 columns apart), at most half of the shared
-// memory (the residual is read straight from HBM instead of through a staging tile) and 72 registers, so that two CTAs
+// memory (the residual comes through a small ring instead of a staging tile) and 72 registers, so that two CTAs
 // share an SM: every warp role here is a few warps running dependent chains, and a second independent pipeline on the SM
 // fills the issue slots, the tensor pipe and the memory pipes the first one leaves idle.
 template <int MODE, int CPS>
@@ -436,8 +436,9 @@ inline size_t smem_bytes(int mode, const Geometry& g) {
            (2 * A_SLOTS + 2 * B_STAGES + 4 + E_WARPS * 32) * 8 + 16;
 }
 
-// cps = 2: the layer as two CTAs per SM (half the tensor memory, K chunks of 32 channels, no residual staging), when its
-// accumulator fits 256 columns and the CTA fits half an SM's shared memory
+// cps = 2: the layer as two CTAs per SM (half the tensor memory, K chunks of at most 32 channels -- kc_cap = 16 where the
+// residual ring needs the room --, no residual staging tile), when its accumulator fits 256 columns and the CTA fits half
+// an SM's shared memory
 inline bool geometry(const ConvDesc& c, int mode, Geometry* g, int cps = 1, int kc_cap = 64) {
     if (c.k > MAX_TAPS || c.stride < 1 || c.stride > 2 || c.pad < 0) return false;
     g->cps = cps;
