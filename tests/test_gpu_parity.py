@@ -62,6 +62,8 @@ def test_read_convolver_per_read(gpu, name):
     got_rcl = net.engine.run_net("read_convolver0", pl.reads[0].transpose(1, 2).contiguous(), _lib.LAYOUT_RCL).cpu()
     ref = oracle_for(cfg).read_features(pl.reads[0].transpose(1, 2))            # [R, 64, 36]
     assert got_rlc.shape == (pl.reads[0].shape[0], 36, 64)
+    # (row-major rows take the first convolution through conv_stem_u8_kernel, channel-major ones through conv1d_fp32_kernel:
+    # the two accumulate in the same order and must agree bit for bit)
     assert torch.equal(got_rlc, got_rcl), "the two input layouts must give identical results"
     err = (got_rlc.transpose(1, 2) - ref).abs().max().item()
     assert err < 2e-3 * max(1.0, ref.abs().max().item() / 100), err
